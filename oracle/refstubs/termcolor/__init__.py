@@ -1,0 +1,6 @@
+def colored(text, *a, **k):
+    return text
+
+
+def cprint(text, *a, **k):
+    print(text)
