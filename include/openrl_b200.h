@@ -73,13 +73,181 @@ int orl_device_sm_count(int* sm_count_out);
 #define ORL_GS_COUNT 2        /* T*B                                              */
 #define ORL_GS_ADV_ACT_SUM 3  /* sum adv   where active_masks[t] != 0             */
 #define ORL_GS_ADV_ACT_SQSUM 4
-#define ORL_GS_ACT_COUNT 5    /* number of active elements                        */
-#define ORL_GS_RET_SUM 6      /* sum returns[t<T]                                 */
-#define ORL_GS_RET_SQSUM 7    /* sum returns[t<T]^2                               */
+#define ORL_GS_RET_SUM 5      /* sum returns[t<T]       } {5,6,7} is the mb_stats triple  */
+#define ORL_GS_RET_SQSUM 6    /* sum returns[t<T]^2     } of orl_ppo_* for a minibatch    */
+#define ORL_GS_ACT_COUNT 7    /* number of active elements } covering the whole buffer    */
 int orl_gae(const float* rewards, float* value_preds, const float* masks,
             const float* bad_masks, const float* active_masks, const float* next_value,
             const float* vn_state, float* returns, float* advantages, double* stats,
             int T, int B, double gamma, double gae_lambda, int flags, void* stream);
+
+
+/* ---- device-resident vectorised envs -------------------------------------------------
+ * Replace SyncVectorEnv/AsyncVectorEnv stepping (openrl/envs/vec_env/sync_venv.py:129-247,
+ * async_venv.py:316-430,731-875) + the per-env wrappers Single2MultiAgentWrapper /
+ * RemoveTruncated (openrl/envs/wrappers/multiagent_wrapper.py:33-79,
+ * extra_wrappers.py:122-134) for the simple gym-class envs.  State lives in caller-owned
+ * device arrays (SoA over envs):
+ *   CARTPOLE : env_f64 [4][N] (x, x_dot, theta, theta_dot) float64 like gymnasium;
+ *              env_i32 [1][N] elapsed steps (TimeLimit 500);
+ *              env_u64 [4][N] numpy-PCG64 {state_hi, state_lo, inc_hi, inc_lo} of the env's
+ *              np_random (seeded seed + i*10086 by the host, sync_venv.py:137).
+ *   GRIDWORLD: env_i32 [4][N] (x, y, steps, resets); env_table optional int32
+ *              [N][env_table_len][2] start cells for parity runs; else Philox(rng_seed).
+ *   NONE     : no device env (host env.step, e.g. MuJoCo): orl_rollout only acts.
+ */
+#define ORL_ENV_NONE 0
+#define ORL_ENV_CARTPOLE 1
+#define ORL_ENV_GRIDWORLD 2
+#define ORL_ENV_MPE_SPREAD 3
+
+/* Draw initial states (env.reset()) and write the observations of slot `obs_out` (B, d).
+ * Mirrors SyncVectorEnv._reset (sync_venv.py:129-169).  RNG streams must already be seeded. */
+int orl_env_reset(int env_kind, int n_envs, int n_agents, double* env_f64, uint64_t* env_u64,
+                  int32_t* env_i32, const int32_t* env_table, int env_table_len,
+                  uint64_t rng_seed, float* policy_obs_out, float* critic_obs_out, void* stream);
+
+/* One vectorised env.step outside the fused rollout (the BaseVecEnv.step duck type used by
+ * evaluation loops): actions (B) float -> obs (B,d), rewards (B), dones (B) as 0/1 floats and,
+ * optionally, the pre-reset terminal observation (info["final_observation"], sync_venv.py:213-218). */
+int orl_env_step(int env_kind, int n_envs, int n_agents, double* env_f64, uint64_t* env_u64,
+                 int32_t* env_i32, const int32_t* env_table, int env_table_len, uint64_t rng_seed,
+                 float* ep_return, int32_t* ep_length, double* episode_stats, const float* actions,
+                 float* obs_out, float* rewards_out, float* dones_out, float* final_obs_out,
+                 void* stream);
+
+/* ---- fused rollout: policy forward + sampling + env.step + buffer insert -----------------
+ * Replaces the body of OnPolicyDriver.actor_rollout for steps [t_begin, t_end)
+ * (openrl/drivers/onpolicy_driver.py:154-203): act() :236-279 (policy half:
+ * PolicyNetwork.forward_original policy_network.py:130-162, MLPBase mlp.py:160-176,
+ * Categorical distributions.py:58-72, sampling = torch.multinomial == argmax(probs/q)),
+ * envs.step() (see above), add2buffer() :80-152 and ReplayData.insert
+ * (openrl/buffers/replay_data.py:245-284).  Envs are independent, so one launch can cover all
+ * T steps (t_begin = 0, t_end = T); per-step launches (t_end = t_begin + 1) serve callbacks.
+ * Critic values are produced separately by orl_critic_values (they do not influence the
+ * trajectory).
+ *
+ * Sampling: exp_noise != NULL ("parity mode") supplies q ~ Exp(1) of shape (T, B, n) drawn by
+ * the host with torch's CPU generator in the reference's order; NULL uses Philox4x32-10 keyed
+ * by rng_seed with counter (rng_step_base + *rng_counter + t, row).  deterministic != 0 takes the mode.
+ */
+typedef struct OrlRolloutArgs {
+    int32_t env_kind;       /* ORL_ENV_* */
+    int32_t n_envs;         /* N */
+    int32_t n_agents;       /* A; rows B = N*A */
+    int32_t episode_length; /* T: depth of the (T[+1], B, .) buffers */
+    int32_t t_begin, t_end; /* steps to run, 0 <= t_begin < t_end <= T */
+    int32_t obs_dim;        /* d, policy observation width (<= 64) */
+    int32_t critic_obs_dim; /* 0: critic obs == policy obs (critic_obs may be NULL) */
+    int32_t n_actions;      /* n <= 8, Discrete(n) */
+    int32_t activation_id;  /* cfg.activation_id: 0 tanh, 1 relu, 2 leaky_relu, 3 elu */
+    int32_t deterministic;
+    int32_t env_table_len;
+    const float* policy_params; /* flat net parameters, layout in orl_mlp.cuh / DESIGN.md */
+    float* policy_obs;          /* (T+1, B, d)   slot t read at t_begin, slots t+1 written */
+    float* critic_obs;          /* (T+1, B, dc)  or NULL */
+    float* actions;             /* (T, B, 1)  sampled index stored as float32 (replay_data.py:163-166) */
+    float* action_log_probs;    /* (T, B, 1) */
+    float* rewards;             /* (T, B, 1) */
+    float* masks;               /* (T+1, B, 1) */
+    float* active_masks;        /* (T+1, B, 1) */
+    const float* action_masks;  /* (T+1, B, n) or NULL (all actions available) */
+    const float* exp_noise;     /* (T, B, n) or NULL */
+    uint64_t rng_seed;
+    uint64_t rng_step_base;     /* Philox counter of step t is rng_step_base + *rng_counter + t */
+    uint64_t* rng_counter;      /* (1) device counter or NULL; += (t_end - t_begin) after the launch,
+                                   so a captured CUDA graph draws fresh noise on every replay */
+    double* env_f64;
+    uint64_t* env_u64;
+    int32_t* env_i32;
+    const int32_t* env_table;
+    float* ep_return;           /* (N) running episode return  (VecMonitor-style statistics) */
+    int32_t* ep_length;         /* (N) running episode length */
+    double* episode_stats;      /* (4) += {sum return, sum length, #episodes, 0} of finished episodes */
+} OrlRolloutArgs;
+int orl_rollout(const OrlRolloutArgs* args, void* stream);
+
+/* ---- critic forward over a flat batch of rows ------------------------------------------
+ * Replaces the critic half of act() (ValueNetwork.forward, value_network.py:113-136) for all
+ * T+1 slots at once and the bootstrap forward of OnPolicyDriver.compute_returns
+ * (onpolicy_driver.py:206-215).  obs (rows, d) -> values (rows). */
+int orl_critic_values(const float* critic_params, int obs_dim, int activation_id,
+                      const float* obs, float* values, long long rows, void* stream);
+
+
+/* ---- PPO minibatch update ---------------------------------------------------------------
+ * Replaces PPOAlgorithm.ppo_update (openrl/algorithms/ppo.py:46-176): prepare_loss :238-361
+ * (evaluate_actions -> PolicyNetwork.eval_actions policy_network.py:164-203 / ValueNetwork.forward
+ * value_network.py:113-136, ratio + clipped surrogate :300-319, cal_value_loss :178-220 incl.
+ * ValueNorm.update/normalize valuenorm.py:59-90, entropy act.py:160-168, construct_loss_list
+ * :226-236), loss.backward(), clip_grad_norm_ (:139-150) and Adam.step (rl_module.py:80-87), and
+ * the minibatch gather of ReplayData.feed_forward_generator (replay_data.py:553-646).
+ *
+ * Three launches per update, all asynchronous, no host round trip:
+ *   orl_ppo_fwdbwd : fused gather + forward + loss + backward over the minibatch rows; every CTA
+ *                    writes its partial FOLDED gradients and loss sums to `partials`.
+ *   orl_ppo_reduce : deterministic reduction of the partials over CTAs -> `folded` (2*stride
+ *                    floats: policy net then critic net).  With >1 GPU the caller all-reduces
+ *                    (SUM) `folded` here — the single NCCL all-reduce per update.
+ *   orl_ppo_apply  : unfold to true gradients, per-net global-norm clip, Adam, ValueNorm commit,
+ *                    train_info accumulation.
+ * flags: */
+#define ORL_PPO_HUBER 1               /* cfg.use_huber_loss */
+#define ORL_PPO_CLIP_VALUE 2          /* cfg.use_clipped_value_loss */
+#define ORL_PPO_VALUE_ACTIVE_MASKS 4  /* cfg.use_value_active_masks */
+#define ORL_PPO_POLICY_ACTIVE_MASKS 8 /* cfg.use_policy_active_masks */
+#define ORL_PPO_VALUENORM 16          /* cfg.use_valuenorm (normaliser present) */
+#define ORL_PPO_ADV_NORMALIZE 32      /* cfg.use_adv_normalize (ppo.py:402-403) */
+#define ORL_PPO_MAX_GRAD_NORM 64      /* cfg.use_max_grad_norm */
+
+typedef struct OrlPpoArgs {
+    int32_t obs_dim;         /* d  policy obs width  (<= 64) */
+    int32_t critic_obs_dim;  /* dc critic obs width  (<= 64) */
+    int32_t n_actions;       /* n <= 8 */
+    int32_t activation_id;
+    int32_t flags;           /* ORL_PPO_* */
+    int32_t grid_per_net;    /* CTAs per net in orl_ppo_fwdbwd (partials has 2*grid_per_net rows) */
+    int64_t batch_rows;      /* rows of this minibatch */
+    int64_t row_begin;       /* used when indices == NULL: rows [row_begin, row_begin+batch_rows) */
+    int64_t total_rows;      /* T*B, rows of the flattened buffers (bounds) */
+    const int64_t* indices;  /* (batch_rows) flat row ids (torch.randperm slice) or NULL */
+    /* rollout data flattened to (T*B, .) */
+    const float* policy_obs;     /* (T*B, d)  */
+    const float* critic_obs;     /* (T*B, dc) */
+    const float* actions;        /* (T*B)     */
+    const float* old_log_probs;  /* (T*B)     */
+    const float* advantages;     /* (T*B) raw, normalised on the fly from gae_stats */
+    const float* value_preds;    /* (T*B)     */
+    const float* returns;        /* (T*B)     */
+    const float* active_masks;   /* (T*B)     */
+    const float* action_masks;   /* (T*B, n) or NULL */
+    const double* gae_stats;     /* (ORL_GAE_NSTATS) global moments of the raw advantages */
+    const double* mb_stats;      /* (3) {sum returns, sum returns^2, sum active} over this minibatch */
+    float* vn_state;             /* (3) ValueNorm state BEFORE this update; orl_ppo_apply commits the update */
+    float* policy_params;        /* flat, updated in place by orl_ppo_apply */
+    float* critic_params;
+    float* policy_adam_m; float* policy_adam_v;   /* Adam moments, same layout as params */
+    float* critic_adam_m; float* critic_adam_v;
+    int32_t* adam_steps;         /* (2) step counters {policy, critic}, incremented by apply */
+    const float* lrs;            /* (2) {lr, critic_lr} (device so that CUDA graphs can be replayed) */
+    float clip_param, entropy_coef, value_loss_coef, huber_delta, max_grad_norm;
+    float adam_beta1, adam_beta2, adam_eps, weight_decay, vn_beta;
+    float* partials;             /* (2*grid_per_net, stride) scratch */
+    float* folded;               /* (2, stride): reduced folded gradients + loss sums */
+    float* grads;                /* (2, stride): true gradients (written by apply; for inspection) */
+    float* train_info;           /* (6) += {value_loss, critic_grad_norm, policy_loss, dist_entropy,
+                                             actor_grad_norm, ratio}  (ppo.py:430-451) */
+} OrlPpoArgs;
+/* floats per partial row for given shapes (>= folded gradient size + 8 loss slots, multiple of 4) */
+int orl_ppo_stride(int obs_dim, int critic_obs_dim, int n_actions);
+/* number of parameters of one MLP net with head width n (layout in DESIGN.md) */
+int orl_net_param_count(int obs_dim, int n_out);
+int orl_ppo_fwdbwd(const OrlPpoArgs* args, void* stream);
+int orl_ppo_reduce(const OrlPpoArgs* args, void* stream);
+int orl_ppo_apply(const OrlPpoArgs* args, void* stream);
+/* {sum returns, sum returns^2, sum active} over a minibatch given by `indices` (see mb_stats). */
+int orl_minibatch_stats(const int64_t* indices, int64_t batch_rows, const float* returns,
+                        const float* active_masks, double* mb_stats_out, void* stream);
 
 #ifdef __cplusplus
 }

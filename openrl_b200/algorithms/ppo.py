@@ -1,0 +1,141 @@
+"""PPOAlgorithm(cfg, init_module, agent_num, device).train(buffer_data) -> dict
+(reference: openrl/algorithms/ppo.py:32-469, base_algorithm.py:24-86).
+
+`train` runs `ppo_epoch x num_mini_batch` updates, each three asynchronous CUDA launches
+(orl_ppo_fwdbwd / orl_ppo_reduce / orl_ppo_apply) plus, with >1 GPU, ONE all-reduce of the
+folded gradient bucket.  Nothing is read back until the metrics are logged.
+
+Minibatch order: the reference draws one `torch.randperm(T*N*A)` per epoch from the global CPU
+generator (replay_data.py:578-580).  cfg.parity_mode=True reproduces exactly that (host draw,
+H2D copy); otherwise the permutation is drawn on the device, and with num_mini_batch == 1 no
+permutation is needed at all (a minibatch that is the whole buffer is a sum over all rows).
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .. import lib
+
+
+class PPOAlgorithm:
+    def __init__(self, cfg, init_module, agent_num=1, device="cuda:0"):
+        self.cfg = cfg
+        self.algo_module = init_module
+        self.agent_num = agent_num
+        self.device = torch.device(device) if not isinstance(device, torch.device) else device
+        self.world_size = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.ppo_epoch, self.num_mini_batch = cfg.ppo_epoch, cfg.num_mini_batch
+        self.clip_param = cfg.clip_param
+        self._lib = lib.load()
+        pol, cri = init_module.models["policy"], init_module.models["critic"]
+        self.d, self.dc, self.n = pol.obs_dim, cri.obs_dim, pol.n_actions
+        self.stride = self._lib.orl_ppo_stride(self.d, self.dc, self.n)
+        sm = torch.cuda.get_device_properties(self.device).multi_processor_count
+        self.grid_per_net = max(1, sm // 2)
+        dev = self.device
+        self.partials = torch.zeros(2 * self.grid_per_net, self.stride, dtype=torch.float32, device=dev)
+        self.folded = torch.zeros(2, self.stride, dtype=torch.float32, device=dev)
+        self.grads = torch.zeros(2, self.stride, dtype=torch.float32, device=dev)
+        self.train_info = torch.zeros(6, dtype=torch.float32, device=dev)
+        self.lrs = torch.zeros(2, dtype=torch.float32, device=dev)
+        self.mb_stats = torch.zeros(3, dtype=torch.float64, device=dev)
+        self.flags = ((lib.PPO_HUBER if cfg.use_huber_loss else 0) | (lib.PPO_CLIP_VALUE if cfg.use_clipped_value_loss else 0)
+                      | (lib.PPO_VALUE_ACTIVE_MASKS if cfg.use_value_active_masks else 0)
+                      | (lib.PPO_POLICY_ACTIVE_MASKS if cfg.use_policy_active_masks else 0)
+                      | (lib.PPO_VALUENORM if (cfg.use_valuenorm and cri.value_normalizer is not None) else 0)
+                      | (lib.PPO_ADV_NORMALIZE if cfg.use_adv_normalize else 0)
+                      | (lib.PPO_MAX_GRAD_NORM if cfg.use_max_grad_norm else 0))
+        for name in ("use_joint_action_loss", "dual_clip_ppo", "use_policy_vhead", "use_share_model", "use_popart",
+                     "use_amp", "use_deepspeed", "use_naive_recurrent_policy", "use_recurrent_policy"):
+            if getattr(cfg, name, False):
+                raise NotImplementedError(f"cfg.{name} is not built into the CUDA update yet (SURVEY.md §8f)")
+        self.gpu_launches = 0
+
+    def prep_rollout(self):
+        pass
+
+    def prep_training(self):
+        pass
+
+    def _args(self, buf, batch_rows, indices, row_begin):
+        m = self.algo_module
+        pol, cri = m.models["policy"], m.models["critic"]
+        op, oc = m.optimizers["policy"], m.optimizers["critic"]
+        cfg = self.cfg
+        a = lib.OrlPpoArgs()
+        a.obs_dim, a.critic_obs_dim, a.n_actions, a.activation_id = self.d, self.dc, self.n, pol.activation_id
+        a.flags, a.grid_per_net = self.flags, self.grid_per_net
+        total = buf.episode_length * buf.n_rollout_threads * buf.num_agents
+        a.batch_rows, a.row_begin, a.total_rows = int(batch_rows), int(row_begin), int(total)
+        a.indices = lib.ptr(indices)
+        a.policy_obs, a.critic_obs = lib.ptr(buf.policy_obs), lib.ptr(buf.critic_obs)
+        a.actions, a.old_log_probs = lib.ptr(buf.actions), lib.ptr(buf.action_log_probs)
+        a.advantages, a.value_preds, a.returns = lib.ptr(buf.advantages), lib.ptr(buf.value_preds), lib.ptr(buf.returns)
+        a.active_masks = lib.ptr(buf.active_masks)
+        a.action_masks = None if buf.action_masks_trivial else lib.ptr(buf.action_masks)
+        a.gae_stats = lib.ptr(buf.gae_stats)
+        vn = cri.value_normalizer
+        a.vn_state = None if vn is None else lib.ptr(vn.state)
+        a.policy_params, a.critic_params = lib.ptr(pol.flat_params), lib.ptr(cri.flat_params)
+        a.policy_adam_m, a.policy_adam_v = lib.ptr(op.exp_avg), lib.ptr(op.exp_avg_sq)
+        a.critic_adam_m, a.critic_adam_v = lib.ptr(oc.exp_avg), lib.ptr(oc.exp_avg_sq)
+        a.adam_steps, a.lrs = lib.ptr(m.adam_steps), lib.ptr(self.lrs)
+        a.clip_param, a.entropy_coef, a.value_loss_coef = cfg.clip_param, cfg.entropy_coef, cfg.value_loss_coef
+        a.huber_delta, a.max_grad_norm = cfg.huber_delta, cfg.max_grad_norm
+        g = op.param_groups[0]
+        a.adam_beta1, a.adam_beta2, a.adam_eps, a.weight_decay = g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"]
+        a.vn_beta = 0.99999 if vn is None else vn.beta
+        a.partials, a.folded, a.grads, a.train_info = (lib.ptr(self.partials), lib.ptr(self.folded),
+                                                        lib.ptr(self.grads), lib.ptr(self.train_info))
+        return a
+
+    def ppo_update(self, buf, batch_rows, indices=None, row_begin=0, mb_stats=None):
+        """One minibatch update (ppo.py:46-176) — asynchronous."""
+        L, s = self._lib, lib.current_stream()
+        if mb_stats is None:
+            lib.check(L.orl_minibatch_stats(lib.ptr(indices), int(batch_rows), lib.ptr(buf.returns),
+                                            lib.ptr(buf.active_masks), lib.ptr(self.mb_stats), s), "orl_minibatch_stats")
+            mb_stats = self.mb_stats
+            self.gpu_launches += 1
+            if self.world_size > 1:
+                dist.all_reduce(mb_stats)
+        a = self._args(buf, batch_rows, indices, row_begin)
+        a.mb_stats = lib.ptr(mb_stats)
+        lib.check(L.orl_ppo_fwdbwd(a, s), "orl_ppo_fwdbwd")
+        lib.check(L.orl_ppo_reduce(a, s), "orl_ppo_reduce")
+        if self.world_size > 1:
+            dist.all_reduce(self.folded)  # the single gradient-bucket all-reduce of the update
+        lib.check(L.orl_ppo_apply(a, s), "orl_ppo_apply")
+        self.gpu_launches += 3
+
+    def train(self, buffer, turn_on=True):
+        """train_ppo (ppo.py:383-458).  `buffer` is the device ReplayData whose returns/advantages
+        were produced by `compute_returns` (orl_gae)."""
+        buf = buffer
+        m = self.algo_module
+        self.lrs.copy_(torch.tensor([m.optimizers["policy"].param_groups[0]["lr"],
+                                     m.optimizers["critic"].param_groups[0]["lr"]], dtype=torch.float32),
+                       non_blocking=True)
+        self.train_info.zero_()
+        if self.world_size > 1:
+            dist.all_reduce(buf.gae_stats)  # global advantage / return moments (ppo.py:402-409 semantics)
+        total = buf.episode_length * buf.n_rollout_threads * buf.num_agents
+        mb = total // self.num_mini_batch
+        whole = self.num_mini_batch == 1
+        for _ in range(self.ppo_epoch):
+            if self.cfg.parity_mode:
+                perm = torch.randperm(total).to(self.device, non_blocking=True)  # global CPU generator, like the reference
+            elif whole:
+                perm = None
+            else:
+                perm = torch.randperm(total, device=self.device)
+            for i in range(self.num_mini_batch):
+                if whole:
+                    # {sum ret, sum ret^2, sum active} over the whole buffer == gae_stats[5:8]
+                    self.ppo_update(buf, mb, perm, 0, mb_stats=buf.gae_stats[5:8])
+                else:
+                    self.ppo_update(buf, mb, perm[i * mb:(i + 1) * mb])
+        num_updates = self.ppo_epoch * self.num_mini_batch
+        info = (self.train_info / num_updates).cpu().numpy()
+        keys = ["value_loss", "critic_grad_norm", "policy_loss", "dist_entropy", "actor_grad_norm", "ratio"]
+        return {k: float(v) for k, v in zip(keys, info)}

@@ -1,0 +1,363 @@
+// Fused rollout kernel: policy MLP forward + categorical sampling + device env.step + in-place
+// buffer insert, for steps [t_begin, t_end) of one rollout, plus env reset and the batched critic
+// forward.  See include/openrl_b200.h for the reference functions this replaces.
+//
+// Mapping: a CTA of 128 threads owns ROWS = 32 consecutive rows (env, agent) for the whole step
+// range — envs never interact, so there is no grid-wide dependency and ONE launch covers all T
+// steps; the policy weights (folded, 37 KB) stay resident in shared memory.  Per step the trunk is
+// two register-tiled tile GEMMs (32x64xd, 32x64x64; see orl_mlp.cuh), then 4 lanes per row compute
+// the logits, one lane samples and steps the env, writing slot t / t+1 of the buffers directly.
+// The step chain is latency-bound (T sequential steps); the grid is N*A/32 CTAs.
+#include "orl_envs.cuh"
+#include "orl_mlp.cuh"
+
+namespace {
+using namespace orl;
+
+constexpr int R_M = 32;    // rows per CTA
+constexpr int R_NT = 128;  // threads per CTA
+
+
+struct EnvPtrs {
+    double* f64; uint64_t* u64; int32_t* i32; const int32_t* table; int table_len; uint64_t seed;
+    float* ep_return; int32_t* ep_length; double* episode_stats;
+};
+
+// One env.step of a single-agent, 4-wide-observation env (CartPole-v1 / GridWorldEnv) with the
+// reference's auto-reset (sync_venv.py:213-218): on done the returned obs is the reset obs and the
+// terminal obs goes to `fin` (info["final_observation"]).
+__device__ __forceinline__ void env_step_single(const EnvPtrs& E, int kind, int e, int N, int act, float (&ob)[4],
+                                                float& reward, bool& done, float (&fin)[4]) {
+    if (kind == ORL_ENV_CARTPOLE) {
+        double s[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s[k] = E.f64[(size_t)k * N + e];
+        int elapsed = E.i32[e];
+        const bool terminated = cartpole_dynamics(s, act);
+        elapsed += 1;
+        done = terminated || (elapsed >= 500);
+        reward = 1.0f;
+        float ret = E.ep_return[e] + 1.0f;
+        int len = E.ep_length[e] + 1;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) fin[k] = (float)s[k];
+        if (done) {
+            Pcg64 g = pcg_load(E.u64, e, N);
+            cartpole_reset(s, g);
+            pcg_store(E.u64, e, N, g);
+            elapsed = 0;
+            atomicAdd(E.episode_stats + 0, (double)ret);
+            atomicAdd(E.episode_stats + 1, (double)len);
+            atomicAdd(E.episode_stats + 2, 1.0);
+            ret = 0.f; len = 0;
+        }
+        E.ep_return[e] = ret; E.ep_length[e] = len;
+        E.i32[e] = elapsed;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { E.f64[(size_t)k * N + e] = s[k]; ob[k] = (float)s[k]; }
+    } else {  // ORL_ENV_GRIDWORLD
+        int x = E.i32[0 * N + e], y = E.i32[1 * N + e], steps = E.i32[2 * N + e];
+        int nreset = E.i32[3 * N + e];
+        const int nrow = 10, ncol = 10;
+        if (act == 1) x -= 1; else if (act == 2) x += 1; else if (act == 3) y -= 1; else if (act == 4) y += 1;
+        x = min(max(x, 0), nrow - 1); y = min(max(y, 0), ncol - 1);
+        done = false;
+        if (x == 1 && y == 1) { reward = 10.f; done = true; } else reward = -1.f;
+        if (steps == 100) { done = true; reward -= 10.f; } else steps += 1;  // gridworld_env.py:68-72
+        float ret = E.ep_return[e] + reward;
+        int len = E.ep_length[e] + 1;
+        fin[0] = (float)x; fin[1] = (float)y; fin[2] = 1.f; fin[3] = 1.f;
+        if (done) {
+            gridworld_reset(x, y, e, nreset, E.seed, E.table, E.table_len, nrow, ncol);
+            nreset += 1; steps = 0;
+            atomicAdd(E.episode_stats + 0, (double)ret);
+            atomicAdd(E.episode_stats + 1, (double)len);
+            atomicAdd(E.episode_stats + 2, 1.0);
+            ret = 0.f; len = 0;
+        }
+        E.ep_return[e] = ret; E.ep_length[e] = len;
+        E.i32[0 * N + e] = x; E.i32[1 * N + e] = y; E.i32[2 * N + e] = steps; E.i32[3 * N + e] = nreset;
+        ob[0] = (float)x; ob[1] = (float)y; ob[2] = 1.f; ob[3] = 1.f;
+    }
+}
+
+__global__ void env_step_kernel(int kind, int N, EnvPtrs E, const float* __restrict__ actions, float* __restrict__ obs_out,
+                                float* __restrict__ rewards_out, float* __restrict__ dones_out, float* __restrict__ final_obs_out) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= N) return;
+    float ob[4], fin[4], reward; bool done;
+    env_step_single(E, kind, e, N, (int)actions[e], ob, reward, done, fin);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        obs_out[(size_t)e * 4 + k] = ob[k];
+        if (final_obs_out) final_obs_out[(size_t)e * 4 + k] = fin[k];
+    }
+    rewards_out[e] = reward;
+    dones_out[e] = done ? 1.f : 0.f;
+}
+
+__device__ __forceinline__ int sample_categorical(const float (&p)[MAX_OUT], int n, const float (&q)[MAX_OUT]) {
+    // torch.multinomial(probs, 1) == argmax(probs / q), first index wins ties
+    int best = 0;
+    float bv = p[0] / q[0];
+#pragma unroll
+    for (int j = 1; j < MAX_OUT; ++j)
+        if (j < n) { const float v = p[j] / q[j]; if (v > bv) { bv = v; best = j; } }
+    return best;
+}
+
+__global__ void __launch_bounds__(R_NT) rollout_kernel(const OrlRolloutArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    const int N = a.n_envs, A = a.n_agents, B = N * A, d = a.obs_dim, n = a.n_actions;
+    const int ldx = pad4(d) + 4;
+    float* p = smem;
+    SmemWeights w = carve_weights(p, d, false);
+    float* Xs = p;  p += R_M * ldx;
+    float* N1s = p; p += R_M * LDA;
+    float* N3s = p; p += R_M * LDA;
+    int* act_s = reinterpret_cast<int*>(p); p += R_M;
+
+    // rows of this CTA: whole envs only
+    const int envs_per_cta = R_M / A;
+    const int env0 = blockIdx.x * envs_per_cta;
+    const int n_env_here = min(envs_per_cta, N - env0);
+    const int row0 = env0 * A;
+    const int rows_here = n_env_here * A;
+    const int tid = threadIdx.x;
+
+    load_weights_folded<R_NT>(w, a.policy_params, d, n, false);
+
+    // stage obs of slot t_begin (zero padding for the k tail and for idle rows)
+    for (int i = tid; i < R_M * ldx; i += R_NT) {
+        const int r = i / ldx, k = i % ldx;
+        Xs[i] = (r < rows_here && k < d) ? a.policy_obs[((size_t)a.t_begin * B + row0 + r) * d + k] : 0.f;
+    }
+    __syncthreads();
+
+    constexpr int PPR = R_NT / R_M;
+    const int hrow = tid / PPR, hpart = tid % PPR;
+    const uint64_t rng_base = a.rng_step_base + (a.rng_counter ? *a.rng_counter : 0ull);
+
+    for (int t = a.t_begin; t < a.t_end; ++t) {
+        float mu1[R_M / (R_NT / 16)], rstd1[R_M / (R_NT / 16)], rstd3[R_M / (R_NT / 16)];
+        unsigned pm;
+        trunk_forward<R_M, R_NT, false>(w, Xs, ldx, d, a.activation_id, N1s, N3s, mu1, rstd1, rstd3, pm);
+        __syncthreads();
+        float logit[MAX_OUT];
+        head_dots<R_M, R_NT>(w, N3s, n, logit);
+        if (hpart == 0 && hrow < rows_here) {
+            const size_t grow = (size_t)t * B + row0 + hrow;
+            if (a.action_masks) {
+#pragma unroll
+                for (int j = 0; j < MAX_OUT; ++j)
+                    if (j < n && a.action_masks[grow * n + j] == 0.f) logit[j] = -6e4f;
+            }
+            float nl[MAX_OUT], pr[MAX_OUT];
+            log_softmax_n(logit, n, nl, pr);
+            int act;
+            if (a.deterministic) {
+                act = 0;
+#pragma unroll
+                for (int j = 1; j < MAX_OUT; ++j) if (j < n && pr[j] > pr[act]) act = j;
+            } else {
+                float q[MAX_OUT];
+                if (a.exp_noise) {
+#pragma unroll
+                    for (int j = 0; j < MAX_OUT; ++j) q[j] = (j < n) ? a.exp_noise[grow * n + j] : 1.f;
+                } else {
+                    const uint64_t step = rng_base + (uint64_t)t;
+                    const uint2 key = make_uint2((uint32_t)a.rng_seed, (uint32_t)(a.rng_seed >> 32));
+                    const uint4 r0 = philox4x32_10(make_uint4((uint32_t)step, (uint32_t)(step >> 32), (uint32_t)(row0 + hrow), 0u), key);
+                    const uint4 r1 = philox4x32_10(make_uint4((uint32_t)step, (uint32_t)(step >> 32), (uint32_t)(row0 + hrow), 1u), key);
+                    const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+                    for (int j = 0; j < MAX_OUT; ++j) q[j] = -logf(u32_to_unit_open(rr[j]));
+                }
+                act = sample_categorical(pr, n, q);
+            }
+            float lp = nl[0];
+#pragma unroll
+            for (int j = 1; j < MAX_OUT; ++j) if (j == act) lp = nl[j];
+            a.actions[grow] = (float)act;
+            a.action_log_probs[grow] = lp;
+            act_s[hrow] = act;
+        }
+        __syncthreads();
+
+        // ---- env.step for the envs of this CTA (one thread per env) ----
+        if (a.env_kind != ORL_ENV_NONE && tid < n_env_here) {
+            const int e = env0 + tid;
+            EnvPtrs E{a.env_f64, a.env_u64, a.env_i32, a.env_table, a.env_table_len, a.rng_seed,
+                      a.ep_return, a.ep_length, a.episode_stats};
+            float ob[4], fin[4], reward; bool done;
+            env_step_single(E, a.env_kind, e, N, act_s[tid], ob, reward, done, fin);
+            const size_t o1 = ((size_t)(t + 1) * B + e);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { Xs[tid * ldx + k] = ob[k]; a.policy_obs[o1 * 4 + k] = ob[k]; }
+            a.rewards[(size_t)t * B + e] = reward;
+            a.masks[o1] = done ? 0.f : 1.f;
+            a.active_masks[o1] = 1.f;  // onpolicy_driver.py:118-124 with A == 1
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void bump_counter_kernel(uint64_t* c, uint64_t by) { *c += by; }
+
+__global__ void env_reset_kernel(int env_kind, int N, double* env_f64, uint64_t* env_u64, int32_t* env_i32,
+                                 const int32_t* env_table, int env_table_len, uint64_t seed, float* obs_out) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= N) return;
+    if (env_kind == ORL_ENV_CARTPOLE) {
+        double s[4];
+        Pcg64 g = pcg_load(env_u64, e, N);
+        cartpole_reset(s, g);
+        pcg_store(env_u64, e, N, g);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { env_f64[(size_t)k * N + e] = s[k]; obs_out[(size_t)e * 4 + k] = (float)s[k]; }
+        env_i32[e] = 0;
+    } else if (env_kind == ORL_ENV_GRIDWORLD) {
+        int x, y, nreset = env_i32[3 * N + e];
+        gridworld_reset(x, y, e, nreset, seed, env_table, env_table_len, 10, 10);
+        env_i32[0 * N + e] = x; env_i32[1 * N + e] = y; env_i32[2 * N + e] = 0; env_i32[3 * N + e] = nreset + 1;
+        obs_out[(size_t)e * 4 + 0] = (float)x; obs_out[(size_t)e * 4 + 1] = (float)y;
+        obs_out[(size_t)e * 4 + 2] = 1.f; obs_out[(size_t)e * 4 + 3] = 1.f;
+    }
+}
+
+// ---- batched critic forward --------------------------------------------------------------------
+constexpr int C_M = 128, C_NT = 256;
+
+__global__ void __launch_bounds__(C_NT) critic_values_kernel(const float* __restrict__ params, int d, int activation_id,
+                                                             const float* __restrict__ obs, float* __restrict__ values,
+                                                             long long rows) {
+    extern __shared__ __align__(16) float smem[];
+    const int ldx = pad4(d) + 4;
+    float* p = smem;
+    SmemWeights w = carve_weights(p, d, false);
+    float* Xs = p;  p += C_M * ldx;
+    float* N1s = p; p += C_M * LDA;
+    float* N3s = p; p += C_M * LDA;
+    const int tid = threadIdx.x;
+    load_weights_folded<C_NT>(w, params, d, 1, false);
+    const long long n_tiles = (rows + C_M - 1) / C_M;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long r0 = tile * C_M;
+        const int rows_here = (int)min((long long)C_M, rows - r0);
+        for (int i = tid; i < C_M * ldx; i += C_NT) {
+            const int r = i / ldx, k = i % ldx;
+            Xs[i] = (r < rows_here && k < d) ? obs[(r0 + r) * d + k] : 0.f;
+        }
+        __syncthreads();
+        float mu1[C_M / (C_NT / 16)], rstd1[C_M / (C_NT / 16)], rstd3[C_M / (C_NT / 16)];
+        unsigned pm;
+        trunk_forward<C_M, C_NT, false>(w, Xs, ldx, d, activation_id, N1s, N3s, mu1, rstd1, rstd3, pm);
+        __syncthreads();
+        float out[MAX_OUT];
+        head_dots<C_M, C_NT>(w, N3s, 1, out);
+        constexpr int PPR = C_NT / C_M;
+        if (tid % PPR == 0 && tid / PPR < rows_here) values[r0 + tid / PPR] = out[0];
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+extern "C" int orl_env_reset(int env_kind, int n_envs, int n_agents, double* env_f64, uint64_t* env_u64,
+                             int32_t* env_i32, const int32_t* env_table, int env_table_len, uint64_t rng_seed,
+                             float* policy_obs_out, float* critic_obs_out, void* stream) {
+    ORL_CHECK_ARG(n_envs > 0 && n_agents > 0, "n_envs/n_agents");
+    ORL_CHECK_ARG(policy_obs_out, "policy_obs_out");
+    (void)critic_obs_out;
+    if (env_kind == ORL_ENV_CARTPOLE) ORL_CHECK_ARG(env_f64 && env_u64 && env_i32 && n_agents == 1, "cartpole state");
+    else if (env_kind == ORL_ENV_GRIDWORLD) ORL_CHECK_ARG(env_i32 && n_agents == 1, "gridworld state");
+    else { orl::set_last_error("orl_env_reset: unsupported env_kind %d", env_kind); return ORL_ERR_UNSUPPORTED; }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    env_reset_kernel<<<(n_envs + 127) / 128, 128, 0, st>>>(env_kind, n_envs, env_f64, env_u64, env_i32, env_table,
+                                                          env_table_len, rng_seed, policy_obs_out);
+    ORL_LAUNCH_CHECK("env_reset_kernel");
+    return 0;
+}
+
+
+extern "C" int orl_env_step(int env_kind, int n_envs, int n_agents, double* env_f64, uint64_t* env_u64, int32_t* env_i32,
+                            const int32_t* env_table, int env_table_len, uint64_t rng_seed, float* ep_return,
+                            int32_t* ep_length, double* episode_stats, const float* actions, float* obs_out,
+                            float* rewards_out, float* dones_out, float* final_obs_out, void* stream) {
+    ORL_CHECK_ARG(n_envs > 0 && n_agents == 1, "n_envs / n_agents");
+    ORL_CHECK_ARG(actions && obs_out && rewards_out && dones_out && ep_return && ep_length && episode_stats, "null buffer");
+    if (env_kind == ORL_ENV_CARTPOLE) ORL_CHECK_ARG(env_f64 && env_u64 && env_i32, "cartpole state");
+    else if (env_kind == ORL_ENV_GRIDWORLD) ORL_CHECK_ARG(env_i32, "gridworld state");
+    else { orl::set_last_error("orl_env_step: unsupported env_kind %d", env_kind); return ORL_ERR_UNSUPPORTED; }
+    EnvPtrs E{env_f64, env_u64, env_i32, env_table, env_table_len, rng_seed, ep_return, ep_length, episode_stats};
+    env_step_kernel<<<(n_envs + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        env_kind, n_envs, E, actions, obs_out, rewards_out, dones_out, final_obs_out);
+    ORL_LAUNCH_CHECK("env_step_kernel");
+    return 0;
+}
+
+extern "C" int orl_rollout(const OrlRolloutArgs* args, void* stream) {
+    ORL_CHECK_ARG(args, "args");
+    const OrlRolloutArgs& a = *args;
+    ORL_CHECK_ARG(a.n_envs > 0 && a.n_agents > 0 && a.n_agents <= R_M, "n_envs / n_agents");
+    ORL_CHECK_ARG(a.obs_dim > 0 && a.obs_dim <= 64, "obs_dim must be in 1..64");
+    ORL_CHECK_ARG(a.n_actions > 0 && a.n_actions <= orl::MAX_OUT, "n_actions must be in 1..8");
+    ORL_CHECK_ARG(a.t_begin >= 0 && a.t_begin < a.t_end && a.t_end <= a.episode_length, "step range");
+    ORL_CHECK_ARG(a.activation_id >= 0 && a.activation_id <= 3, "activation_id");
+    ORL_CHECK_ARG(a.policy_params && a.policy_obs && a.actions && a.action_log_probs, "null buffer");
+    if (a.env_kind == ORL_ENV_NONE) {
+        ORL_CHECK_ARG(a.t_end == a.t_begin + 1, "ORL_ENV_NONE acts for one step per call");
+    } else if (a.env_kind == ORL_ENV_CARTPOLE) {
+        ORL_CHECK_ARG(a.n_agents == 1 && a.obs_dim == 4 && a.n_actions == 2, "CartPole shapes");
+        ORL_CHECK_ARG(a.env_f64 && a.env_u64 && a.env_i32 && a.rewards && a.masks && a.active_masks && a.ep_return &&
+                          a.ep_length && a.episode_stats, "CartPole state buffers");
+    } else if (a.env_kind == ORL_ENV_GRIDWORLD) {
+        ORL_CHECK_ARG(a.n_agents == 1 && a.obs_dim == 4 && a.n_actions == 5, "GridWorld shapes");
+        ORL_CHECK_ARG(a.env_i32 && a.rewards && a.masks && a.active_masks && a.ep_return && a.ep_length &&
+                          a.episode_stats, "GridWorld state buffers");
+    } else {
+        orl::set_last_error("orl_rollout: unsupported env_kind %d", a.env_kind);
+        return ORL_ERR_UNSUPPORTED;
+    }
+    const int envs_per_cta = R_M / a.n_agents;
+    const int grid = (a.n_envs + envs_per_cta - 1) / envs_per_cta;
+    const int ldx = orl::pad4(a.obs_dim) + 4;
+    const size_t smem = sizeof(float) * (orl::smem_weights_floats(a.obs_dim, false) + R_M * ldx + 2 * R_M * orl::LDA + R_M);
+    static bool attr_set = false;
+    if (!attr_set) {
+        int e = orl::check_cuda(cudaFuncSetAttribute(rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
+                                "cudaFuncSetAttribute(rollout)");
+        if (e) return e;
+        attr_set = true;
+    }
+    rollout_kernel<<<grid, R_NT, smem, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+    ORL_LAUNCH_CHECK("rollout_kernel");
+    if (a.rng_counter) {
+        bump_counter_kernel<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a.rng_counter, (uint64_t)(a.t_end - a.t_begin));
+        ORL_LAUNCH_CHECK("bump_counter_kernel");
+    }
+    return 0;
+}
+
+extern "C" int orl_critic_values(const float* critic_params, int obs_dim, int activation_id, const float* obs,
+                                 float* values, long long rows, void* stream) {
+    ORL_CHECK_ARG(critic_params && obs && values, "null buffer");
+    ORL_CHECK_ARG(obs_dim > 0 && obs_dim <= 64, "obs_dim must be in 1..64");
+    ORL_CHECK_ARG(rows > 0, "rows");
+    ORL_CHECK_ARG(activation_id >= 0 && activation_id <= 3, "activation_id");
+    const int ldx = orl::pad4(obs_dim) + 4;
+    const size_t smem = sizeof(float) * (orl::smem_weights_floats(obs_dim, false) + C_M * ldx + 2 * C_M * orl::LDA);
+    static bool attr_set = false;
+    if (!attr_set) {
+        int e = orl::check_cuda(cudaFuncSetAttribute(critic_values_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
+                                "cudaFuncSetAttribute(critic_values)");
+        if (e) return e;
+        attr_set = true;
+    }
+    const long long n_tiles = (rows + C_M - 1) / C_M;
+    const int grid = (int)std::min<long long>(n_tiles, 2LL * orl::sm_count());
+    critic_values_kernel<<<grid, C_NT, smem, reinterpret_cast<cudaStream_t>(stream)>>>(critic_params, obs_dim, activation_id,
+                                                                                      obs, values, rows);
+    ORL_LAUNCH_CHECK("critic_values_kernel");
+    return 0;
+}

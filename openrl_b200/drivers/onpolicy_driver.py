@@ -1,0 +1,162 @@
+"""OnPolicyDriver: rollout -> returns -> update loop on the device
+(reference: openrl/drivers/rl_driver.py:27-180, onpolicy_driver.py:32-279).
+
+Per iteration (`_inner_loop`):
+  actor_rollout   ONE orl_rollout launch for all T steps when no callback needs per-step locals
+                  (envs are independent), else T one-step launches with the
+                  reference's `update_locals(locals()) / on_step()` contract;
+  compute_returns one orl_critic_values launch over the (T+1)*B observations (values of every
+                  slot + bootstrap), then the orl_gae scan (returns + raw advantages + moments);
+  trainer.train   ppo_epoch x num_mini_batch fused updates;
+  after_update    slot T -> slot 0.
+Sampling noise: cfg.parity_mode draws `exponential_` per step from torch's global CPU generator in
+the reference's order (act.py:79-81 -> torch.multinomial) and uploads it; otherwise Philox on device.
+"""
+import numpy as np
+import torch
+
+from .. import lib
+
+
+class OnPolicyDriver:
+    def __init__(self, config, trainer, buffer, agent, rank=0, world_size=1, client=None, logger=None, callback=None):
+        cfg = config["cfg"]
+        self.cfg = cfg
+        self.trainer, self.buffer, self.agent = trainer, buffer, agent
+        self.envs = config["envs"]
+        self.device = config["device"]
+        self.num_agents = config["num_agents"]
+        self.rank, self.world_size = rank, world_size
+        self.logger, self.callback = logger, callback
+        self.num_env_steps = cfg.num_env_steps
+        self.episode_length = cfg.episode_length
+        self.n_rollout_threads = cfg.n_rollout_threads
+        self.learner_n_rollout_threads = cfg.learner_n_rollout_threads
+        self.use_linear_lr_decay = cfg.use_linear_lr_decay
+        self.log_interval = cfg.log_interval
+        self.episode = 0
+        self.total_num_steps = 0
+        self._lib = lib.load()
+        self._global_step = 0
+        self.rng_counter = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.gpu_launches = 0
+
+    # -- reference surface -------------------------------------------------------------------
+    def run(self):
+        episodes = int(self.num_env_steps) // self.episode_length // self.learner_n_rollout_threads
+        self.episodes = episodes
+        self.reset_and_buffer_init()
+        for episode in range(episodes):
+            if self.cfg.log_each_episode and self.logger is not None:
+                self.logger.info("Episode: {}/{}".format(episode, episodes))
+            self.episode = episode
+            if not self._inner_loop():
+                break
+
+    def reset_and_buffer_init(self):
+        d = self.buffer.data
+        self.envs.reset_into(d.policy_obs[0].view(-1, d.obs_dim))  # rl_driver.py:118-131, no host copy
+        d.masks[0].fill_(1.0)
+        d.active_masks[0].fill_(1.0)
+
+    def _inner_loop(self):
+        rollout_infos, cont = self.actor_rollout()
+        if not cont:
+            return False
+        train_infos = self.learner_update()
+        self.buffer.after_update()
+        self.total_num_steps = (self.episode + 1) * self.episode_length * self.n_rollout_threads
+        if self.episode % self.log_interval == 0 and self.logger is not None:
+            self.logger.log_info(rollout_infos, step=self.total_num_steps)
+            self.logger.log_info(train_infos, step=self.total_num_steps)
+        return True
+
+    def learner_update(self):
+        if self.use_linear_lr_decay:
+            self.trainer.algo_module.lr_decay(self.episode, self.episodes)
+        self.compute_returns()
+        self.trainer.prep_training()
+        return self.trainer.train(self.buffer.data)
+
+    # -- rollout -----------------------------------------------------------------------------
+    def _rollout_args(self, t_begin, t_end, noise):
+        d, env = self.buffer.data, self.envs
+        pol = self.trainer.algo_module.models["policy"]
+        a = lib.OrlRolloutArgs()
+        a.env_kind, a.n_envs, a.n_agents = env.kind, env.parallel_env_num, env.agent_num
+        a.episode_length, a.t_begin, a.t_end = self.episode_length, t_begin, t_end
+        a.obs_dim, a.critic_obs_dim, a.n_actions = d.obs_dim, 0, d.n_actions
+        a.activation_id, a.deterministic = pol.activation_id, 0
+        a.env_table_len = env.env_table_len
+        a.policy_params = lib.ptr(pol.flat_params)
+        a.policy_obs, a.critic_obs = lib.ptr(d.policy_obs), None
+        a.actions, a.action_log_probs, a.rewards = lib.ptr(d.actions), lib.ptr(d.action_log_probs), lib.ptr(d.rewards)
+        a.masks, a.active_masks = lib.ptr(d.masks), lib.ptr(d.active_masks)
+        a.action_masks = None if d.action_masks_trivial else lib.ptr(d.action_masks)
+        a.exp_noise = lib.ptr(noise)
+        a.rng_seed, a.rng_step_base, a.rng_counter = int(self.cfg.seed) + 0x9E3779B9 * (self.rank + 1), 0, lib.ptr(self.rng_counter)
+        a.env_f64, a.env_u64, a.env_i32 = lib.ptr(env.env_f64), lib.ptr(env.env_u64), lib.ptr(env.env_i32)
+        a.env_table = lib.ptr(env.env_table)
+        a.ep_return, a.ep_length, a.episode_stats = lib.ptr(env.ep_return), lib.ptr(env.ep_length), lib.ptr(env.episode_stats)
+        return a
+
+    def _draw_noise(self):
+        """(T, B, n) Exp(1) noise from the global CPU generator, one draw per step like the
+        reference's `torch.multinomial` inside Categorical.sample()."""
+        d = self.buffer.data
+        B, n = d.n_rollout_threads * d.num_agents, d.n_actions
+        host = torch.empty(self.episode_length, B, n, dtype=torch.float32, pin_memory=True)
+        for t in range(self.episode_length):
+            host[t].exponential_(1)
+        return host.to(self.device, non_blocking=True)
+
+    def actor_rollout(self):
+        cb = self.callback
+        if cb is not None:
+            cb.on_rollout_start()
+        self.trainer.prep_rollout()
+        noise = self._draw_noise() if self.cfg.parity_mode else None
+        T, N = self.episode_length, self.envs.parallel_env_num
+        per_step = cb is not None and getattr(cb, "needs_per_step", True)
+        s = lib.current_stream()
+        if not per_step:
+            lib.check(self._lib.orl_rollout(self._rollout_args(0, T, noise), s), "orl_rollout")
+            self.gpu_launches += 2
+            self.agent.num_time_steps += N * T
+        else:
+            d = self.buffer.data
+            for step in range(T):
+                lib.check(self._lib.orl_rollout(self._rollout_args(step, step + 1, noise), s), "orl_rollout")
+                self.gpu_launches += 2
+                self.agent.num_time_steps += N
+                # materialise the reference's per-step locals for the callbacks
+                actions = d.actions[step].cpu().numpy()  # noqa: F841
+                action_log_probs = d.action_log_probs[step].cpu().numpy()  # noqa: F841
+                obs = d.policy_obs[step + 1].cpu().numpy()  # noqa: F841
+                rewards = d.rewards[step].cpu().numpy()  # noqa: F841
+                dones = d.masks[step + 1].cpu().numpy()[..., 0] == 0.0  # noqa: F841
+                infos = [{} for _ in range(N)]  # noqa: F841
+                cb.update_locals(locals())
+                if cb.on_step() is False:
+                    return {}, False
+        batch_rew_infos = self.envs.batch_rewards(self.buffer)
+        if cb is not None:
+            cb.on_rollout_end()
+        if self.envs.use_monitor:
+            info = self.envs.statistics(self.buffer)
+            info.update(batch_rew_infos)
+            return info, True
+        return batch_rew_infos, True
+
+    @torch.no_grad()
+    def compute_returns(self):
+        """onpolicy_driver.py:206-233: critic values of every slot (incl. the bootstrap slot T) in
+        one launch, then the GAE scan."""
+        d = self.buffer.data
+        cri = self.trainer.algo_module.models["critic"]
+        rows = (self.episode_length + 1) * d.n_rollout_threads * d.num_agents
+        lib.check(self._lib.orl_critic_values(lib.ptr(cri.flat_params), cri.obs_dim, cri.activation_id,
+                                              lib.ptr(d.critic_obs), lib.ptr(d.value_preds), rows,
+                                              lib.current_stream()), "orl_critic_values")
+        self.buffer.compute_returns(None, self.trainer.algo_module.get_critic_value_normalizer())
+        self.gpu_launches += 2

@@ -1,0 +1,20 @@
+"""Registry of envs with a device step function (ids as in the reference's make())."""
+import numpy as np
+
+from .. import lib, spaces
+
+
+def _cartpole_space():
+    high = np.array([4.8, np.finfo(np.float32).max, 0.41887903, np.finfo(np.float32).max], np.float32)
+    return spaces.Box(-high, high, dtype=np.float32)
+
+
+def _gridworld_space():
+    # 10x10 through make() (openrl/envs/gridworld/gridworld_env.py:14-18)
+    return spaces.Box(low=np.array([0, 0, 0, 0]), high=np.array([9, 9, 9, 9]), dtype=np.int64)
+
+
+ENV_SPECS = {
+    "CartPole-v1": dict(kind=lib.ENV_CARTPOLE, agents=1, obs_dim=4, n_actions=2, observation_space=_cartpole_space),
+    "GridWorldEnv": dict(kind=lib.ENV_GRIDWORLD, agents=1, obs_dim=4, n_actions=5, observation_space=_gridworld_space),
+}

@@ -1,0 +1,148 @@
+"""Device-resident vectorised environment with the reference's BaseVecEnv duck type.
+
+Replaces SyncVectorEnv / AsyncVectorEnv + RewardWrapper + VecMonitorWrapper
+(openrl/envs/vec_env/{sync_venv,async_venv}.py, wrappers/{reward_wrapper,vec_monitor_wrapper}.py)
+for the envs that have a CUDA step function (CartPole-v1, GridWorldEnv).  All env state lives in
+CUDA tensors owned by this object; stepping happens inside `orl_rollout` (fused with the policy)
+or, for the plain `step()` API, through `orl_env_step`.  Precedent for handing a GPU-resident
+vec-env straight to PPONet/PPOAgent: examples/isaac/isaac2openrl.py:28-96.
+
+Interface kept (usage: rl_driver.py:118-131, onpolicy_driver.py:172-203):
+  parallel_env_num, agent_num, observation_space, action_space, env_name, use_monitor,
+  reset(seed=, options=) -> (obs, infos), step(actions, extra_data) -> (obs, rewards (N,A,1),
+  dones (N,A) bool, infos list[dict]), batch_rewards(buffer), statistics(buffer), close(),
+  random_action().
+"""
+import time
+
+import numpy as np
+import torch
+
+from .. import _kinds
+from ... import lib, spaces
+
+
+def _pcg64_streams(seed, n):
+    """Host-side seeding only (SeedSequence -> PCG64 initial state, sync_venv.py:137 +
+    gymnasium/utils/seeding.py): env i gets np.random.PCG64(SeedSequence(seed + i*10086))."""
+    out = np.zeros((4, n), np.uint64)
+    mask = (1 << 64) - 1
+    for i in range(n):
+        s = None if seed is None else seed + i * 10086
+        st = np.random.PCG64(np.random.SeedSequence(s)).state["state"]
+        out[0, i], out[1, i] = st["state"] >> 64, st["state"] & mask
+        out[2, i], out[3, i] = st["inc"] >> 64, st["inc"] & mask
+    return out
+
+
+class DeviceVecEnv:
+    def __init__(self, env_id, env_num, device="cuda:0", seed=None, reset_table=None):
+        spec = _kinds.ENV_SPECS[env_id]
+        self.env_name = env_id
+        self.kind = spec["kind"]
+        self.parallel_env_num = int(env_num)
+        self.agent_num = spec["agents"]
+        self.obs_dim = spec["obs_dim"]
+        self.n_actions = spec["n_actions"]
+        self.observation_space = spec["observation_space"]()
+        self.action_space = spaces.Discrete(self.n_actions)
+        self.device = torch.device(device)
+        self.use_monitor = True
+        self._lib = lib.load()
+        N = self.parallel_env_num
+        dev = self.device
+        self.env_f64 = torch.zeros(4, N, dtype=torch.float64, device=dev)
+        self.env_u64 = torch.zeros(4, N, dtype=torch.int64, device=dev)  # bit pattern of uint64
+        self.env_i32 = torch.zeros(4, N, dtype=torch.int32, device=dev)
+        self.ep_return = torch.zeros(N, dtype=torch.float32, device=dev)
+        self.ep_length = torch.zeros(N, dtype=torch.int32, device=dev)
+        self.episode_stats = torch.zeros(4, dtype=torch.float64, device=dev)
+        self.rng_seed = 0
+        self.env_table = None
+        self.env_table_len = 0
+        if reset_table is not None:  # (N, K, 2) int start cells for GridWorld parity runs
+            t = torch.as_tensor(np.asarray(reset_table), dtype=torch.int32).contiguous()
+            self.env_table = t.to(dev)
+            self.env_table_len = int(t.shape[1])
+        self._obs = torch.zeros(N * self.agent_num, self.obs_dim, dtype=torch.float32, device=dev)
+        self._start_time = time.time()
+        self._total_step = 0
+        self._seed_streams(seed)
+
+    # -- seeding / reset -------------------------------------------------------------------
+    def _seed_streams(self, seed):
+        if self.kind == lib.ENV_CARTPOLE:
+            st = _pcg64_streams(seed, self.parallel_env_num)
+            self.env_u64.copy_(torch.from_numpy(st.view(np.int64)))
+        self.rng_seed = int(seed if seed is not None else np.random.SeedSequence().entropy % (1 << 63))
+
+    def reset(self, seed=None, options=None):
+        if seed is not None:
+            self._seed_streams(int(seed))
+        self.reset_into(self._obs)
+        obs = self._obs.view(self.parallel_env_num, self.agent_num, self.obs_dim).cpu().numpy()
+        return obs, [{} for _ in range(self.parallel_env_num)]
+
+    def reset_into(self, obs_out):
+        """Device-side reset writing the (B, d) observations into `obs_out` (no host copy)."""
+        L = self._lib
+        lib.check(L.orl_env_reset(self.kind, self.parallel_env_num, self.agent_num, lib.ptr(self.env_f64),
+                                  lib.ptr(self.env_u64), lib.ptr(self.env_i32), lib.ptr(self.env_table),
+                                  self.env_table_len, self.rng_seed, lib.ptr(obs_out), None, lib.current_stream()),
+                  "orl_env_reset")
+        self.ep_return.zero_()
+        self.ep_length.zero_()
+        if obs_out.data_ptr() != self._obs.data_ptr():
+            self._obs.copy_(obs_out.view_as(self._obs))
+
+    # -- plain step API (evaluation loops; the training loop uses the fused rollout) ---------
+    def step(self, actions, extra_data=None):
+        N, A = self.parallel_env_num, self.agent_num
+        act = torch.as_tensor(np.asarray(actions, dtype=np.float32).reshape(N * A)).to(self.device)
+        rew = torch.empty(N * A, dtype=torch.float32, device=self.device)
+        done = torch.empty(N * A, dtype=torch.float32, device=self.device)
+        fin = torch.empty(N * A, self.obs_dim, dtype=torch.float32, device=self.device)
+        lib.check(self._lib.orl_env_step(self.kind, N, A, lib.ptr(self.env_f64), lib.ptr(self.env_u64),
+                                         lib.ptr(self.env_i32), lib.ptr(self.env_table), self.env_table_len,
+                                         self.rng_seed, lib.ptr(self.ep_return), lib.ptr(self.ep_length),
+                                         lib.ptr(self.episode_stats), lib.ptr(act), lib.ptr(self._obs), lib.ptr(rew),
+                                         lib.ptr(done), lib.ptr(fin), lib.current_stream()), "orl_env_step")
+        obs = self._obs.view(N, A, self.obs_dim).cpu().numpy()
+        dones = done.view(N, A).cpu().numpy() != 0
+        rewards = rew.view(N, A, 1).cpu().numpy().astype(np.float64)
+        fin_h = fin.view(N, A, self.obs_dim).cpu().numpy()
+        infos = []
+        for i in range(N):
+            info = {}
+            if dones[i].all():
+                info["final_observation"] = fin_h[i]
+                info["final_info"] = {}
+            infos.append(info)
+        return obs, rewards, dones, infos
+
+    def random_action(self, infos=None):
+        return np.array([[[self.action_space.sample()] for _ in range(self.agent_num)]
+                         for _ in range(self.parallel_env_num)])
+
+    # -- statistics (SimpleVecInfo.statistics, vec_info/simple_vec_info.py:18-32) ------------
+    def batch_rewards(self, buffer):
+        return {}
+
+    def statistics(self, buffer):
+        rewards = buffer.data.rewards  # (T, N, A, 1) device
+        T, N = rewards.shape[0], rewards.shape[1]
+        self._total_step += T * N
+        per_agent = rewards.mean(dim=1).sum(dim=0).reshape(-1)  # (A,)
+        vals = per_agent.cpu().numpy()
+        info = {f"agent_{i}/rollout_episode_reward": float(v) for i, v in enumerate(vals)}
+        info["FPS"] = int(self._total_step / max(time.time() - self._start_time, 1e-9))
+        info["rollout_episode_reward"] = float(np.mean(vals))
+        st = self.episode_stats.cpu().numpy()
+        if st[2] > 0:
+            info["episode_return_mean"] = float(st[0] / st[2])
+            info["episode_length_mean"] = float(st[1] / st[2])
+        self.episode_stats.zero_()
+        return info
+
+    def close(self):
+        pass

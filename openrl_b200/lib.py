@@ -93,3 +93,55 @@ def current_stream():
     import torch
 
     return torch.cuda.current_stream().cuda_stream
+
+
+# ---- argument structs (mirror include/openrl_b200.h field for field) -------------------------
+class OrlRolloutArgs(ctypes.Structure):
+    _fields_ = [
+        ("env_kind", _c.c_int32), ("n_envs", _c.c_int32), ("n_agents", _c.c_int32), ("episode_length", _c.c_int32),
+        ("t_begin", _c.c_int32), ("t_end", _c.c_int32), ("obs_dim", _c.c_int32), ("critic_obs_dim", _c.c_int32),
+        ("n_actions", _c.c_int32), ("activation_id", _c.c_int32), ("deterministic", _c.c_int32),
+        ("env_table_len", _c.c_int32),
+        ("policy_params", _P), ("policy_obs", _P), ("critic_obs", _P), ("actions", _P), ("action_log_probs", _P),
+        ("rewards", _P), ("masks", _P), ("active_masks", _P), ("action_masks", _P), ("exp_noise", _P),
+        ("rng_seed", _c.c_uint64), ("rng_step_base", _c.c_uint64), ("rng_counter", _P),
+        ("env_f64", _P), ("env_u64", _P), ("env_i32", _P), ("env_table", _P),
+        ("ep_return", _P), ("ep_length", _P), ("episode_stats", _P),
+    ]
+
+
+class OrlPpoArgs(ctypes.Structure):
+    _fields_ = [
+        ("obs_dim", _c.c_int32), ("critic_obs_dim", _c.c_int32), ("n_actions", _c.c_int32),
+        ("activation_id", _c.c_int32), ("flags", _c.c_int32), ("grid_per_net", _c.c_int32),
+        ("batch_rows", _c.c_int64), ("row_begin", _c.c_int64), ("total_rows", _c.c_int64),
+        ("indices", _P),
+        ("policy_obs", _P), ("critic_obs", _P), ("actions", _P), ("old_log_probs", _P), ("advantages", _P),
+        ("value_preds", _P), ("returns", _P), ("active_masks", _P), ("action_masks", _P),
+        ("gae_stats", _P), ("mb_stats", _P), ("vn_state", _P),
+        ("policy_params", _P), ("critic_params", _P),
+        ("policy_adam_m", _P), ("policy_adam_v", _P), ("critic_adam_m", _P), ("critic_adam_v", _P),
+        ("adam_steps", _P), ("lrs", _P),
+        ("clip_param", _F), ("entropy_coef", _F), ("value_loss_coef", _F), ("huber_delta", _F), ("max_grad_norm", _F),
+        ("adam_beta1", _F), ("adam_beta2", _F), ("adam_eps", _F), ("weight_decay", _F), ("vn_beta", _F),
+        ("partials", _P), ("folded", _P), ("grads", _P), ("train_info", _P),
+    ]
+
+
+_SIGNATURES.update({
+    "orl_env_reset": [_I, _I, _I, _P, _P, _P, _P, _I, _c.c_uint64, _P, _P, _P],
+    "orl_rollout": [_c.POINTER(OrlRolloutArgs), _P],
+    "orl_env_step": [_I, _I, _I, _P, _P, _P, _P, _I, _c.c_uint64, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "orl_critic_values": [_P, _I, _I, _P, _P, _L, _P],
+    "orl_ppo_stride": [_I, _I, _I],
+    "orl_net_param_count": [_I, _I],
+    "orl_ppo_fwdbwd": [_c.POINTER(OrlPpoArgs), _P],
+    "orl_ppo_reduce": [_c.POINTER(OrlPpoArgs), _P],
+    "orl_ppo_apply": [_c.POINTER(OrlPpoArgs), _P],
+    "orl_minibatch_stats": [_P, _c.c_int64, _P, _P, _P, _P],
+})
+
+ENV_NONE, ENV_CARTPOLE, ENV_GRIDWORLD, ENV_MPE_SPREAD = 0, 1, 2, 3
+GAE_USE_GAE, GAE_PROPER_TIME_LIMITS, GAE_DENORM = 1, 2, 4
+PPO_HUBER, PPO_CLIP_VALUE, PPO_VALUE_ACTIVE_MASKS, PPO_POLICY_ACTIVE_MASKS = 1, 2, 4, 8
+PPO_VALUENORM, PPO_ADV_NORMALIZE, PPO_MAX_GRAD_NORM = 16, 32, 64

@@ -1,0 +1,109 @@
+"""Building blocks with the reference's module tree / state_dict names
+(openrl/modules/networks/utils/mlp.py:8-46,100-176; distributions.py:58-66; valuenorm.py:6-57).
+
+Parameters are created on the CPU with the reference's initialisation sequence (default
+nn.Linear init, then orthogonal_/constant_) so that the global torch generator is consumed
+identically and a given seed yields the reference's initial weights; `FlatParams` then moves them
+into ONE flat float32 CUDA buffer in state_dict order — the layout the kernels read
+(orl_mlp.cuh) — and re-points every nn.Parameter at its slice, so `state_dict()`,
+`load_state_dict()` and `torch.save(module)` keep working.
+
+These modules carry no torch forward: the numeric path is CUDA only (`orl_rollout`,
+`orl_critic_values`, `orl_ppo_*`)."""
+import torch
+import torch.nn as nn
+
+ACT_NAMES = ["tanh", "relu", "leaky_relu", "selu"]
+
+
+def _init(module, gain, use_orthogonal=True):
+    (nn.init.orthogonal_ if use_orthogonal else nn.init.xavier_uniform_)(module.weight.data, gain=gain)
+    nn.init.constant_(module.bias.data, 0)
+    return module
+
+
+class MLPLayer(nn.Module):
+    def __init__(self, input_dim, hidden_size, layer_N, use_orthogonal, activation_id):
+        super().__init__()
+        if layer_N != 1:
+            raise NotImplementedError("openrl_b200 kernels are built for layer_N == 1 (the reference default)")
+        act = [nn.Tanh(), nn.ReLU(), nn.LeakyReLU(), nn.ELU()][activation_id]
+        gain = nn.init.calculate_gain(ACT_NAMES[activation_id])
+        self.fc1 = nn.Sequential(_init(nn.Linear(input_dim, hidden_size), gain, use_orthogonal), act,
+                                 nn.LayerNorm(hidden_size))
+        self.fc3 = nn.Sequential(_init(nn.Linear(hidden_size, hidden_size), gain, use_orthogonal),
+                                 nn.LayerNorm(hidden_size))
+
+
+class MLPBase(nn.Module):
+    def __init__(self, cfg, obs_shape):
+        super().__init__()
+        if cfg.use_feature_normalization:
+            raise NotImplementedError("use_feature_normalization is not built into the kernels yet")
+        if cfg.hidden_size != 64:
+            raise NotImplementedError("openrl_b200 kernels are built for hidden_size == 64 (the reference default)")
+        self.hidden_size = cfg.hidden_size
+        self.mlp = MLPLayer(obs_shape[0], cfg.hidden_size, cfg.layer_N, cfg.use_orthogonal, cfg.activation_id)
+
+    @property
+    def output_size(self):
+        return self.hidden_size
+
+
+class Categorical(nn.Module):
+    def __init__(self, num_inputs, num_outputs, use_orthogonal=True, gain=0.01):
+        super().__init__()
+        self.linear = _init(nn.Linear(num_inputs, num_outputs), gain, use_orthogonal)
+
+
+class ACTLayer(nn.Module):
+    def __init__(self, action_space, inputs_dim, use_orthogonal, gain):
+        super().__init__()
+        if action_space.__class__.__name__ != "Discrete":
+            raise NotImplementedError("only Discrete action heads are built so far")
+        self.action_out = Categorical(inputs_dim, action_space.n, use_orthogonal, gain)
+
+
+class ValueNorm(nn.Module):
+    """Running statistics of the value targets (valuenorm.py:6-57); the three scalars live in one
+    float32 CUDA tensor `state` = (running_mean, running_mean_sq, debiasing_term) updated by
+    orl_ppo_apply and read by orl_gae / orl_ppo_fwdbwd."""
+
+    def __init__(self, input_shape=1, beta=0.99999, device="cpu"):
+        super().__init__()
+        self.beta = beta
+        self.register_buffer("state", torch.zeros(3, dtype=torch.float32, device=device))
+
+    @property
+    def running_mean(self):
+        return self.state[0:1]
+
+    @property
+    def running_mean_sq(self):
+        return self.state[1:2]
+
+    @property
+    def debiasing_term(self):
+        return self.state[2]
+
+    def running_mean_var(self):
+        d = self.state[2].clamp(min=1e-5)
+        m = self.state[0] / d
+        var = (self.state[1] / d - m * m).clamp(min=1e-2)
+        return m, var
+
+
+class FlatParams:
+    """Flatten a module's parameters (named_parameters order) into one CUDA buffer."""
+
+    def __init__(self, module, device):
+        ps = [p for _, p in module.named_parameters()]
+        self.numel = sum(p.numel() for p in ps)
+        self.flat = torch.empty(self.numel, dtype=torch.float32, device=device)
+        off = 0
+        for p in ps:
+            n = p.numel()
+            view = self.flat[off:off + n].view(p.shape)
+            view.copy_(p.data.to(torch.float32))
+            p.data = view
+            off += n

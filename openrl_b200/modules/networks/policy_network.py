@@ -1,0 +1,31 @@
+"""PolicyNetwork (reference: openrl/modules/networks/policy_network.py:33): base -> act."""
+import torch
+import torch.nn as nn
+
+from .base import ACTLayer, FlatParams, MLPBase
+
+
+def _policy_shape(space):
+    return space["policy"].shape if space.__class__.__name__ == "Dict" else space.shape
+
+
+class PolicyNetwork(nn.Module):
+    def __init__(self, cfg, input_space, action_space, device=torch.device("cpu"), use_half=False, extra_args=None):
+        super().__init__()
+        if cfg.use_recurrent_policy or cfg.use_naive_recurrent_policy:
+            raise NotImplementedError("recurrent policies are the next row of the build plan (DESIGN.md)")
+        self.hidden_size = cfg.hidden_size
+        shape = _policy_shape(input_space)
+        if len(shape) != 1 or shape[0] > 64:
+            raise NotImplementedError("vector observations of width <= 64 only")
+        self.obs_dim = shape[0]
+        self.n_actions = action_space.n
+        self.activation_id = cfg.activation_id
+        self.base = MLPBase(cfg, shape)
+        self.act = ACTLayer(action_space, self.base.output_size, cfg.use_orthogonal, cfg.gain)
+        self.device = torch.device(device)
+        self._flat = FlatParams(self, self.device)
+
+    @property
+    def flat_params(self):
+        return self._flat.flat

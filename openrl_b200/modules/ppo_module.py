@@ -1,0 +1,111 @@
+"""PPOModule: bundle of models {"policy","critic"} + optimizers with the reference's method
+surface (openrl/modules/ppo_module.py:32-224, rl_module.py:29-190).
+
+Numeric methods launch CUDA through the C-ABI; optimizers are `FusedAdamState` objects whose
+moments the `orl_ppo_apply` kernel updates (torch.optim.Adam semantics, rl_module.py:80-87)."""
+import numpy as np
+import torch
+
+from .. import lib
+from .networks import PolicyNetwork, ValueNetwork
+
+
+class FusedAdamState:
+    """State of one Adam optimiser living in flat CUDA buffers (exp_avg, exp_avg_sq, step)."""
+
+    def __init__(self, flat_params, lr, eps, weight_decay, betas=(0.9, 0.999)):
+        self.param_groups = [dict(lr=lr, eps=eps, weight_decay=weight_decay, betas=betas)]
+        self.exp_avg = torch.zeros_like(flat_params)
+        self.exp_avg_sq = torch.zeros_like(flat_params)
+
+    def zero_grad(self):
+        pass
+
+    def state_dict(self):
+        return dict(param_groups=self.param_groups, exp_avg=self.exp_avg.clone(), exp_avg_sq=self.exp_avg_sq.clone())
+
+    def load_state_dict(self, sd):
+        self.param_groups = sd["param_groups"]
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+
+
+class PPOModule:
+    def __init__(self, cfg, policy_input_space, critic_input_space, act_space, share_model=False, device="cuda:0",
+                 rank=0, world_size=1, model_dict=None):
+        if share_model:
+            raise NotImplementedError("use_share_model (PolicyValueNetwork) is a 'next' row (SURVEY.md §8f)")
+        self.cfg = cfg
+        self.device = torch.device(device)
+        self.lr, self.critic_lr = cfg.lr, cfg.critic_lr
+        self.opti_eps, self.weight_decay = cfg.opti_eps, cfg.weight_decay
+        self.act_space = act_space
+        self.rank, self.world_size = rank, world_size
+        self.share_model = False
+        self.models, self.optimizers = {}, {}
+        # dict order as in the reference: policy first, then critic (ppo_module.py:71-88)
+        pol_cls = (model_dict or {}).get("policy", PolicyNetwork)
+        cri_cls = (model_dict or {}).get("critic", ValueNetwork)
+        self.models["policy"] = pol_cls(cfg=cfg, input_space=policy_input_space, action_space=act_space,
+                                        device=self.device, use_half=False, extra_args=None)
+        self.optimizers["policy"] = FusedAdamState(self.models["policy"].flat_params, cfg.lr, cfg.opti_eps, cfg.weight_decay)
+        self.models["critic"] = cri_cls(cfg=cfg, input_space=critic_input_space, action_space=act_space,
+                                        device=self.device, use_half=False, extra_args=None)
+        self.optimizers["critic"] = FusedAdamState(self.models["critic"].flat_params, cfg.critic_lr, cfg.opti_eps,
+                                                   cfg.weight_decay)
+        self.adam_steps = torch.zeros(2, dtype=torch.int32, device=self.device)
+        self._lib = lib.load()
+
+    # -- reference surface -----------------------------------------------------------------
+    def lr_decay(self, episode, episodes):
+        """update_linear_schedule (openrl/modules/utils/util.py:13-17)."""
+        for key, base in (("policy", self.lr), ("critic", self.critic_lr)):
+            lr = base - (base * (episode / float(episodes)))
+            for g in self.optimizers[key].param_groups:
+                g["lr"] = lr
+
+    def get_critic_value_normalizer(self):
+        return self.models["critic"].value_normalizer
+
+    def get_values(self, critic_obs, rnn_states_critic=None, masks=None):
+        """ValueNetwork.forward on a (rows, d_c) batch -> (rows, 1) CUDA tensor."""
+        obs = torch.as_tensor(critic_obs, dtype=torch.float32).to(self.device).contiguous()
+        rows = obs.shape[0]
+        out = torch.empty(rows, 1, dtype=torch.float32, device=self.device)
+        cri = self.models["critic"]
+        lib.check(self._lib.orl_critic_values(lib.ptr(cri.flat_params), cri.obs_dim, cri.activation_id, lib.ptr(obs),
+                                              lib.ptr(out), rows, lib.current_stream()), "orl_critic_values")
+        return out
+
+    def act(self, obs, rnn_states_actor=None, masks=None, action_masks=None, deterministic=False, exp_noise=None,
+            rng_seed=0, rng_step=0):
+        """PolicyNetwork.forward_original on a (rows, d) batch (ppo_module.py:195-210):
+        returns (actions (rows,1) float CUDA tensor, log-probs (rows,1))."""
+        pol = self.models["policy"]
+        obs = torch.as_tensor(obs, dtype=torch.float32).to(self.device).contiguous().view(-1, pol.obs_dim)
+        rows = obs.shape[0]
+        actions = torch.empty(rows, 1, dtype=torch.float32, device=self.device)
+        logp = torch.empty(rows, 1, dtype=torch.float32, device=self.device)
+        am = None if action_masks is None else torch.as_tensor(action_masks, dtype=torch.float32).to(self.device).contiguous()
+        noise = None if exp_noise is None else torch.as_tensor(exp_noise, dtype=torch.float32).to(self.device).contiguous()
+        a = lib.OrlRolloutArgs()
+        a.env_kind, a.n_envs, a.n_agents, a.episode_length = lib.ENV_NONE, rows, 1, 1
+        a.t_begin, a.t_end = 0, 1
+        a.obs_dim, a.critic_obs_dim, a.n_actions = pol.obs_dim, 0, pol.n_actions
+        a.activation_id, a.deterministic = pol.activation_id, int(bool(deterministic))
+        a.policy_params, a.policy_obs = lib.ptr(pol.flat_params), lib.ptr(obs)
+        a.actions, a.action_log_probs = lib.ptr(actions), lib.ptr(logp)
+        a.action_masks, a.exp_noise = lib.ptr(am), lib.ptr(noise)
+        a.rng_seed, a.rng_step_base = int(rng_seed), int(rng_step)
+        lib.check(self._lib.orl_rollout(a, lib.current_stream()), "orl_rollout(act)")
+        return actions, logp
+
+    @staticmethod
+    def init_rnn_states(rollout_num, agent_num, rnn_layers, hidden_size):
+        masks = np.ones((rollout_num * agent_num, 1), dtype=np.float32)
+        rnn_state = np.zeros((rollout_num * agent_num, rnn_layers, hidden_size))
+        return rnn_state, masks
+
+    def load_policy(self, model_path):
+        sd = torch.load(str(model_path), map_location=self.device)
+        self.models["policy"].load_state_dict(sd)

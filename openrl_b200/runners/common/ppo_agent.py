@@ -1,0 +1,104 @@
+"""PPOAgent(net).train(total_time_steps) / act / save / load
+(reference: openrl/runners/common/ppo_agent.py:39-158, rl_agent.py:35-216, base_agent.py:31)."""
+import io
+import pathlib
+
+import numpy as np
+import torch
+
+from ...algorithms.ppo import PPOAlgorithm
+from ...buffers import NormalReplayBuffer
+from ...drivers.onpolicy_driver import OnPolicyDriver
+from ...utils.callbacks import BaseCallback, CallbackList
+from ...utils.logger import Logger
+
+
+class PPOAgent:
+    def __init__(self, net, env=None, run_dir=None, env_num=None, rank=0, world_size=1, use_wandb=False,
+                 use_tensorboard=False, project_name="PPOAgent"):
+        self.net = net
+        self._cfg = net.cfg
+        self._use_wandb, self._use_tensorboard = use_wandb, use_tensorboard
+        self.project_name = project_name
+        self._env = env if env is not None else net.env
+        self.net.reset()
+        self._cfg.n_rollout_threads = self._env.parallel_env_num if env_num is None else env_num
+        self._cfg.learner_n_rollout_threads = self._cfg.n_rollout_threads
+        self.env_num = self._cfg.n_rollout_threads
+        self.run_dir = run_dir
+        self.rank, self.world_size = rank, world_size
+        self.client = None
+        self.agent_num = self._env.agent_num
+        self.num_time_steps = 0
+        self._episode_num = 0
+        self._total_time_steps = 0
+        self.driver = None
+
+    def train(self, total_time_steps, callback=None, train_algo_class=PPOAlgorithm, logger=None,
+              driver_class=OnPolicyDriver):
+        self._cfg.num_env_steps = total_time_steps
+        self._total_time_steps = total_time_steps
+        self.config = {"cfg": self._cfg, "num_agents": self.agent_num, "run_dir": self.run_dir, "envs": self._env,
+                       "device": self.net.device}
+        trainer = train_algo_class(cfg=self._cfg, init_module=self.net.module, device=self.net.device,
+                                   agent_num=self.agent_num)
+        buffer = NormalReplayBuffer(self._cfg, self.agent_num, self._env.observation_space, self._env.action_space,
+                                    data_client=None, device=self.net.device)
+        if logger is None:
+            logger = Logger(cfg=self._cfg, project_name=self.project_name, quiet=getattr(self._cfg, "quiet", False))
+        self._logger = logger
+        callback = self._setup_callback(callback)
+        driver = driver_class(config=self.config, trainer=trainer, buffer=buffer, agent=self, client=self.client,
+                              rank=self.rank, world_size=self.world_size, logger=logger, callback=callback)
+        self.driver = driver
+        if callback is not None:
+            callback.on_training_start(locals(), globals())
+        driver.run()
+        if callback is not None:
+            callback.on_training_end()
+        logger.close()
+
+    def _setup_callback(self, callback):
+        if callback is None:
+            return None
+        if isinstance(callback, (list, tuple)):
+            callback = CallbackList(callback)
+        callback.init_callback(self)
+        return callback
+
+    def act(self, observation, info=None, deterministic=True, episode_starts=None):
+        """ppo_agent.py:134-158: observation (N, A, d) -> actions (N, A, 1) numpy."""
+        obs = np.asarray(observation, dtype=np.float32)
+        N, A = obs.shape[0], obs.shape[1]
+        actions, _ = self.net.act(obs.reshape(N * A, -1), deterministic=deterministic, episode_starts=episode_starts)
+        return actions.view(N, A, 1).cpu().numpy().astype(np.int64), None
+
+    def set_env(self, env):
+        self.net.reset(env)
+        self._env = env
+        self.env_num = env.parallel_env_num
+        self.agent_num = env.agent_num
+
+    def save(self, path):
+        """rl_agent.py:187-191: torch.save(self.net.module, path/"module.pt")."""
+        path = pathlib.Path(path)
+        path.mkdir(parents=True, exist_ok=True)
+        m = self.net.module
+        state = {
+            "models": {k: v.state_dict() for k, v in m.models.items()},
+            "optimizers": {k: v.state_dict() for k, v in m.optimizers.items()},
+            "adam_steps": m.adam_steps.clone(),
+        }
+        torch.save(state, path / "module.pt")
+
+    def load(self, path):
+        path = pathlib.Path(path)
+        f = path / "module.pt" if path.is_dir() else path
+        state = torch.load(f, map_location=self.net.device, weights_only=False)
+        m = self.net.module
+        for k, sd in state["models"].items():
+            m.models[k].load_state_dict(sd)
+        for k, sd in state["optimizers"].items():
+            m.optimizers[k].load_state_dict(sd)
+        m.adam_steps.copy_(state["adam_steps"])
+        self.net.reset()

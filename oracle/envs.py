@@ -1,0 +1,126 @@
+"""Oracle: vectorised env semantics of the reference for the simple gym-class envs (numpy).
+
+TEST INFRASTRUCTURE (see oracle/__init__.py).  Follows
+  SyncVectorEnv._reset / _step (auto-reset)   openrl/envs/vec_env/sync_venv.py:129-247
+  Single2MultiAgentWrapper / RemoveTruncated  openrl/envs/wrappers/multiagent_wrapper.py:33-79,
+                                              openrl/envs/wrappers/extra_wrappers.py:52-134
+  gymnasium TimeLimit (500 steps) + CartPole  oracle/cartpole_ref.py (third-party restated)
+  GridWorldEnv                                openrl/envs/gridworld/gridworld_env.py:21-86
+Returns the reference's 4-tuple: obs (N,A,d) , rewards (N,A,1) float64, dones (N,A) bool, infos.
+"""
+import numpy as np
+
+from .cartpole_ref import MAX_EPISODE_STEPS, cartpole_step_f64
+
+
+def pcg64_np_random(seed):
+    """gymnasium.utils.seeding.np_random: PCG64(SeedSequence(seed))."""
+    return np.random.Generator(np.random.PCG64(np.random.SeedSequence(seed)))
+
+
+class CartPoleVec:
+    obs_dim = 4
+    n_actions = 2
+    agent_num = 1
+
+    def __init__(self, env_num):
+        self.N = env_num
+        self.rng = [pcg64_np_random(None) for _ in range(env_num)]
+        self.state = np.zeros((env_num, 4), np.float64)
+        self.elapsed = np.zeros(env_num, np.int64)
+
+    def _reset_one(self, i):
+        self.state[i] = self.rng[i].uniform(low=-0.05, high=0.05, size=(4,))
+        self.elapsed[i] = 0
+
+    def reset(self, seed=None):
+        for i in range(self.N):
+            if seed is not None:
+                self.rng[i] = pcg64_np_random(seed + i * 10086)  # sync_venv.py:137
+            self._reset_one(i)
+        return self.state.astype(np.float32)[:, None, :].copy()
+
+    def step(self, actions):
+        """actions (N,1,1) -> obs (N,1,4) f32, rewards (N,1,1) f64, dones (N,1) bool, final_obs (N,4)."""
+        obs = np.zeros((self.N, 1, 4), np.float32)
+        rewards = np.ones((self.N, 1, 1), np.float64)
+        dones = np.zeros((self.N, 1), bool)
+        final_obs = np.full((self.N, 4), np.nan, np.float32)
+        for i in range(self.N):
+            s, terminated = cartpole_step_f64(tuple(self.state[i]), int(actions[i, 0, 0]))
+            self.state[i] = s
+            self.elapsed[i] += 1
+            truncated = self.elapsed[i] >= MAX_EPISODE_STEPS
+            done = terminated or truncated
+            dones[i, 0] = done
+            if done:  # sync_venv.py:213-218 auto-reset; the terminal obs goes to info["final_observation"]
+                final_obs[i] = np.array(s, dtype=np.float32)
+                self._reset_one(i)
+            obs[i, 0] = self.state[i].astype(np.float32)
+        return obs, rewards, dones, final_obs
+
+
+class GridWorldVec:
+    """GridWorldEnv (10x10 via make(): nrow=ncol=10, goal (1,1)); resets consume the GLOBAL
+    np.random (MT19937) in env order (gridworld_env.py:76-81) — or a caller-supplied table
+    `reset_positions[k]` (k-th reset overall) for device-parity runs."""
+    obs_dim = 4
+    n_actions = 5
+    agent_num = 1
+
+    def __init__(self, env_num, nrow=10, ncol=10, reset_table=None):
+        self.N, self.nrow, self.ncol = env_num, nrow, ncol
+        self.pos = np.zeros((env_num, 2), np.int64)
+        self.steps = np.zeros(env_num, np.int64)
+        self.goal = np.array([1, 1])
+        self.reset_table = reset_table
+        self.reset_count = 0
+
+    def _reset_one(self, i):
+        self.steps[i] = 0
+        if self.reset_table is not None:
+            self.pos[i] = self.reset_table[self.reset_count]
+            self.reset_count += 1
+            return
+        while True:
+            p = np.random.randint(low=[0, 0], high=[self.nrow, self.ncol])
+            if not (p == self.goal).all():
+                self.pos[i] = p
+                return
+
+    def _obs(self):
+        return np.concatenate([self.pos, np.tile(self.goal, (self.N, 1))], axis=1)[:, None, :]
+
+    def reset(self, seed=None):
+        for i in range(self.N):
+            self._reset_one(i)
+        return self._obs()
+
+    def step(self, actions):
+        rewards = np.zeros((self.N, 1, 1), np.float64)
+        dones = np.zeros((self.N, 1), bool)
+        delta = {0: (0, 0), 1: (-1, 0), 2: (1, 0), 3: (0, -1), 4: (0, 1)}
+        final_obs = np.full((self.N, 4), -1, np.int64)
+        for i in range(self.N):
+            d = delta[int(actions[i, 0, 0])]
+            self.pos[i] = np.clip(self.pos[i] + np.array(d), [0, 0], [self.nrow - 1, self.ncol - 1])
+            reward, done = 0, False
+            if (self.pos[i] == self.goal).all():
+                reward += 10
+                done = True
+            else:
+                reward -= 1
+            if self.steps[i] == 100:
+                done = True
+                reward -= 10
+            else:
+                self.steps[i] += 1
+            rewards[i, 0, 0] = reward
+            dones[i, 0] = done
+            if done:
+                final_obs[i] = np.concatenate([self.pos[i], self.goal])
+                self._reset_one(i)
+        return self._obs(), rewards, dones, final_obs
+
+
+ENVS = {"CartPole-v1": CartPoleVec, "GridWorldEnv": GridWorldVec}

@@ -87,10 +87,10 @@ def test_gae_bit_exact_vs_oracle_random(orl_lib, cuda, T, N, A, flags):
     assert stats[2] == T * N * A
     np.testing.assert_allclose(stats[3], a64[on].sum(), rtol=1e-9, atol=1e-9)
     np.testing.assert_allclose(stats[4], (a64[on] ** 2).sum(), rtol=1e-9)
-    assert stats[5] == on.sum()
+    assert stats[7] == on.sum()
     r64 = want_ret[:-1].astype(np.float64)
-    np.testing.assert_allclose(stats[6], r64.sum(), rtol=1e-9, atol=1e-9)
-    np.testing.assert_allclose(stats[7], (r64 ** 2).sum(), rtol=1e-9)
+    np.testing.assert_allclose(stats[5], r64.sum(), rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(stats[6], (r64 ** 2).sum(), rtol=1e-9)
 
 
 def test_gae_large_shape_properties(orl_lib, cuda):

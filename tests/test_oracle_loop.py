@@ -1,0 +1,47 @@
+"""The full-iteration oracle (oracle/loop.py) against traces of the unmodified reference
+(tests/golden/trace_*.npz, produced by oracle/gen_golden.py): same seeds -> same actions
+(bit-exact), same rollout buffer, same losses / grad norms and same parameters."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle import loop
+
+
+def _params(tr):
+    out = {}
+    for mk, d in (("policy", tr.pol), ("critic", tr.cri)):
+        for k, v in d.items():
+            out[f"{mk}.{k}"] = v.detach().numpy()
+    return out
+
+
+@pytest.mark.parametrize("tag,env_id", [("cartpole", "CartPole-v1"), ("cartpole_c1", "CartPole-v1")])
+def test_oracle_reproduces_reference_trace(tag, env_id):
+    d = np.load(os.path.join(GOLDEN, f"trace_{tag}.npz"), allow_pickle=True)
+    cfg = loop.cfg_from_flags(str(d["meta/flags"]))
+    tr = loop.Trainer(cfg, env_id, int(d["meta/env_num"]))
+    for k, v in _params(tr).items():
+        assert np.array_equal(v, d[f"init/{k}"]), k  # same init stream as the reference
+    for it in range(int(d["meta/iters"])):
+        tr.rollout()
+        b = tr.buf
+        assert np.array_equal(b.actions, d[f"it{it}/actions"])  # bit-exact sampling
+        assert np.array_equal(b.obs, d[f"it{it}/policy_obs"])   # bit-exact trajectories
+        assert np.array_equal(b.rewards, d[f"it{it}/rewards"])
+        assert np.array_equal(b.masks, d[f"it{it}/masks"])
+        np.testing.assert_allclose(b.action_log_probs, d[f"it{it}/action_log_probs"], rtol=0, atol=1e-6)
+        tr.compute_returns()
+        np.testing.assert_allclose(b.value_preds, d[f"it{it}/value_preds"], rtol=0, atol=1e-5)
+        np.testing.assert_allclose(b.returns[:-1], d[f"it{it}/returns"][:-1], rtol=1e-5, atol=1e-5)
+        updates, perms = tr.train()
+        assert np.array_equal(perms, d[f"it{it}/perms"])
+        np.testing.assert_allclose(tr.last_adv, d[f"it{it}/advantages"], rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(updates, d[f"it{it}/updates"], rtol=1e-4, atol=1e-6)
+        tr.after_update()
+        for k, v in _params(tr).items():
+            np.testing.assert_allclose(v, d[f"it{it}/params/{k}"], rtol=1e-4, atol=1e-6, err_msg=k)
+        np.testing.assert_allclose(tr.vn.state(), d[f"it{it}/vn_after_update"], rtol=1e-6)

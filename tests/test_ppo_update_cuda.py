@@ -1,0 +1,147 @@
+"""Fused PPO update (orl_ppo_fwdbwd / reduce / apply) against the torch-CPU oracle and the
+reference's golden traces.  Tolerance: fp32 losses within 1e-4 relative (north_star), gradients
+and parameters compared through the oracle on identical inputs."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(d, flags_extra=()):
+    import torch
+
+    from openrl_b200.algorithms.ppo import PPOAlgorithm
+    from openrl_b200.buffers import NormalReplayBuffer
+    from test_rollout_cuda import _product
+
+    flags = str(d["meta/flags"]).split() + list(flags_extra)
+    cfg, env, net, agent = _product("CartPole-v1", int(d["meta/env_num"]), flags, golden=d)
+    trainer = PPOAlgorithm(cfg, net.module, agent_num=1, device=net.device)
+    buf = NormalReplayBuffer(cfg, 1, env.observation_space, env.action_space, device=net.device)
+    return cfg, net, trainer, buf
+
+
+def _load_buffer(buf, d, it):
+    import torch
+
+    b = buf.data
+    g = lambda k: torch.from_numpy(d[f"it{it}/{k}"]).cuda()
+    b.policy_obs.copy_(g("policy_obs"))
+    b.actions.copy_(g("actions"))
+    b.action_log_probs.copy_(g("action_log_probs"))
+    b.rewards.copy_(g("rewards"))
+    b.masks.copy_(g("masks"))
+    b.active_masks.copy_(g("active_masks"))
+    b.value_preds.copy_(g("value_preds"))
+
+
+@pytest.mark.parametrize("tag", ["cartpole", "cartpole_c1"])
+def test_first_iteration_updates_match_reference(cuda, tag):
+    """Golden rollout buffer of iteration 0 -> GAE kernel -> all updates of the iteration; compare
+    the 6 scalars of every update with the reference's (ppo.py:166-176) and the resulting
+    parameters / ValueNorm state."""
+    import torch
+
+    d = np.load(os.path.join(GOLDEN, f"trace_{tag}.npz"), allow_pickle=True)
+    cfg, net, trainer, buf = _setup(d)
+    _load_buffer(buf, d, 0)
+    vn = net.module.get_critic_value_normalizer()
+    buf.data.compute_returns(buf.data.value_preds[-1].clone(), vn)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(buf.data.returns.cpu().numpy()[:-1], d["it0/returns"][:-1], rtol=1e-6, atol=1e-6)
+    perms = d["it0/perms"]
+    T, N = cfg.episode_length, int(d["meta/env_num"])
+    total = T * N
+    mb = total // cfg.num_mini_batch
+    want = d["it0/updates"]
+    got = []
+    trainer.lrs.copy_(torch.tensor([cfg.lr, cfg.critic_lr]))
+    u = 0
+    for e in range(cfg.ppo_epoch):
+        perm = torch.from_numpy(perms[e]).cuda()
+        for i in range(cfg.num_mini_batch):
+            trainer.train_info.zero_()
+            trainer.ppo_update(buf.data, mb, perm[i * mb:(i + 1) * mb].contiguous())
+            got.append(trainer.train_info.cpu().numpy().copy())
+            u += 1
+    got = np.array(got, np.float64)
+    # order of the reference tuple: value_loss, critic_grad_norm, policy_loss, dist_entropy, actor_grad_norm, ratio
+    for col, name in enumerate(["value_loss", "critic_grad_norm", "policy_loss", "dist_entropy", "actor_grad_norm", "ratio"]):
+        np.testing.assert_allclose(got[:, col], want[:, col], rtol=1e-4, atol=2e-6, err_msg=name)
+    for mk in ("policy", "critic"):
+        for k, v in net.module.models[mk].state_dict().items():
+            gk = f"it0/params/{mk}.{k}"
+            if gk in d:
+                np.testing.assert_allclose(v.cpu().numpy(), d[gk], rtol=1e-3, atol=2e-6, err_msg=gk)
+    np.testing.assert_allclose(vn.state.cpu().numpy(), d["it0/vn_after_update"], rtol=1e-5)
+
+
+def test_gradients_match_oracle_autograd(cuda):
+    """True (unfolded) gradients written by orl_ppo_apply vs torch autograd on the oracle nets."""
+    import torch
+
+    from oracle import loop, nets, ppo as oppo
+
+    d = np.load(os.path.join(GOLDEN, "trace_cartpole.npz"), allow_pickle=True)
+    cfg, net, trainer, buf = _setup(d)
+    _load_buffer(buf, d, 0)
+    vn = net.module.get_critic_value_normalizer()
+    buf.data.compute_returns(buf.data.value_preds[-1].clone(), vn)
+    total = cfg.episode_length * int(d["meta/env_num"])
+    perm = torch.from_numpy(d["it0/perms"][0]).cuda()
+    mb = total // cfg.num_mini_batch
+    idx = perm[:mb].contiguous()
+    # oracle on the same minibatch
+    ocfg = loop.cfg_from_flags(str(d["meta/flags"]))
+    pol = {k[len("init/policy."):]: torch.from_numpy(d[k]).clone() for k in d.keys() if k.startswith("init/policy.")}
+    cri = {k[len("init/critic."):]: torch.from_numpy(d[k]).clone() for k in d.keys()
+           if k.startswith("init/critic.") and "value_normalizer" not in k}
+    opt_p, opt_c = oppo.make_optimizers(ocfg, pol, cri)
+    ovn = oppo.ValueNormState()
+    flat = lambda x: torch.from_numpy(x.reshape(total, -1))
+    ii = torch.from_numpy(d["it0/perms"][0][:mb])
+    batch = dict(critic_obs=flat(d["it0/policy_obs"][:-1])[ii], policy_obs=flat(d["it0/policy_obs"][:-1])[ii],
+                 actions=flat(d["it0/actions"])[ii], value_preds=flat(d["it0/value_preds"][:-1])[ii],
+                 returns=flat(d["it0/returns"][:-1])[ii], active_masks=flat(d["it0/active_masks"][:-1])[ii],
+                 old_logp=flat(d["it0/action_log_probs"])[ii], adv=flat(d["it0/advantages"])[ii],
+                 action_masks=flat(d["it0/action_masks"][:-1])[ii])
+    oppo.ppo_update(ocfg, pol, cri, opt_p, opt_c, ovn, batch)
+    trainer.lrs.copy_(torch.tensor([cfg.lr, cfg.critic_lr]))
+    trainer.ppo_update(buf.data, mb, idx)
+    torch.cuda.synchronize()
+    grads = trainer.grads.cpu().numpy()
+    for net_i, params in ((0, pol), (1, cri)):
+        want = np.concatenate([p.grad.numpy().reshape(-1) for p in params.values()])
+        got = grads[net_i, :want.size]
+        # clip_grad_norm_ rescaled the oracle's .grad in place; undo through the norm ratio
+        scale = np.linalg.norm(got) / max(np.linalg.norm(want), 1e-30)
+        np.testing.assert_allclose(got, want * scale, rtol=2e-3, atol=2e-6 * np.abs(got).max())
+        assert abs(scale - 1.0) < 1e-3 or np.linalg.norm(got) > cfg.max_grad_norm
+
+
+def test_whole_buffer_minibatch_equals_permuted_minibatch(cuda):
+    """num_mini_batch == 1: the contiguous (indices=NULL) path gives the same update as any
+    permutation of all rows (sum over rows), to fp32 reassociation."""
+    import torch
+
+    d = np.load(os.path.join(GOLDEN, "trace_cartpole_c1.npz"), allow_pickle=True)
+    res = []
+    for use_perm in (False, True):
+        cfg, net, trainer, buf = _setup(d)
+        _load_buffer(buf, d, 0)
+        vn = net.module.get_critic_value_normalizer()
+        buf.data.compute_returns(buf.data.value_preds[-1].clone(), vn)
+        total = cfg.episode_length * int(d["meta/env_num"])
+        trainer.lrs.copy_(torch.tensor([cfg.lr, cfg.critic_lr]))
+        trainer.train_info.zero_()
+        if use_perm:
+            trainer.ppo_update(buf.data, total, torch.from_numpy(d["it0/perms"][0]).cuda())
+        else:
+            trainer.ppo_update(buf.data, total, None, 0, mb_stats=buf.data.gae_stats[5:8])
+        res.append((trainer.train_info.cpu().numpy().copy(), net.module.models["policy"].flat_params.cpu().numpy().copy()))
+    np.testing.assert_allclose(res[0][0], res[1][0], rtol=2e-5, atol=1e-7)
+    np.testing.assert_allclose(res[0][1], res[1][1], rtol=1e-4, atol=1e-6)

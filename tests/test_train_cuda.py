@@ -1,0 +1,90 @@
+"""End-to-end through the public API (make -> PPONet -> PPOAgent.train) against the reference's
+golden traces: same seeds -> same trajectories (bit-exact actions) and fp32 losses within 1e-4
+relative over all recorded iterations; plus a learning-outcome check modelled on the reference's
+tests/test_examples/test_train_cartpole.py:39-54."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("tag", ["cartpole", "cartpole_c1"])
+def test_train_matches_reference_trace(cuda, tag):
+    import torch
+
+    from openrl_b200.utils.logger import Logger
+    from test_rollout_cuda import _product
+
+    d = np.load(os.path.join(GOLDEN, f"trace_{tag}.npz"), allow_pickle=True)
+    iters, N = int(d["meta/iters"]), int(d["meta/env_num"])
+    cfg, env, net, agent = _product("CartPole-v1", N, str(d["meta/flags"]).split(), golden=d)
+    logger = Logger(quiet=True)
+    agent.train(total_time_steps=cfg.episode_length * N * iters, logger=logger)
+    train_logs = [h[1] for h in logger.history if "value_loss" in h[1]]
+    assert len(train_logs) == iters
+    for it in range(iters):
+        want = d[f"it{it}/updates"].mean(axis=0)
+        got = train_logs[it]
+        for col, name in enumerate(["value_loss", "critic_grad_norm", "policy_loss", "dist_entropy", "actor_grad_norm", "ratio"]):
+            np.testing.assert_allclose(got[name], want[col], rtol=1e-4, atol=2e-6, err_msg=f"it{it} {name}")
+    b = agent.driver.buffer.data
+    last = iters - 1
+    # the buffer still holds the last rollout: bit-exact trajectories after `last` parameter updates
+    assert np.array_equal(b.actions.cpu().numpy(), d[f"it{last}/actions"])
+    assert np.array_equal(b.policy_obs.cpu().numpy()[1:], d[f"it{last}/policy_obs"][1:])
+    for mk in ("policy", "critic"):
+        for k, v in net.module.models[mk].state_dict().items():
+            gk = f"it{last}/params/{mk}.{k}"
+            if gk in d:
+                np.testing.assert_allclose(v.cpu().numpy(), d[gk], rtol=2e-3, atol=5e-6, err_msg=gk)
+
+
+def test_cartpole_learns(cuda):
+    """Reference bar (tests/test_examples/test_train_cartpole.py:41-53): 9 envs, default config,
+    20 000 steps, greedy return >= 450.  Here: fast mode (device RNG), same budget."""
+    from openrl_b200.configs.config import create_config_parser
+    from openrl_b200.envs.common import make
+    from openrl_b200.modules.common import PPONet
+    from openrl_b200.runners.common import PPOAgent
+
+    cfg = create_config_parser().parse_args(["--seed", "0"])
+    cfg.quiet = True
+    env = make("CartPole-v1", env_num=9)
+    agent = PPOAgent(PPONet(env, cfg=cfg, device="cuda:0"))
+    agent.train(total_time_steps=20000)
+    ev = make("CartPole-v1", env_num=9)
+    obs, _ = ev.reset(seed=123)
+    totals = np.zeros(9)
+    finished = np.zeros(9, bool)
+    for _ in range(500):
+        action, _ = agent.act(obs, deterministic=True)
+        obs, r, done, _ = ev.step(action)
+        totals += r[:, 0, 0] * (~finished)
+        finished |= done[:, 0]
+        if finished.all():
+            break
+    assert totals.mean() >= 450, totals
+
+
+def test_callback_per_step_contract(cuda):
+    """n_calls * env_num == num_time_steps and early stop (reference tests/test_callbacks/test_callbacks.py:94-101)."""
+    from openrl_b200.configs.config import create_config_parser
+    from openrl_b200.envs.common import make
+    from openrl_b200.modules.common import PPONet
+    from openrl_b200.runners.common import PPOAgent
+    from openrl_b200.utils.callbacks import StopTrainingOnMaxSteps
+
+    cfg = create_config_parser().parse_args(["--episode_length", "16", "--ppo_epoch", "1"])
+    cfg.quiet = True
+    env = make("CartPole-v1", env_num=4)
+    agent = PPOAgent(PPONet(env, cfg=cfg, device="cuda:0"))
+    cb = StopTrainingOnMaxSteps(40)
+    agent.train(total_time_steps=16 * 4 * 10, callback=cb)
+    assert cb.n_calls == 40
+    assert cb.n_calls * 4 == agent.num_time_steps
+    assert "obs" in cb.locals and cb.locals["obs"].shape == (4, 1, 4)
+    assert cb.locals["dones"].shape == (4, 1)
