@@ -231,15 +231,19 @@ typedef struct OrlPpoArgs {
     int32_t* adam_steps;         /* (2) step counters {policy, critic}, incremented by apply */
     const float* lrs;            /* (2) {lr, critic_lr} (device so that CUDA graphs can be replayed) */
     float clip_param, entropy_coef, value_loss_coef, huber_delta, max_grad_norm;
-    float adam_beta1, adam_beta2, adam_eps, weight_decay, vn_beta;
+    float adam_beta1, adam_beta2, adam_eps, weight_decay;
+    float reserved0;
+    double vn_beta;              /* ValueNorm beta (0.99999); double: (1 - beta) is taken in double like the reference */
     float* partials;             /* (2*grid_per_net, stride) scratch */
     float* folded;               /* (2, stride): reduced folded gradients + loss sums */
-    float* grads;                /* (2, stride): true gradients (written by apply; for inspection) */
+    float* grads;                /* (2, orl_ppo_grads_stride): true gradients, parameter layout (written by apply) */
     float* train_info;           /* (6) += {value_loss, critic_grad_norm, policy_loss, dist_entropy,
                                              actor_grad_norm, ratio}  (ppo.py:430-451) */
 } OrlPpoArgs;
 /* floats per partial row for given shapes (>= folded gradient size + 8 loss slots, multiple of 4) */
 int orl_ppo_stride(int obs_dim, int critic_obs_dim, int n_actions);
+/* floats per net row of `grads` (>= parameter count of the larger net, multiple of 4) */
+int orl_ppo_grads_stride(int obs_dim, int critic_obs_dim, int n_actions);
 /* number of parameters of one MLP net with head width n (layout in DESIGN.md) */
 int orl_net_param_count(int obs_dim, int n_out);
 int orl_ppo_fwdbwd(const OrlPpoArgs* args, void* stream);

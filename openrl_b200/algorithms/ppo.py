@@ -35,7 +35,8 @@ class PPOAlgorithm:
         dev = self.device
         self.partials = torch.zeros(2 * self.grid_per_net, self.stride, dtype=torch.float32, device=dev)
         self.folded = torch.zeros(2, self.stride, dtype=torch.float32, device=dev)
-        self.grads = torch.zeros(2, self.stride, dtype=torch.float32, device=dev)
+        self.grads_stride = self._lib.orl_ppo_grads_stride(self.d, self.dc, self.n)
+        self.grads = torch.zeros(2, self.grads_stride, dtype=torch.float32, device=dev)
         self.train_info = torch.zeros(6, dtype=torch.float32, device=dev)
         self.lrs = torch.zeros(2, dtype=torch.float32, device=dev)
         self.mb_stats = torch.zeros(3, dtype=torch.float64, device=dev)

@@ -29,6 +29,11 @@ __host__ __device__ inline int ppo_stride(int obs_dim, int critic_obs_dim, int n
     return ((a > b ? a : b) + N_LOSS + 3) & ~3;
 }
 
+__host__ __device__ inline int ppo_grads_stride(int obs_dim, int critic_obs_dim, int n_actions) {
+    const int a = orl::net_offsets(obs_dim, n_actions).total, b = orl::net_offsets(critic_obs_dim, 1).total;
+    return ((a > b ? a : b) + 3) & ~3;
+}
+
 struct WgMap { int jb, kb, mg, MG; bool active; };
 __device__ __forceinline__ WgMap wg_map(int JB, int KB) {
     WgMap m;
@@ -123,10 +128,11 @@ __device__ __forceinline__ float apply_adv_norm(const AdvNorm& r, float a) {
 
 // ValueNorm.update (valuenorm.py:59-76) applied to the old state with this minibatch's moments.
 __device__ __forceinline__ void vn_updated(const float* __restrict__ vn_state, const double* __restrict__ mb_stats,
-                                           double batch_rows, float beta, float (&out)[3]) {
+                                           double batch_rows, double beta_d, float (&out)[3]) {
     const float bm = (float)(mb_stats[0] / batch_rows);
     const float bsq = (float)(mb_stats[1] / batch_rows);
-    const float omw = (float)(1.0 - (double)beta);
+    const float beta = (float)beta_d;
+    const float omw = (float)(1.0 - beta_d);
     out[0] = __fadd_rn(__fmul_rn(vn_state[0], beta), __fmul_rn(bm, omw));
     out[1] = __fadd_rn(__fmul_rn(vn_state[1], beta), __fmul_rn(bsq, omw));
     out[2] = __fadd_rn(__fmul_rn(vn_state[2], beta), __fmul_rn(1.0f, omw));
@@ -392,7 +398,7 @@ __global__ void __launch_bounds__(1024) ppo_apply_kernel(const OrlPpoArgs a) {
     float* am = net == 0 ? a.policy_adam_m : a.critic_adam_m;
     float* av = net == 0 ? a.policy_adam_v : a.critic_adam_v;
     const float* f = a.folded + (size_t)net * stride;
-    float* grads = a.grads + (size_t)net * stride;
+    float* grads = a.grads + (size_t)net * ppo_grads_stride(a.obs_dim, a.critic_obs_dim, a.n_actions);
     __shared__ float red[32];
     __shared__ float s_norm;
     const int tid = threadIdx.x;
@@ -523,6 +529,10 @@ int check_ppo_args(const OrlPpoArgs& a) {
 
 extern "C" int orl_ppo_stride(int obs_dim, int critic_obs_dim, int n_actions) {
     return ppo_stride(obs_dim, critic_obs_dim, n_actions);
+}
+
+extern "C" int orl_ppo_grads_stride(int obs_dim, int critic_obs_dim, int n_actions) {
+    return ppo_grads_stride(obs_dim, critic_obs_dim, n_actions);
 }
 
 extern "C" int orl_net_param_count(int obs_dim, int n_out) { return orl::net_offsets(obs_dim, n_out).total; }

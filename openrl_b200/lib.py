@@ -123,7 +123,8 @@ class OrlPpoArgs(ctypes.Structure):
         ("policy_adam_m", _P), ("policy_adam_v", _P), ("critic_adam_m", _P), ("critic_adam_v", _P),
         ("adam_steps", _P), ("lrs", _P),
         ("clip_param", _F), ("entropy_coef", _F), ("value_loss_coef", _F), ("huber_delta", _F), ("max_grad_norm", _F),
-        ("adam_beta1", _F), ("adam_beta2", _F), ("adam_eps", _F), ("weight_decay", _F), ("vn_beta", _F),
+        ("adam_beta1", _F), ("adam_beta2", _F), ("adam_eps", _F), ("weight_decay", _F), ("reserved0", _F),
+        ("vn_beta", _D),
         ("partials", _P), ("folded", _P), ("grads", _P), ("train_info", _P),
     ]
 
@@ -134,6 +135,7 @@ _SIGNATURES.update({
     "orl_env_step": [_I, _I, _I, _P, _P, _P, _P, _I, _c.c_uint64, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "orl_critic_values": [_P, _I, _I, _P, _P, _L, _P],
     "orl_ppo_stride": [_I, _I, _I],
+    "orl_ppo_grads_stride": [_I, _I, _I],
     "orl_net_param_count": [_I, _I],
     "orl_ppo_fwdbwd": [_c.POINTER(OrlPpoArgs), _P],
     "orl_ppo_reduce": [_c.POINTER(OrlPpoArgs), _P],

@@ -97,9 +97,8 @@ def test_gradients_match_oracle_autograd(cuda):
     idx = perm[:mb].contiguous()
     # oracle on the same minibatch
     ocfg = loop.cfg_from_flags(str(d["meta/flags"]))
-    pol = {k[len("init/policy."):]: torch.from_numpy(d[k]).clone() for k in d.keys() if k.startswith("init/policy.")}
-    cri = {k[len("init/critic."):]: torch.from_numpy(d[k]).clone() for k in d.keys()
-           if k.startswith("init/critic.") and "value_normalizer" not in k}
+    pol = {k: torch.from_numpy(d["init/policy." + k]).clone() for k, _ in net.module.models["policy"].named_parameters()}
+    cri = {k: torch.from_numpy(d["init/critic." + k]).clone() for k, _ in net.module.models["critic"].named_parameters()}
     opt_p, opt_c = oppo.make_optimizers(ocfg, pol, cri)
     ovn = oppo.ValueNormState()
     flat = lambda x: torch.from_numpy(x.reshape(total, -1))
