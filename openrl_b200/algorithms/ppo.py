@@ -51,6 +51,9 @@ class PPOAlgorithm:
             if getattr(cfg, name, False):
                 raise NotImplementedError(f"cfg.{name} is not built into the CUDA update yet (SURVEY.md §8f)")
         self.gpu_launches = 0
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+        self._lrs_host = None
 
     def prep_rollout(self):
         pass
@@ -111,12 +114,26 @@ class PPOAlgorithm:
 
     def train(self, buffer, turn_on=True):
         """train_ppo (ppo.py:383-458).  `buffer` is the device ReplayData whose returns/advantages
-        were produced by `compute_returns` (orl_gae)."""
+        were produced by `compute_returns` (orl_gae).  Returns the averaged metrics (one D2H read)."""
+        self.train_async(buffer)
+        return self.read_train_info()
+
+    def read_train_info(self):
+        num_updates = self.ppo_epoch * self.num_mini_batch
+        info = (self.train_info / num_updates).cpu().numpy()
+        self.d2h_bytes += info.nbytes
+        keys = ["value_loss", "critic_grad_norm", "policy_loss", "dist_entropy", "actor_grad_norm", "ratio"]
+        return {k: float(v) for k, v in zip(keys, info)}
+
+    def train_async(self, buffer):
+        """All launches of one training phase, no host read-back."""
         buf = buffer
         m = self.algo_module
-        self.lrs.copy_(torch.tensor([m.optimizers["policy"].param_groups[0]["lr"],
-                                     m.optimizers["critic"].param_groups[0]["lr"]], dtype=torch.float32),
-                       non_blocking=True)
+        lrs = (m.optimizers["policy"].param_groups[0]["lr"], m.optimizers["critic"].param_groups[0]["lr"])
+        if lrs != self._lrs_host:  # H2D only when the schedule changed them
+            self.lrs.copy_(torch.tensor(lrs, dtype=torch.float32), non_blocking=True)
+            self._lrs_host = lrs
+            self.h2d_bytes += 8
         self.train_info.zero_()
         if self.world_size > 1:
             dist.all_reduce(buf.gae_stats)  # global advantage / return moments (ppo.py:402-409 semantics)
@@ -126,6 +143,7 @@ class PPOAlgorithm:
         for _ in range(self.ppo_epoch):
             if self.cfg.parity_mode:
                 perm = torch.randperm(total).to(self.device, non_blocking=True)  # global CPU generator, like the reference
+                self.h2d_bytes += total * 8
             elif whole:
                 perm = None
             else:
@@ -136,7 +154,3 @@ class PPOAlgorithm:
                     self.ppo_update(buf, mb, perm, 0, mb_stats=buf.gae_stats[5:8])
                 else:
                     self.ppo_update(buf, mb, perm[i * mb:(i + 1) * mb])
-        num_updates = self.ppo_epoch * self.num_mini_batch
-        info = (self.train_info / num_updates).cpu().numpy()
-        keys = ["value_loss", "critic_grad_norm", "policy_loss", "dist_entropy", "actor_grad_norm", "ratio"]
-        return {k: float(v) for k, v in zip(keys, info)}

@@ -40,6 +40,9 @@ class OnPolicyDriver:
         self._global_step = 0
         self.rng_counter = torch.zeros(1, dtype=torch.int64, device=self.device)
         self.gpu_launches = 0
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+        self.phase_events = None  # set to a list by bench.py to collect (name, start, end) CUDA events
 
     # -- reference surface -------------------------------------------------------------------
     def run(self):
@@ -76,7 +79,36 @@ class OnPolicyDriver:
             self.trainer.algo_module.lr_decay(self.episode, self.episodes)
         self.compute_returns()
         self.trainer.prep_training()
-        return self.trainer.train(self.buffer.data)
+        with self._phase("update"):
+            return self.trainer.train(self.buffer.data)
+
+    def device_iteration(self):
+        """One collect + update iteration as pure device work (no host read-back, no logging):
+        what bench.py times as `value`."""
+        self._rollout_launch()
+        self.compute_returns()
+        with self._phase("update"):
+            self.trainer.train_async(self.buffer.data)
+        with self._phase("after_update"):
+            self.buffer.after_update()
+
+    class _Phase:
+        def __init__(self, drv, name):
+            self.drv, self.name = drv, name
+
+        def __enter__(self):
+            if self.drv.phase_events is not None:
+                self.e0 = torch.cuda.Event(enable_timing=True)
+                self.e0.record()
+
+        def __exit__(self, *a):
+            if self.drv.phase_events is not None:
+                e1 = torch.cuda.Event(enable_timing=True)
+                e1.record()
+                self.drv.phase_events.append((self.name, self.e0, e1))
+
+    def _phase(self, name):
+        return OnPolicyDriver._Phase(self, name)
 
     # -- rollout -----------------------------------------------------------------------------
     def _rollout_args(self, t_begin, t_end, noise):
@@ -108,22 +140,29 @@ class OnPolicyDriver:
         host = torch.empty(self.episode_length, B, n, dtype=torch.float32, pin_memory=True)
         for t in range(self.episode_length):
             host[t].exponential_(1)
+        self.h2d_bytes += host.numel() * 4
         return host.to(self.device, non_blocking=True)
+
+    def _rollout_launch(self):
+        noise = self._draw_noise() if self.cfg.parity_mode else None
+        with self._phase("rollout"):
+            lib.check(self._lib.orl_rollout(self._rollout_args(0, self.episode_length, noise), lib.current_stream()),
+                      "orl_rollout")
+        self.gpu_launches += 2
+        self.agent.num_time_steps += self.envs.parallel_env_num * self.episode_length
 
     def actor_rollout(self):
         cb = self.callback
         if cb is not None:
             cb.on_rollout_start()
         self.trainer.prep_rollout()
-        noise = self._draw_noise() if self.cfg.parity_mode else None
         T, N = self.episode_length, self.envs.parallel_env_num
         per_step = cb is not None and getattr(cb, "needs_per_step", True)
         s = lib.current_stream()
         if not per_step:
-            lib.check(self._lib.orl_rollout(self._rollout_args(0, T, noise), s), "orl_rollout")
-            self.gpu_launches += 2
-            self.agent.num_time_steps += N * T
+            self._rollout_launch()
         else:
+            noise = self._draw_noise() if self.cfg.parity_mode else None
             d = self.buffer.data
             for step in range(T):
                 lib.check(self._lib.orl_rollout(self._rollout_args(step, step + 1, noise), s), "orl_rollout")
@@ -155,8 +194,10 @@ class OnPolicyDriver:
         d = self.buffer.data
         cri = self.trainer.algo_module.models["critic"]
         rows = (self.episode_length + 1) * d.n_rollout_threads * d.num_agents
-        lib.check(self._lib.orl_critic_values(lib.ptr(cri.flat_params), cri.obs_dim, cri.activation_id,
-                                              lib.ptr(d.critic_obs), lib.ptr(d.value_preds), rows,
-                                              lib.current_stream()), "orl_critic_values")
-        self.buffer.compute_returns(None, self.trainer.algo_module.get_critic_value_normalizer())
+        with self._phase("critic"):
+            lib.check(self._lib.orl_critic_values(lib.ptr(cri.flat_params), cri.obs_dim, cri.activation_id,
+                                                  lib.ptr(d.critic_obs), lib.ptr(d.value_preds), rows,
+                                                  lib.current_stream()), "orl_critic_values")
+        with self._phase("gae"):
+            self.buffer.compute_returns(None, self.trainer.algo_module.get_critic_value_normalizer())
         self.gpu_launches += 2

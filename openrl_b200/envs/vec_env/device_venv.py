@@ -22,13 +22,13 @@ from .. import _kinds
 from ... import lib, spaces
 
 
-def _pcg64_streams(seed, n):
+def _pcg64_streams(seed, n, index_offset=0):
     """Host-side seeding only (SeedSequence -> PCG64 initial state, sync_venv.py:137 +
     gymnasium/utils/seeding.py): env i gets np.random.PCG64(SeedSequence(seed + i*10086))."""
     out = np.zeros((4, n), np.uint64)
     mask = (1 << 64) - 1
     for i in range(n):
-        s = None if seed is None else seed + i * 10086
+        s = None if seed is None else seed + (index_offset + i) * 10086
         st = np.random.PCG64(np.random.SeedSequence(s)).state["state"]
         out[0, i], out[1, i] = st["state"] >> 64, st["state"] & mask
         out[2, i], out[3, i] = st["inc"] >> 64, st["inc"] & mask
@@ -36,9 +36,12 @@ def _pcg64_streams(seed, n):
 
 
 class DeviceVecEnv:
-    def __init__(self, env_id, env_num, device="cuda:0", seed=None, reset_table=None):
+    def __init__(self, env_id, env_num, device="cuda:0", seed=None, reset_table=None, env_index_offset=0):
         spec = _kinds.ENV_SPECS[env_id]
         self.env_name = env_id
+        # global index of env 0 when a larger vec-env is sharded over ranks (multi-GPU): env i is seeded
+        # seed + (offset + i)*10086, i.e. exactly the stream it would own in the unsharded vec-env
+        self.env_index_offset = int(env_index_offset)
         self.kind = spec["kind"]
         self.parallel_env_num = int(env_num)
         self.agent_num = spec["agents"]
@@ -72,7 +75,7 @@ class DeviceVecEnv:
     # -- seeding / reset -------------------------------------------------------------------
     def _seed_streams(self, seed):
         if self.kind == lib.ENV_CARTPOLE:
-            st = _pcg64_streams(seed, self.parallel_env_num)
+            st = _pcg64_streams(seed, self.parallel_env_num, self.env_index_offset)
             self.env_u64.copy_(torch.from_numpy(st.view(np.int64)))
         self.rng_seed = int(seed if seed is not None else np.random.SeedSequence().entropy % (1 << 63))
 
@@ -134,6 +137,7 @@ class DeviceVecEnv:
         self._total_step += T * N
         per_agent = rewards.mean(dim=1).sum(dim=0).reshape(-1)  # (A,)
         vals = per_agent.cpu().numpy()
+        self.d2h_bytes = getattr(self, "d2h_bytes", 0) + vals.nbytes + 32
         info = {f"agent_{i}/rollout_episode_reward": float(v) for i, v in enumerate(vals)}
         info["FPS"] = int(self._total_step / max(time.time() - self._start_time, 1e-9))
         info["rollout_episode_reward"] = float(np.mean(vals))
