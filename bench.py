@@ -202,7 +202,8 @@ def run_ours(args):
     cfg2.log_interval = 1
     agent2.train(total_time_steps=N_ENVS * T * 3, logger=Logger(quiet=True))  # warm-up call
     barrier()
-    cfg2.log_interval = 1
+    h2d0 = agent2.driver.trainer.h2d_bytes
+    d2h0 = (agent2.driver.trainer.d2h_bytes, getattr(env2, "d2h_bytes", 0))
     t0 = time.perf_counter()
     agent2.train(total_time_steps=N_ENVS * T * args.steps, logger=Logger(quiet=True))
     barrier()
@@ -212,8 +213,8 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
     tr2, dr2 = agent2.driver.trainer, agent2.driver
-    h2d = (tr2.h2d_bytes + dr2.h2d_bytes) / args.steps
-    d2h = (tr2.d2h_bytes + dr2.d2h_bytes + getattr(env2, "d2h_bytes", 0)) / args.steps
+    h2d = (tr2.h2d_bytes - h2d0 + dr2.h2d_bytes) / args.steps
+    d2h = (tr2.d2h_bytes - d2h0[0] + dr2.d2h_bytes + getattr(env2, "d2h_bytes", 0) - d2h0[1]) / args.steps
 
     if rank != 0:
         if world > 1:

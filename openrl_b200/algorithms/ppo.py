@@ -12,9 +12,7 @@ permutation is needed at all (a minibatch that is the whole buffer is a sum over
 """
 import numpy as np
 import torch
-import torch.distributed as dist
-
-from .. import lib
+from .. import lib, parallel
 
 
 class PPOAlgorithm:
@@ -23,7 +21,7 @@ class PPOAlgorithm:
         self.algo_module = init_module
         self.agent_num = agent_num
         self.device = torch.device(device) if not isinstance(device, torch.device) else device
-        self.world_size = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.world_size = parallel.world_size()
         self.ppo_epoch, self.num_mini_batch = cfg.ppo_epoch, cfg.num_mini_batch
         self.clip_param = cfg.clip_param
         self._lib = lib.load()
@@ -101,14 +99,12 @@ class PPOAlgorithm:
                                             lib.ptr(buf.active_masks), lib.ptr(self.mb_stats), s), "orl_minibatch_stats")
             mb_stats = self.mb_stats
             self.gpu_launches += 1
-            if self.world_size > 1:
-                dist.all_reduce(mb_stats)
+            parallel.allreduce_sum_(mb_stats)
         a = self._args(buf, batch_rows, indices, row_begin)
         a.mb_stats = lib.ptr(mb_stats)
         lib.check(L.orl_ppo_fwdbwd(a, s), "orl_ppo_fwdbwd")
         lib.check(L.orl_ppo_reduce(a, s), "orl_ppo_reduce")
-        if self.world_size > 1:
-            dist.all_reduce(self.folded)  # the single gradient-bucket all-reduce of the update
+        parallel.allreduce_sum_(self.folded)  # the single gradient-bucket all-reduce of the update
         lib.check(L.orl_ppo_apply(a, s), "orl_ppo_apply")
         self.gpu_launches += 3
 
@@ -135,8 +131,7 @@ class PPOAlgorithm:
             self._lrs_host = lrs
             self.h2d_bytes += 8
         self.train_info.zero_()
-        if self.world_size > 1:
-            dist.all_reduce(buf.gae_stats)  # global advantage / return moments (ppo.py:402-409 semantics)
+        parallel.allreduce_sum_(buf.gae_stats)  # global advantage / return moments (ppo.py:402-409 semantics)
         total = buf.episode_length * buf.n_rollout_threads * buf.num_agents
         mb = total // self.num_mini_batch
         whole = self.num_mini_batch == 1

@@ -40,16 +40,27 @@ class PPOAgent:
         self._total_time_steps = total_time_steps
         self.config = {"cfg": self._cfg, "num_agents": self.agent_num, "run_dir": self.run_dir, "envs": self._env,
                        "device": self.net.device}
-        trainer = train_algo_class(cfg=self._cfg, init_module=self.net.module, device=self.net.device,
-                                   agent_num=self.agent_num)
-        buffer = NormalReplayBuffer(self._cfg, self.agent_num, self._env.observation_space, self._env.action_space,
-                                    data_client=None, device=self.net.device)
+        # device objects (scratch, rollout buffer) are kept across train() calls while the shapes
+        # and classes are unchanged: a second call starts without allocations
+        key = (train_algo_class, driver_class, self._cfg.episode_length, self._cfg.n_rollout_threads, self.agent_num,
+               id(self._env), self._cfg.ppo_epoch, self._cfg.num_mini_batch)
+        if self.driver is not None and getattr(self, "_driver_key", None) == key:
+            trainer, buffer = self.driver.trainer, self.driver.buffer
+        else:
+            trainer = train_algo_class(cfg=self._cfg, init_module=self.net.module, device=self.net.device,
+                                       agent_num=self.agent_num)
+            buffer = NormalReplayBuffer(self._cfg, self.agent_num, self._env.observation_space, self._env.action_space,
+                                        data_client=None, device=self.net.device)
+        self._driver_key = key
         if logger is None:
             logger = Logger(cfg=self._cfg, project_name=self.project_name, quiet=getattr(self._cfg, "quiet", False))
         self._logger = logger
         callback = self._setup_callback(callback)
+        prev = self.driver
         driver = driver_class(config=self.config, trainer=trainer, buffer=buffer, agent=self, client=self.client,
                               rank=self.rank, world_size=self.world_size, logger=logger, callback=callback)
+        if prev is not None and prev.trainer is trainer:
+            driver.rng_counter = prev.rng_counter  # keep the device noise stream moving forward
         self.driver = driver
         if callback is not None:
             callback.on_training_start(locals(), globals())
