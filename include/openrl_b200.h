@@ -199,6 +199,9 @@ int orl_critic_values(const float* critic_params, int obs_dim, int activation_id
 #define ORL_PPO_VALUENORM 16          /* cfg.use_valuenorm (normaliser present) */
 #define ORL_PPO_ADV_NORMALIZE 32      /* cfg.use_adv_normalize (ppo.py:402-403) */
 #define ORL_PPO_MAX_GRAD_NORM 64      /* cfg.use_max_grad_norm */
+#define ORL_PPO_TF32 128              /* fast mode: the 64x64 GEMMs of the trunk on tcgen05 tensor cores
+                                         (TF32 operands, FP32 accumulate in TMEM); obs widths <= 8.
+                                         Without it everything is fp32 FFMA (1e-4 loss parity mode). */
 
 typedef struct OrlPpoArgs {
     int32_t obs_dim;         /* d  policy obs width  (<= 64) */

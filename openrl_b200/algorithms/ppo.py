@@ -44,6 +44,9 @@ class PPOAlgorithm:
                       | (lib.PPO_VALUENORM if (cfg.use_valuenorm and cri.value_normalizer is not None) else 0)
                       | (lib.PPO_ADV_NORMALIZE if cfg.use_adv_normalize else 0)
                       | (lib.PPO_MAX_GRAD_NORM if cfg.use_max_grad_norm else 0))
+        self.use_tf32 = bool(getattr(cfg, "use_tf32", True)) and not cfg.parity_mode and max(self.d, self.dc) <= 8
+        if self.use_tf32:
+            self.flags |= lib.PPO_TF32
         for name in ("use_joint_action_loss", "dual_clip_ppo", "use_policy_vhead", "use_share_model", "use_popart",
                      "use_amp", "use_deepspeed", "use_naive_recurrent_policy", "use_recurrent_policy"):
             if getattr(cfg, name, False):

@@ -53,6 +53,9 @@ FLAGS = [
     ("use_attn", _bool, False), ("use_conv1d", _bool, False), ("use_influence_policy", _bool, False),
     # openrl_b200 additions (not in the reference): how sampling noise / minibatch order are drawn
     ("parity_mode", _bool, False),
+    # fast mode: 64x64 trunk GEMMs of the update on tcgen05 tensor cores (TF32 in, FP32 accumulate);
+    # ignored (fp32 FFMA everywhere) in parity_mode or when an observation is wider than 8
+    ("use_tf32", _bool, True),
 ]
 
 

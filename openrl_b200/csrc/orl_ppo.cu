@@ -527,6 +527,11 @@ int check_ppo_args(const OrlPpoArgs& a) {
 
 }  // namespace
 
+namespace orl {
+int ppo_stride_host(int obs_dim, int critic_obs_dim, int n_actions) { return ppo_stride(obs_dim, critic_obs_dim, n_actions); }
+int launch_ppo_fwdbwd_tc(const OrlPpoArgs& a, cudaStream_t st);
+}  // namespace orl
+
 extern "C" int orl_ppo_stride(int obs_dim, int critic_obs_dim, int n_actions) {
     return ppo_stride(obs_dim, critic_obs_dim, n_actions);
 }
@@ -545,6 +550,7 @@ extern "C" int orl_ppo_fwdbwd(const OrlPpoArgs* args, void* stream) {
                       a.returns && a.active_masks && a.gae_stats && a.mb_stats, "null rollout buffer");
     ORL_CHECK_ARG(!(a.flags & ORL_PPO_VALUENORM) || a.vn_state, "vn_state required with VALUENORM");
     ORL_CHECK_ARG(a.indices || (a.row_begin >= 0 && a.row_begin + a.batch_rows <= a.total_rows), "row range");
+    if (a.flags & ORL_PPO_TF32) return orl::launch_ppo_fwdbwd_tc(a, reinterpret_cast<cudaStream_t>(stream));
     const size_t smem = fwdbwd_smem_bytes(a.obs_dim, a.critic_obs_dim);
     static bool attr_set = false;
     if (!attr_set) {

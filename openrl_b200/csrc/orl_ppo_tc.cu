@@ -1,0 +1,495 @@
+// PPO minibatch forward+backward on the 5th-gen tensor cores (tcgen05, TF32 in / FP32 accumulate in
+// TMEM) — the "fast mode" sibling of ppo_fwdbwd_kernel (orl_ppo.cu), producing the same folded
+// partial gradients and loss sums.  Selected with ORL_PPO_TF32; obs widths <= 8 (CartPole, GridWorld).
+//
+// CTA = 128 threads = 128 tile rows: a thread owns one minibatch row, so every row-wise operation
+// (fc1 with K = d <= 8, LayerNorm forward/backward, head, loss) is thread-local in registers, and the
+// three 64-wide GEMMs of the row tile go to the tensor core, issued by one elected thread:
+//     GEMM1  Z3 [128x64]  = n1 [128x64]  . W3f^T            (M=128, N=64, K=64)    fwd fc3
+//     GEMM2  dN1[128x64]  = dZ3[128x64]  . W3f              (M=128, N=64, K=64)    bwd-data fc3
+//     GEMM3  G  [128x80] += [dZ3^T;dZ1^T][128x128] . [n1^T;X^T;1^T]^T  (M=128, N=80, K=128 rows)
+// GEMM3's accumulator stays in TMEM for the whole kernel: rows 0..63 are G3 = dZ3^T n1 (cols 0..63)
+// and db3 (col 72, the ones row); rows 64..127 are G1 = dZ1^T X (cols 64..64+d) and db1 (col 72).
+// Operands are staged by the row-owning threads in the canonical no-swizzle K-major layout
+// (orl_tc.cuh) — transposed operands are written with conflict-free scalar stores thanks to a
+// 16-byte pad on the panel stride.  GH = dL^T n3 (n x 64) is a small FFMA reduction.
+// TF32 operands are rounded to nearest on store (the MMA truncates); accumulation is fp32.
+#include <algorithm>
+
+#include "orl_mlp.cuh"
+#include "orl_tc.cuh"
+
+namespace orl {
+int ppo_stride_host(int obs_dim, int critic_obs_dim, int n_actions);
+}
+
+namespace {
+using namespace orl;
+using namespace orl::tc;
+
+constexpr int T_M = 128, T_NT = 128;
+constexpr int NB3 = 80;                       // rows of B3: 64 (n1^T) + 8 (X^T) + 8 (ones / zero)
+constexpr uint32_t LBO_A = 128 * 16 + 16;     // panel stride of 128-row tiles (padded)
+constexpr uint32_t LBO_B3 = NB3 * 16 + 16;
+constexpr uint32_t LBO_W = 64 * 16 + 16;
+constexpr int N_LOSS_TC = 8;
+
+__device__ __forceinline__ uint32_t poff(uint32_t lbo, int row, int col) { return (uint32_t)(col >> 2) * lbo + row * 16 + (col & 3) * 4; }
+__device__ __forceinline__ void pst(uint8_t* t, uint32_t lbo, int row, int col, float v) { *reinterpret_cast<float*>(t + poff(lbo, row, col)) = v; }
+__device__ __forceinline__ float pld(const uint8_t* t, uint32_t lbo, int row, int col) { return *reinterpret_cast<const float*>(t + poff(lbo, row, col)); }
+__device__ __forceinline__ uint64_t kdesc(const uint8_t* tile, uint32_t lbo, int k0) {
+    return desc_common(smem_u32(tile) + (uint32_t)(k0 >> 2) * lbo, lbo, 128);
+}
+
+struct AdvNormTc { float m0, s0, m1, s1; bool two; };
+
+template <bool POLICY>
+__device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, uint8_t* smem, int cta, int G, int stride) {
+    const int d = POLICY ? a.obs_dim : a.critic_obs_dim;
+    const int n = POLICY ? a.n_actions : 1;
+    const float* params = POLICY ? a.policy_params : a.critic_params;
+    const float* obs = POLICY ? a.policy_obs : a.critic_obs;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const NetOffsets po = net_offsets(d, n);
+
+    // ---- shared memory carve-up (all tensor-core tiles 128-byte aligned) ----
+    uint8_t* A12 = smem;                         // n1 -> dZ3 : rows m, cols 64
+    uint8_t* A3 = A12 + 16 * LBO_A;              // rows 0..63 dZ3^T, 64..127 dZ1^T ; cols m
+    uint8_t* B3 = A3 + 32 * LBO_A;               // rows 0..63 n1^T, 64..71 X^T, 72 ones ; cols m
+    uint8_t* B1 = B3 + 32 * LBO_B3;              // W3f   rows j, cols k
+    uint8_t* B2 = B1 + 16 * LBO_W;               // W3f^T rows k, cols j
+    uint8_t* N3s = B2 + 16 * LBO_W;              // n3 rows (fp32) for the GH reduction: rows m, cols 64
+    float* w1t = reinterpret_cast<float*>(N3s + 16 * LBO_A);  // [8][64] k-major, zero padded
+    float* b1s = w1t + 8 * H;
+    float* b3f = b1s + H;
+    float* whf = b3f + H;                        // [8][64] folded head
+    float* bhf = whf + MAX_OUT * H;
+    float* DLs = bhf + MAX_OUT;                  // [128][8]
+    float* red = DLs + T_M * 8;                  // [32]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(red + 32);  // 3 mbarriers
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 3);
+
+    // ---- stage weights (folded; tensor-core copies rounded to TF32) ----
+    for (int i = tid; i < 8 * H; i += T_NT) { const int k = i / H, j = i % H; w1t[i] = (k < d) ? params[po.w1 + j * d + k] : 0.f; }
+    for (int i = tid; i < H; i += T_NT) b1s[i] = params[po.b1 + i];
+    for (int i = tid; i < H * H; i += T_NT) {
+        const int j = i / H, k = i % H;
+        const float v = to_tf32(params[po.w3 + i] * params[po.g1 + k]);
+        pst(B1, LBO_W, j, k, v);
+        pst(B2, LBO_W, k, j, v);
+    }
+    for (int i = tid; i < MAX_OUT * H; i += T_NT) { const int j = i / H, k = i % H; whf[i] = (j < n) ? params[po.wh + j * H + k] * params[po.g3 + k] : 0.f; }
+    for (int j = tid; j < H; j += T_NT) {
+        float s = params[po.b3 + j];
+        for (int k = 0; k < H; ++k) s = fmaf(params[po.w3 + j * H + k], params[po.be1 + k], s);
+        b3f[j] = s;
+    }
+    for (int j = tid; j < MAX_OUT; j += T_NT) {
+        float s = 0.f;
+        if (j < n) { s = params[po.bh + j]; for (int k = 0; k < H; ++k) s = fmaf(params[po.wh + j * H + k], params[po.be3 + k], s); }
+        bhf[j] = s;
+    }
+    // constant rows of B3: ones row 72, zero rows 64+d..71 and 73..79 (this thread's column m = tid)
+    for (int r = 64; r < NB3; ++r) pst(B3, LBO_B3, r, tid, r == 72 ? 1.0f : 0.f);
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); }
+    if (warp == 0) tmem_alloc(tmem_holder, 256);
+    fence_proxy_async();
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem = *tmem_holder;
+    const uint32_t tmem_row = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t idesc64 = make_idesc_tf32(128, 64, false, false);
+    const uint32_t idesc80 = make_idesc_tf32(128, NB3, false, false);
+
+    // ---- minibatch constants ----
+    const bool pol_masks = a.flags & ORL_PPO_POLICY_ACTIVE_MASKS, val_masks = a.flags & ORL_PPO_VALUE_ACTIVE_MASKS;
+    const double rows_d = (double)a.batch_rows;
+    const float inv_rows = (float)(1.0 / rows_d), inv_act = (float)(1.0 / a.mb_stats[2]);
+    AdvNormTc an = {0.f, 1.f, 0.f, 1.f, false};
+    float vn_mean = 0.f, vn_std = 1.f;
+    if (POLICY) {  // ppo.py:402-409
+        const double* gs = a.gae_stats;
+        const double n_all = gs[ORL_GS_COUNT], n_act = gs[ORL_GS_ACT_COUNT];
+        const double mean_all = gs[ORL_GS_ADV_SUM] / n_all;
+        const double var_all = fmax(gs[ORL_GS_ADV_SQSUM] / n_all - mean_all * mean_all, 0.0);
+        double mean_act = gs[ORL_GS_ADV_ACT_SUM] / n_act;
+        double std_act = sqrt(fmax(gs[ORL_GS_ADV_ACT_SQSUM] / n_act - mean_act * mean_act, 0.0));
+        if (a.flags & ORL_PPO_ADV_NORMALIZE) {
+            const double s0 = (double)((float)sqrt(var_all)) + 1e-5;
+            an.two = true; an.m0 = (float)mean_all; an.s0 = (float)s0;
+            mean_act = (mean_act - mean_all) / s0; std_act = std_act / s0;
+        }
+        an.m1 = (float)mean_act; an.s1 = (float)((double)((float)std_act) + 1e-5);
+    } else if (a.flags & ORL_PPO_VALUENORM) {
+        const float bm = (float)(a.mb_stats[0] / rows_d), bsq = (float)(a.mb_stats[1] / rows_d);
+        const float beta = (float)a.vn_beta, omw = (float)(1.0 - a.vn_beta);
+        float st[3];
+        st[0] = __fadd_rn(__fmul_rn(a.vn_state[0], beta), __fmul_rn(bm, omw));
+        st[1] = __fadd_rn(__fmul_rn(a.vn_state[1], beta), __fmul_rn(bsq, omw));
+        st[2] = __fadd_rn(__fmul_rn(a.vn_state[2], beta), __fmul_rn(1.0f, omw));
+        const VnScalars s = vn_mean_std(st);
+        vn_mean = s.mean; vn_std = s.std;
+    }
+
+    float gh_acc[4] = {0.f, 0.f, 0.f, 0.f};   // GH outputs o = tid + 128*q  (j = o/64, k = o%64), o < n*64
+    float dbh_acc = 0.f;                        // thread t < n: sum_m dL[m][t]
+    float loss0 = 0.f, loss1 = 0.f, loss2 = 0.f;
+    uint32_t it = 0;
+
+    const long long n_tiles = (a.batch_rows + T_M - 1) / T_M;
+    for (long long tile = cta; tile < n_tiles; tile += G, ++it) {
+        const uint32_t par = it & 1u;
+        const long long r = tile * T_M + tid;
+        const bool valid = r < a.batch_rows;
+        const long long gi = valid ? (a.indices ? a.indices[r] : a.row_begin + r) : -1;
+
+        // ---- fc1 + activation + LayerNorm (thread-local) ----
+        float x[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] = (valid && k < d) ? obs[gi * d + k] : 0.f;
+        float h[H];
+#pragma unroll
+        for (int j4 = 0; j4 < H; j4 += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(b1s + j4);
+            h[j4] = b.x; h[j4 + 1] = b.y; h[j4 + 2] = b.z; h[j4 + 3] = b.w;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (k < d) {
+#pragma unroll
+                for (int j4 = 0; j4 < H; j4 += 4) {
+                    const float4 wv = *reinterpret_cast<const float4*>(w1t + k * H + j4);
+                    h[j4] = fmaf(x[k], wv.x, h[j4]); h[j4 + 1] = fmaf(x[k], wv.y, h[j4 + 1]);
+                    h[j4 + 2] = fmaf(x[k], wv.z, h[j4 + 2]); h[j4 + 3] = fmaf(x[k], wv.w, h[j4 + 3]);
+                }
+            }
+        }
+        unsigned long long posmask = 0ull;
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < H; ++j) {
+            if (h[j] > 0.f) posmask |= 1ull << j;
+            h[j] = act_fwd(h[j], a.activation_id);
+            s += h[j];
+        }
+        const float mu1 = s * (1.f / H);
+        float vs = 0.f;
+#pragma unroll
+        for (int j = 0; j < H; ++j) { h[j] -= mu1; vs = fmaf(h[j], h[j], vs); }
+        const float rstd1 = 1.0f / sqrtf(vs * (1.f / H) + LN_EPS);
+
+        // previous tile's GEMM3 must have finished reading A3 / B3 / (n3 in A12 is read by threads only)
+        if (it > 0) mbar_wait(&bars[2], (it - 1) & 1u);
+        __syncthreads();   // all threads done with the previous tile's GH reads of N3s / DLs
+#pragma unroll
+        for (int j4 = 0; j4 < H; j4 += 4) {
+            float4 v;
+            v.x = to_tf32(h[j4] * rstd1); v.y = to_tf32(h[j4 + 1] * rstd1); v.z = to_tf32(h[j4 + 2] * rstd1); v.w = to_tf32(h[j4 + 3] * rstd1);
+            *reinterpret_cast<float4*>(A12 + poff(LBO_A, tid, j4)) = v;         // n1 row (GEMM1 A operand)
+            pst(B3, LBO_B3, j4, tid, v.x); pst(B3, LBO_B3, j4 + 1, tid, v.y);   // n1^T (GEMM3 B operand)
+            pst(B3, LBO_B3, j4 + 2, tid, v.z); pst(B3, LBO_B3, j4 + 3, tid, v.w);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) if (k < d) pst(B3, LBO_B3, 64 + k, tid, to_tf32(x[k]));
+        fence_proxy_async();
+        tcgen05_fence_before();
+        __syncthreads();
+        if (warp == 0 && elect_one()) {   // GEMM1: Z3 = n1 . W3f^T
+            tcgen05_fence_after();
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) mma_tf32(tmem, kdesc(A12, LBO_A, kk * 8), kdesc(B1, LBO_W, kk * 8), idesc64, kk > 0);
+            mma_commit(&bars[0]);
+        }
+
+        // row scalars while the tensor core works
+        float row_a = 0.f, row_b = 0.f, row_c = 0.f, active = 0.f;
+        if (valid) {
+            if (POLICY) { row_a = a.actions[gi]; row_b = a.old_log_probs[gi]; row_c = a.advantages[gi]; }
+            else { row_a = a.value_preds[gi]; row_b = a.returns[gi]; }
+            active = a.active_masks[gi];
+        }
+        mbar_wait(&bars[0], par);
+        tcgen05_fence_after();
+
+        // ---- Z3 -> LayerNorm -> n3 (registers) ----
+        float n3[H];
+        {
+            float lo[32], hi[32];
+            tmem_ld_row32_nowait(tmem_row, lo);
+            tmem_ld_row32_nowait(tmem_row + 32, hi);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { n3[j] = lo[j] + b3f[j]; n3[32 + j] = hi[j] + b3f[32 + j]; }
+        }
+        float s3 = 0.f;
+#pragma unroll
+        for (int j = 0; j < H; ++j) s3 += n3[j];
+        const float mu3 = s3 * (1.f / H);
+        float v3 = 0.f;
+#pragma unroll
+        for (int j = 0; j < H; ++j) { n3[j] -= mu3; v3 = fmaf(n3[j], n3[j], v3); }
+        const float rstd3 = 1.0f / sqrtf(v3 * (1.f / H) + LN_EPS);
+#pragma unroll
+        for (int j = 0; j < H; ++j) n3[j] *= rstd3;
+#pragma unroll
+        for (int j4 = 0; j4 < H; j4 += 4)   // previous tile's GH reads of N3s finished before this tile's first barrier
+            *reinterpret_cast<float4*>(N3s + poff(LBO_A, tid, j4)) = make_float4(n3[j4], n3[j4 + 1], n3[j4 + 2], n3[j4 + 3]);
+
+        // ---- head + loss + dL/dhead ----
+        float out[MAX_OUT];
+#pragma unroll
+        for (int j = 0; j < MAX_OUT; ++j) {
+            out[j] = 0.f;
+            if (j < n) {
+                float sacc = bhf[j];
+#pragma unroll
+                for (int k4 = 0; k4 < H; k4 += 4) {
+                    const float4 wv = *reinterpret_cast<const float4*>(whf + j * H + k4);
+                    sacc = fmaf(n3[k4], wv.x, fmaf(n3[k4 + 1], wv.y, fmaf(n3[k4 + 2], wv.z, fmaf(n3[k4 + 3], wv.w, sacc))));
+                }
+                out[j] = sacc;
+            }
+        }
+        float dl[MAX_OUT];
+#pragma unroll
+        for (int j = 0; j < MAX_OUT; ++j) dl[j] = 0.f;
+        if (valid) {
+            if (POLICY) {
+                unsigned masked = 0;
+                if (a.action_masks) {
+#pragma unroll
+                    for (int j = 0; j < MAX_OUT; ++j)
+                        if (j < n && a.action_masks[gi * n + j] == 0.f) { out[j] = -6e4f; masked |= 1u << j; }
+                }
+                float nl[MAX_OUT], pr[MAX_OUT];
+                log_softmax_n(out, n, nl, pr);
+                const int act = (int)row_a;
+                float lp = nl[0];
+#pragma unroll
+                for (int j = 1; j < MAX_OUT; ++j) if (j == act) lp = nl[j];
+                const float ratio = expf(lp - row_b);
+                float adv = row_c;
+                if (an.two) adv = (adv - an.m0) / an.s0;
+                adv = (adv - an.m1) / an.s1;
+                const float lo = 1.0f - a.clip_param, hi = 1.0f + a.clip_param;
+                const float surr1 = ratio * adv, surr2 = fminf(fmaxf(ratio, lo), hi) * adv;
+                const bool inside = ratio >= lo && ratio <= hi;
+                const float sel = surr1 < surr2 ? 1.f : (surr1 > surr2 ? 0.f : (inside ? 1.f : 0.5f));
+                const float wrow = pol_masks ? active * inv_act : inv_rows;
+                float ent = 0.f;
+#pragma unroll
+                for (int j = 0; j < MAX_OUT; ++j) if (j < n) ent -= pr[j] * nl[j];
+                loss0 += -fminf(surr1, surr2) * wrow;
+                loss1 += ent * wrow;
+                loss2 += ratio;
+                const float dlp = -sel * adv * ratio * wrow, went = a.entropy_coef * wrow;
+#pragma unroll
+                for (int j = 0; j < MAX_OUT; ++j)
+                    if (j < n && !((masked >> j) & 1u)) dl[j] = dlp * ((j == act ? 1.f : 0.f) - pr[j]) + went * pr[j] * (nl[j] + ent);
+            } else {
+                const float v = out[0], vp = row_a, ret = row_b;
+                const float target = (a.flags & ORL_PPO_VALUENORM) ? (ret - vn_mean) / vn_std : ret;
+                const float diff = v - vp;
+                const float clipped = vp + fminf(fmaxf(diff, -a.clip_param), a.clip_param);
+                const float e_c = target - clipped, e_o = target - v, dlt = a.huber_delta;
+                const bool hub = a.flags & ORL_PPO_HUBER;
+                const float l_c = hub ? (fabsf(e_c) <= dlt ? 0.5f * e_c * e_c : dlt * (fabsf(e_c) - 0.5f * dlt)) : 0.5f * e_c * e_c;
+                const float l_o = hub ? (fabsf(e_o) <= dlt ? 0.5f * e_o * e_o : dlt * (fabsf(e_o) - 0.5f * dlt)) : 0.5f * e_o * e_o;
+                const float gc = hub ? (fabsf(e_c) <= dlt ? e_c : (e_c > 0.f ? dlt : -dlt)) : e_c;
+                const float go = hub ? (fabsf(e_o) <= dlt ? e_o : (e_o > 0.f ? dlt : -dlt)) : e_o;
+                float l = l_o, dv = -go;
+                if (a.flags & ORL_PPO_CLIP_VALUE) {
+                    const bool inrange = diff >= -a.clip_param && diff <= a.clip_param;
+                    const float dc = inrange ? -gc : 0.f;
+                    if (l_o > l_c) { l = l_o; dv = -go; } else if (l_c > l_o) { l = l_c; dv = dc; } else { l = l_o; dv = 0.5f * (-go) + 0.5f * dc; }
+                }
+                const float wrow = val_masks ? active * inv_act : inv_rows;
+                loss0 += l * wrow;
+                dl[0] = a.value_loss_coef * wrow * dv;
+            }
+        }
+        // ---- dn3 = dL . Whf ; LayerNorm-3 backward -> dZ3 ----
+        float g[H];
+#pragma unroll
+        for (int k = 0; k < H; ++k) g[k] = 0.f;
+#pragma unroll
+        for (int j = 0; j < MAX_OUT; ++j) {
+            if (j < n) {
+#pragma unroll
+                for (int k4 = 0; k4 < H; k4 += 4) {
+                    const float4 wv = *reinterpret_cast<const float4*>(whf + j * H + k4);
+                    g[k4] = fmaf(dl[j], wv.x, g[k4]); g[k4 + 1] = fmaf(dl[j], wv.y, g[k4 + 1]);
+                    g[k4 + 2] = fmaf(dl[j], wv.z, g[k4 + 2]); g[k4 + 3] = fmaf(dl[j], wv.w, g[k4 + 3]);
+                }
+            }
+        }
+        {
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int k = 0; k < H; ++k) { s1 += g[k]; s2 = fmaf(g[k], n3[k], s2); }
+            s1 *= (1.f / H); s2 *= (1.f / H);
+#pragma unroll
+            for (int k = 0; k < H; ++k) g[k] = rstd3 * (g[k] - s1 - n3[k] * s2);
+        }
+        // A12 is free (GEMM1 completed): dZ3 row; A3 rows 0..63: dZ3^T
+#pragma unroll
+        for (int j4 = 0; j4 < H; j4 += 4) {
+            float4 v;
+            v.x = to_tf32(g[j4]); v.y = to_tf32(g[j4 + 1]); v.z = to_tf32(g[j4 + 2]); v.w = to_tf32(g[j4 + 3]);
+            *reinterpret_cast<float4*>(A12 + poff(LBO_A, tid, j4)) = v;
+            pst(A3, LBO_A, j4, tid, v.x); pst(A3, LBO_A, j4 + 1, tid, v.y); pst(A3, LBO_A, j4 + 2, tid, v.z); pst(A3, LBO_A, j4 + 3, tid, v.w);
+        }
+        *reinterpret_cast<float4*>(DLs + tid * 8) = make_float4(dl[0], dl[1], dl[2], dl[3]);
+        *reinterpret_cast<float4*>(DLs + tid * 8 + 4) = make_float4(dl[4], dl[5], dl[6], dl[7]);
+        fence_proxy_async();
+        tcgen05_fence_before();
+        __syncthreads();
+        if (warp == 0 && elect_one()) {   // GEMM2: dN1 = dZ3 . W3f
+            tcgen05_fence_after();
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) mma_tf32(tmem, kdesc(A12, LBO_A, kk * 8), kdesc(B2, LBO_W, kk * 8), idesc64, kk > 0);
+            mma_commit(&bars[1]);
+        }
+        mbar_wait(&bars[1], par);
+        tcgen05_fence_after();
+        // ---- dN1 -> LayerNorm-1 backward -> activation backward -> dZ1 ----
+        {
+            float lo[32], hi[32];
+            tmem_ld_row32_nowait(tmem_row, lo);
+            tmem_ld_row32_nowait(tmem_row + 32, hi);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { g[j] = lo[j]; g[32 + j] = hi[j]; }
+        }
+        {
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int k = 0; k < H; ++k) { const float n1k = pld(B3, LBO_B3, k, tid); s1 += g[k]; s2 = fmaf(g[k], n1k, s2); }
+            s1 *= (1.f / H); s2 *= (1.f / H);
+            const float std1 = 1.0f / rstd1;
+#pragma unroll
+            for (int k = 0; k < H; ++k) {
+                const float n1k = pld(B3, LBO_B3, k, tid);   // own column of n1^T (TF32-rounded)
+                const float da = rstd1 * (g[k] - s1 - n1k * s2);
+                const float aval = fmaf(n1k, std1, mu1);     // activation output (tanh / elu derivative)
+                g[k] = da * act_bwd(aval, (posmask >> k) & 1ull, a.activation_id);
+            }
+        }
+        // A3 rows 64..127: dZ1^T
+#pragma unroll
+        for (int j4 = 0; j4 < H; j4 += 4) {
+            pst(A3, LBO_A, 64 + j4, tid, to_tf32(g[j4])); pst(A3, LBO_A, 64 + j4 + 1, tid, to_tf32(g[j4 + 1]));
+            pst(A3, LBO_A, 64 + j4 + 2, tid, to_tf32(g[j4 + 2])); pst(A3, LBO_A, 64 + j4 + 3, tid, to_tf32(g[j4 + 3]));
+        }
+        fence_proxy_async();
+        tcgen05_fence_before();
+        __syncthreads();
+        if (warp == 0 && elect_one()) {   // GEMM3: G += [dZ3^T; dZ1^T] . [n1^T; X^T; 1^T]^T   (K = 128 tile rows)
+            tcgen05_fence_after();
+#pragma unroll
+            for (int kk = 0; kk < 16; ++kk) mma_tf32(tmem + 64, kdesc(A3, LBO_A, kk * 8), kdesc(B3, LBO_B3, kk * 8), idesc80, (it | kk) > 0);
+            mma_commit(&bars[2]);
+        }
+        // ---- GH += dL^T n3 (FFMA reduction over the tile rows, n3 read back from N3s) ----
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int o = tid + T_NT * q;
+            if (o < n * H) {
+                const int j = o >> 6, k = o & 63;
+                float acc = gh_acc[q];
+                const uint8_t* np = N3s + poff(LBO_A, 0, k);
+#pragma unroll 8
+                for (int m = 0; m < T_M; ++m) acc = fmaf(DLs[m * 8 + j], *reinterpret_cast<const float*>(np + m * 16), acc);
+                gh_acc[q] = acc;
+            }
+        }
+        if (tid < n) {
+            float acc = dbh_acc;
+            for (int m = 0; m < T_M; ++m) acc += DLs[m * 8 + tid];
+            dbh_acc = acc;
+        }
+    }
+
+    // ---- flush: G (TMEM) -> partial folded gradients ----
+    float* part = a.partials + (size_t)((POLICY ? 0 : G) + cta) * stride;
+    const FoldOffsets fo = fold_offsets(d, n);
+    if (it > 0) {
+        mbar_wait(&bars[2], (it - 1) & 1u);
+        tcgen05_fence_after();
+        float lo[32], hi[32], ex[16];
+        tmem_ld_row32_nowait(tmem_row + 64, lo);
+        tmem_ld_row32_nowait(tmem_row + 96, hi);
+        tmem_ld_wait();
+        {
+            uint32_t r16[16];
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                         : "=r"(r16[0]), "=r"(r16[1]), "=r"(r16[2]), "=r"(r16[3]), "=r"(r16[4]), "=r"(r16[5]), "=r"(r16[6]), "=r"(r16[7]),
+                           "=r"(r16[8]), "=r"(r16[9]), "=r"(r16[10]), "=r"(r16[11]), "=r"(r16[12]), "=r"(r16[13]), "=r"(r16[14]), "=r"(r16[15])
+                         : "r"(tmem_row + 128));
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) ex[i] = __uint_as_float(r16[i]);
+        }
+        if (tid < 64) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) { part[fo.g3 + tid * H + c] = lo[c]; part[fo.g3 + tid * H + 32 + c] = hi[c]; }
+            part[fo.db3 + tid] = ex[8];
+        } else {
+            const int j = tid - 64;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) if (c < d) part[fo.g1 + j * d + c] = ex[c];
+            part[fo.db1 + j] = ex[8];
+        }
+    } else {
+        for (int i = tid; i < fo.gh; i += T_NT) part[i] = 0.f;   // G1, db1, G3, db3 of an idle CTA
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { const int o = tid + T_NT * q; if (o < n * H) part[fo.gh + o] = gh_acc[q]; }
+    if (tid < n) part[fo.dbh + tid] = dbh_acc;
+    {
+        float v[3] = {loss0, loss1, loss2};
+        const int lane = tid & 31;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { const float sv = warp_sum(v[k]); if (lane == 0) red[k * 4 + warp] = sv; }
+        __syncthreads();
+        if (tid < N_LOSS_TC) {
+            float sv = 0.f;
+            if (tid < 3) sv = red[tid * 4] + red[tid * 4 + 1] + red[tid * 4 + 2] + red[tid * 4 + 3];
+            part[stride - N_LOSS_TC + tid] = sv;
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+__global__ void __launch_bounds__(T_NT, 1) ppo_fwdbwd_tc_kernel(const OrlPpoArgs a, int stride) {
+    extern __shared__ __align__(1024) uint8_t smem_tc[];
+    const int G = a.grid_per_net;
+    if ((int)blockIdx.x < G) tc_net_pass<true>(a, smem_tc, blockIdx.x, G, stride);
+    else tc_net_pass<false>(a, smem_tc, blockIdx.x - G, G, stride);
+}
+
+}  // namespace
+
+namespace orl {
+int launch_ppo_fwdbwd_tc(const OrlPpoArgs& a, cudaStream_t st) {
+    if (a.obs_dim > 8 || a.critic_obs_dim > 8) {
+        set_last_error("orl_ppo_fwdbwd: ORL_PPO_TF32 supports observation widths <= 8 (got %d / %d)", a.obs_dim, a.critic_obs_dim);
+        return ORL_ERR_UNSUPPORTED;
+    }
+    const size_t smem = 16 * LBO_A + 32 * LBO_A + 32 * LBO_B3 + 2 * 16 * LBO_W + 16 * LBO_A +
+                        sizeof(float) * (8 * H + H + H + MAX_OUT * H + MAX_OUT + T_M * 8 + 32) + 3 * 8 + 16 + 128;
+    static bool attr_set = false;
+    if (!attr_set) {
+        int e = check_cuda(cudaFuncSetAttribute(ppo_fwdbwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
+                           "cudaFuncSetAttribute(ppo_fwdbwd_tc)");
+        if (e) return e;
+        attr_set = true;
+    }
+    const int stride = ppo_stride_host(a.obs_dim, a.critic_obs_dim, a.n_actions);
+    ppo_fwdbwd_tc_kernel<<<2 * a.grid_per_net, T_NT, smem, st>>>(a, stride);
+    return check_cuda(cudaGetLastError(), "ppo_fwdbwd_tc_kernel");
+}
+}  // namespace orl

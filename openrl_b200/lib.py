@@ -146,4 +146,4 @@ _SIGNATURES.update({
 ENV_NONE, ENV_CARTPOLE, ENV_GRIDWORLD, ENV_MPE_SPREAD = 0, 1, 2, 3
 GAE_USE_GAE, GAE_PROPER_TIME_LIMITS, GAE_DENORM = 1, 2, 4
 PPO_HUBER, PPO_CLIP_VALUE, PPO_VALUE_ACTIVE_MASKS, PPO_POLICY_ACTIVE_MASKS = 1, 2, 4, 8
-PPO_VALUENORM, PPO_ADV_NORMALIZE, PPO_MAX_GRAD_NORM = 16, 32, 64
+PPO_VALUENORM, PPO_ADV_NORMALIZE, PPO_MAX_GRAD_NORM, PPO_TF32 = 16, 32, 64, 128

@@ -144,3 +144,58 @@ def test_whole_buffer_minibatch_equals_permuted_minibatch(cuda):
         res.append((trainer.train_info.cpu().numpy().copy(), net.module.models["policy"].flat_params.cpu().numpy().copy()))
     np.testing.assert_allclose(res[0][0], res[1][0], rtol=2e-5, atol=1e-7)
     np.testing.assert_allclose(res[0][1], res[1][1], rtol=1e-4, atol=1e-6)
+
+
+def test_tf32_tensor_core_update_matches_fp32_update(cuda):
+    """Fast mode (tcgen05, TF32 operands) vs parity mode (fp32 FFMA) on the same minibatch: losses are
+    means over rows so they agree to ~1e-4; gradients to TF32 accuracy."""
+    import torch
+
+    from openrl_b200 import lib
+
+    d = np.load(os.path.join(GOLDEN, "trace_cartpole_c1.npz"), allow_pickle=True)
+    res = []
+    for tf32 in (False, True):
+        cfg, net, trainer, buf = _setup(d)
+        if tf32:
+            trainer.flags |= lib.PPO_TF32
+        _load_buffer(buf, d, 0)
+        vn = net.module.get_critic_value_normalizer()
+        buf.data.compute_returns(buf.data.value_preds[-1].clone(), vn)
+        total = cfg.episode_length * int(d["meta/env_num"])
+        trainer.lrs.copy_(torch.tensor([cfg.lr, cfg.critic_lr]))
+        trainer.train_info.zero_()
+        trainer.ppo_update(buf.data, total, torch.from_numpy(d["it0/perms"][0]).cuda())
+        torch.cuda.synchronize()
+        res.append((trainer.train_info.cpu().numpy().copy(), trainer.grads.cpu().numpy().copy(),
+                    net.module.models["policy"].flat_params.cpu().numpy().copy()))
+    info32, info_tc = res[0][0], res[1][0]
+    np.testing.assert_allclose(info_tc, info32, rtol=2e-3, atol=1e-5)
+    for net_i in range(2):
+        g32, gtc = res[0][1][net_i], res[1][1][net_i]
+        assert np.linalg.norm(gtc - g32) <= 5e-3 * np.linalg.norm(g32), (np.linalg.norm(gtc - g32), np.linalg.norm(g32))
+    np.testing.assert_allclose(res[1][2], res[0][2], rtol=0, atol=2e-3)
+
+
+def test_tf32_partial_tile_and_idle_ctas(cuda):
+    """Minibatch smaller than one tile (rows < 128) and far fewer tiles than CTAs."""
+    import torch
+
+    from openrl_b200 import lib
+
+    d = np.load(os.path.join(GOLDEN, "trace_cartpole.npz"), allow_pickle=True)
+    res = []
+    for tf32 in (False, True):
+        cfg, net, trainer, buf = _setup(d)
+        if tf32:
+            trainer.flags |= lib.PPO_TF32
+        _load_buffer(buf, d, 0)
+        vn = net.module.get_critic_value_normalizer()
+        buf.data.compute_returns(buf.data.value_preds[-1].clone(), vn)
+        trainer.lrs.copy_(torch.tensor([cfg.lr, cfg.critic_lr]))
+        trainer.train_info.zero_()
+        idx = torch.from_numpy(d["it0/perms"][0][:100]).cuda().contiguous()
+        trainer.ppo_update(buf.data, 100, idx)
+        torch.cuda.synchronize()
+        res.append(trainer.train_info.cpu().numpy().copy())
+    np.testing.assert_allclose(res[1], res[0], rtol=3e-3, atol=1e-5)
