@@ -64,7 +64,8 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, uint8_t* smem, 
     float* b3f = b1s + H;
     float* whf = b3f + H;                        // [8][64] folded head
     float* bhf = whf + MAX_OUT * H;
-    float* DLs = bhf + MAX_OUT;                  // [128][8]
+    float* swh = bhf + MAX_OUT;                  // [8] row sums of whf
+    float* DLs = swh + MAX_OUT;                  // [128][8]
     float* red = DLs + T_M * 8;                  // [32]
     uint64_t* bars = reinterpret_cast<uint64_t*>(red + 32);  // 3 mbarriers
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 3);
@@ -88,6 +89,9 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, uint8_t* smem, 
         float s = 0.f;
         if (j < n) { s = params[po.bh + j]; for (int k = 0; k < H; ++k) s = fmaf(params[po.wh + j * H + k], params[po.be3 + k], s); }
         bhf[j] = s;
+        float rs = 0.f;
+        if (j < n) for (int k = 0; k < H; ++k) rs += params[po.wh + j * H + k] * params[po.g3 + k];
+        swh[j] = rs;
     }
     // constant rows of B3: ones row 72, zero rows 64+d..71 and 73..79 (this thread's column m = tid)
     for (int r = 64; r < NB3; ++r) pst(B3, LBO_B3, r, tid, r == 72 ? 1.0f : 0.f);
@@ -144,51 +148,60 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, uint8_t* smem, 
         const bool valid = r < a.batch_rows;
         const long long gi = valid ? (a.indices ? a.indices[r] : a.row_begin + r) : -1;
 
-        // ---- fc1 + activation + LayerNorm (thread-local) ----
+        // All row-wise phases walk the 64 columns in 8 chunks of 8 with ROLLED loops (the row lives
+        // in shared memory / TMEM between passes): the tile body must stay inside the instruction
+        // cache — with one warp per scheduler an I-cache miss cannot be hidden.
+        // ---- fc1 + activation (pass 1: raw activations to A12, moments) ----
         float x[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) x[k] = (valid && k < d) ? obs[gi * d + k] : 0.f;
-        float h[H];
+        unsigned long long posmask = 0ull;
+        float s = 0.f, sq = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+            float hv[8];
+            {
+                const float4 b0 = *reinterpret_cast<const float4*>(b1s + 8 * c), b1v = *reinterpret_cast<const float4*>(b1s + 8 * c + 4);
+                hv[0] = b0.x; hv[1] = b0.y; hv[2] = b0.z; hv[3] = b0.w; hv[4] = b1v.x; hv[5] = b1v.y; hv[6] = b1v.z; hv[7] = b1v.w;
+            }
 #pragma unroll
-        for (int j4 = 0; j4 < H; j4 += 4) {
-            const float4 b = *reinterpret_cast<const float4*>(b1s + j4);
-            h[j4] = b.x; h[j4 + 1] = b.y; h[j4 + 2] = b.z; h[j4 + 3] = b.w;
-        }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            if (k < d) {
-#pragma unroll
-                for (int j4 = 0; j4 < H; j4 += 4) {
-                    const float4 wv = *reinterpret_cast<const float4*>(w1t + k * H + j4);
-                    h[j4] = fmaf(x[k], wv.x, h[j4]); h[j4 + 1] = fmaf(x[k], wv.y, h[j4 + 1]);
-                    h[j4 + 2] = fmaf(x[k], wv.z, h[j4 + 2]); h[j4 + 3] = fmaf(x[k], wv.w, h[j4 + 3]);
+            for (int k = 0; k < 8; ++k) {
+                if (k < d) {
+                    const float4 w0 = *reinterpret_cast<const float4*>(w1t + k * H + 8 * c), w1v = *reinterpret_cast<const float4*>(w1t + k * H + 8 * c + 4);
+                    hv[0] = fmaf(x[k], w0.x, hv[0]); hv[1] = fmaf(x[k], w0.y, hv[1]); hv[2] = fmaf(x[k], w0.z, hv[2]); hv[3] = fmaf(x[k], w0.w, hv[3]);
+                    hv[4] = fmaf(x[k], w1v.x, hv[4]); hv[5] = fmaf(x[k], w1v.y, hv[5]); hv[6] = fmaf(x[k], w1v.z, hv[6]); hv[7] = fmaf(x[k], w1v.w, hv[7]);
                 }
             }
-        }
-        unsigned long long posmask = 0ull;
-        float s = 0.f;
 #pragma unroll
-        for (int j = 0; j < H; ++j) {
-            if (h[j] > 0.f) posmask |= 1ull << j;
-            h[j] = act_fwd(h[j], a.activation_id);
-            s += h[j];
+            for (int i = 0; i < 8; ++i) {
+                if (hv[i] > 0.f) posmask |= 1ull << (8 * c + i);
+                hv[i] = act_fwd(hv[i], a.activation_id);
+                s += hv[i]; sq = fmaf(hv[i], hv[i], sq);
+            }
+            *reinterpret_cast<float4*>(A12 + poff(LBO_A, tid, 8 * c)) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+            *reinterpret_cast<float4*>(A12 + poff(LBO_A, tid, 8 * c + 4)) = make_float4(hv[4], hv[5], hv[6], hv[7]);
         }
         const float mu1 = s * (1.f / H);
-        float vs = 0.f;
-#pragma unroll
-        for (int j = 0; j < H; ++j) { h[j] -= mu1; vs = fmaf(h[j], h[j], vs); }
-        const float rstd1 = 1.0f / sqrtf(vs * (1.f / H) + LN_EPS);
+        const float rstd1 = 1.0f / sqrtf(fmaxf(sq * (1.f / H) - mu1 * mu1, 0.f) + LN_EPS);
 
-        // previous tile's GEMM3 must have finished reading A3 / B3 / (n3 in A12 is read by threads only)
+        // previous tile's GEMM3 must have finished reading A3 / B3
         if (it > 0) mbar_wait(&bars[2], (it - 1) & 1u);
         __syncthreads();   // all threads done with the previous tile's GH reads of N3s / DLs
-#pragma unroll
-        for (int j4 = 0; j4 < H; j4 += 4) {
-            float4 v;
-            v.x = to_tf32(h[j4] * rstd1); v.y = to_tf32(h[j4 + 1] * rstd1); v.z = to_tf32(h[j4 + 2] * rstd1); v.w = to_tf32(h[j4 + 3] * rstd1);
-            *reinterpret_cast<float4*>(A12 + poff(LBO_A, tid, j4)) = v;         // n1 row (GEMM1 A operand)
-            pst(B3, LBO_B3, j4, tid, v.x); pst(B3, LBO_B3, j4 + 1, tid, v.y);   // n1^T (GEMM3 B operand)
-            pst(B3, LBO_B3, j4 + 2, tid, v.z); pst(B3, LBO_B3, j4 + 3, tid, v.w);
+        // pass 2: normalise -> n1 row (GEMM1 A operand) and n1^T (GEMM3 B operand), TF32-rounded
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+            const float4 r0 = *reinterpret_cast<const float4*>(A12 + poff(LBO_A, tid, 8 * c));
+            const float4 r1 = *reinterpret_cast<const float4*>(A12 + poff(LBO_A, tid, 8 * c + 4));
+            float4 v0, v1;
+            v0.x = to_tf32((r0.x - mu1) * rstd1); v0.y = to_tf32((r0.y - mu1) * rstd1); v0.z = to_tf32((r0.z - mu1) * rstd1); v0.w = to_tf32((r0.w - mu1) * rstd1);
+            v1.x = to_tf32((r1.x - mu1) * rstd1); v1.y = to_tf32((r1.y - mu1) * rstd1); v1.z = to_tf32((r1.z - mu1) * rstd1); v1.w = to_tf32((r1.w - mu1) * rstd1);
+            *reinterpret_cast<float4*>(A12 + poff(LBO_A, tid, 8 * c)) = v0;
+            *reinterpret_cast<float4*>(A12 + poff(LBO_A, tid, 8 * c + 4)) = v1;
+            uint8_t* bt = B3 + poff(LBO_B3, 8 * c, tid);
+            *reinterpret_cast<float*>(bt) = v0.x; *reinterpret_cast<float*>(bt + 16) = v0.y;
+            *reinterpret_cast<float*>(bt + 32) = v0.z; *reinterpret_cast<float*>(bt + 48) = v0.w;
+            *reinterpret_cast<float*>(bt + 64) = v1.x; *reinterpret_cast<float*>(bt + 80) = v1.y;
+            *reinterpret_cast<float*>(bt + 96) = v1.z; *reinterpret_cast<float*>(bt + 112) = v1.w;
         }
 #pragma unroll
         for (int k = 0; k < 8; ++k) if (k < d) pst(B3, LBO_B3, 64 + k, tid, to_tf32(x[k]));
@@ -212,45 +225,45 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, uint8_t* smem, 
         mbar_wait(&bars[0], par);
         tcgen05_fence_after();
 
-        // ---- Z3 -> LayerNorm -> n3 (registers) ----
-        float n3[H];
-        {
-            float lo[32], hi[32];
-            tmem_ld_row32_nowait(tmem_row, lo);
-            tmem_ld_row32_nowait(tmem_row + 32, hi);
-            tmem_ld_wait();
+        // ---- Z3 (TMEM) + b3f -> moments (pass 1, raw to N3s) -> n3 (pass 2, in place) + head dots ----
+        float s3 = 0.f, q3 = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+            float z[8];
+            tmem_ld_row8(tmem_row + 8 * c, z);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) { n3[j] = lo[j] + b3f[j]; n3[32 + j] = hi[j] + b3f[32 + j]; }
+            for (int i = 0; i < 8; ++i) { z[i] += b3f[8 * c + i]; s3 += z[i]; q3 = fmaf(z[i], z[i], q3); }
+            *reinterpret_cast<float4*>(N3s + poff(LBO_A, tid, 8 * c)) = make_float4(z[0], z[1], z[2], z[3]);
+            *reinterpret_cast<float4*>(N3s + poff(LBO_A, tid, 8 * c + 4)) = make_float4(z[4], z[5], z[6], z[7]);
         }
-        float s3 = 0.f;
-#pragma unroll
-        for (int j = 0; j < H; ++j) s3 += n3[j];
         const float mu3 = s3 * (1.f / H);
-        float v3 = 0.f;
-#pragma unroll
-        for (int j = 0; j < H; ++j) { n3[j] -= mu3; v3 = fmaf(n3[j], n3[j], v3); }
-        const float rstd3 = 1.0f / sqrtf(v3 * (1.f / H) + LN_EPS);
-#pragma unroll
-        for (int j = 0; j < H; ++j) n3[j] *= rstd3;
-#pragma unroll
-        for (int j4 = 0; j4 < H; j4 += 4)   // previous tile's GH reads of N3s finished before this tile's first barrier
-            *reinterpret_cast<float4*>(N3s + poff(LBO_A, tid, j4)) = make_float4(n3[j4], n3[j4 + 1], n3[j4 + 2], n3[j4 + 3]);
-
-        // ---- head + loss + dL/dhead ----
+        const float rstd3 = 1.0f / sqrtf(fmaxf(q3 * (1.f / H) - mu3 * mu3, 0.f) + LN_EPS);
         float out[MAX_OUT];
 #pragma unroll
-        for (int j = 0; j < MAX_OUT; ++j) {
-            out[j] = 0.f;
-            if (j < n) {
-                float sacc = bhf[j];
+        for (int j = 0; j < MAX_OUT; ++j) out[j] = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+            float4 r0 = *reinterpret_cast<const float4*>(N3s + poff(LBO_A, tid, 8 * c));
+            float4 r1 = *reinterpret_cast<const float4*>(N3s + poff(LBO_A, tid, 8 * c + 4));
+            r0.x = (r0.x - mu3) * rstd3; r0.y = (r0.y - mu3) * rstd3; r0.z = (r0.z - mu3) * rstd3; r0.w = (r0.w - mu3) * rstd3;
+            r1.x = (r1.x - mu3) * rstd3; r1.y = (r1.y - mu3) * rstd3; r1.z = (r1.z - mu3) * rstd3; r1.w = (r1.w - mu3) * rstd3;
+            *reinterpret_cast<float4*>(N3s + poff(LBO_A, tid, 8 * c)) = r0;
+            *reinterpret_cast<float4*>(N3s + poff(LBO_A, tid, 8 * c + 4)) = r1;
 #pragma unroll
-                for (int k4 = 0; k4 < H; k4 += 4) {
-                    const float4 wv = *reinterpret_cast<const float4*>(whf + j * H + k4);
-                    sacc = fmaf(n3[k4], wv.x, fmaf(n3[k4 + 1], wv.y, fmaf(n3[k4 + 2], wv.z, fmaf(n3[k4 + 3], wv.w, sacc))));
+            for (int j = 0; j < MAX_OUT; ++j) {
+                if (j < n) {
+                    const float4 w0 = *reinterpret_cast<const float4*>(whf + j * H + 8 * c), w1v = *reinterpret_cast<const float4*>(whf + j * H + 8 * c + 4);
+                    out[j] = fmaf(r0.x, w0.x, fmaf(r0.y, w0.y, fmaf(r0.z, w0.z, fmaf(r0.w, w0.w, out[j]))));
+                    out[j] = fmaf(r1.x, w1v.x, fmaf(r1.y, w1v.y, fmaf(r1.z, w1v.z, fmaf(r1.w, w1v.w, out[j]))));
                 }
-                out[j] = sacc;
             }
         }
+        // dot[j] = sum_k Whf[j][k] n3[k] (needed by the LayerNorm-3 backward); logits add the folded bias
+        float dot[MAX_OUT];
+#pragma unroll
+        for (int j = 0; j < MAX_OUT; ++j) { dot[j] = out[j]; out[j] += (j < n) ? bhf[j] : 0.f; }
+
+        // ---- head loss + dL/dhead ----
         float dl[MAX_OUT];
 #pragma unroll
         for (int j = 0; j < MAX_OUT; ++j) dl[j] = 0.f;
@@ -309,36 +322,33 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, uint8_t* smem, 
                 dl[0] = a.value_loss_coef * wrow * dv;
             }
         }
-        // ---- dn3 = dL . Whf ; LayerNorm-3 backward -> dZ3 ----
-        float g[H];
+        // ---- dn3 = dL . Whf ; LayerNorm-3 backward -> dZ3 (single pass: the two row means are
+        //      mean(dn3) = sum_j dL[j] rowsum(Whf[j]) / 64 and mean(dn3 n3) = sum_j dL[j] dot[j] / 64) ----
+        float m1 = 0.f, m2 = 0.f;
 #pragma unroll
-        for (int k = 0; k < H; ++k) g[k] = 0.f;
+        for (int j = 0; j < MAX_OUT; ++j) if (j < n) { m1 = fmaf(dl[j], swh[j], m1); m2 = fmaf(dl[j], dot[j], m2); }
+        m1 *= (1.f / H); m2 *= (1.f / H);
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+            const float4 n0 = *reinterpret_cast<const float4*>(N3s + poff(LBO_A, tid, 8 * c));
+            const float4 n1v = *reinterpret_cast<const float4*>(N3s + poff(LBO_A, tid, 8 * c + 4));
+            float g8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int j = 0; j < MAX_OUT; ++j) {
-            if (j < n) {
-#pragma unroll
-                for (int k4 = 0; k4 < H; k4 += 4) {
-                    const float4 wv = *reinterpret_cast<const float4*>(whf + j * H + k4);
-                    g[k4] = fmaf(dl[j], wv.x, g[k4]); g[k4 + 1] = fmaf(dl[j], wv.y, g[k4 + 1]);
-                    g[k4 + 2] = fmaf(dl[j], wv.z, g[k4 + 2]); g[k4 + 3] = fmaf(dl[j], wv.w, g[k4 + 3]);
+            for (int j = 0; j < MAX_OUT; ++j) {
+                if (j < n) {
+                    const float4 w0 = *reinterpret_cast<const float4*>(whf + j * H + 8 * c), w1v = *reinterpret_cast<const float4*>(whf + j * H + 8 * c + 4);
+                    g8[0] = fmaf(dl[j], w0.x, g8[0]); g8[1] = fmaf(dl[j], w0.y, g8[1]); g8[2] = fmaf(dl[j], w0.z, g8[2]); g8[3] = fmaf(dl[j], w0.w, g8[3]);
+                    g8[4] = fmaf(dl[j], w1v.x, g8[4]); g8[5] = fmaf(dl[j], w1v.y, g8[5]); g8[6] = fmaf(dl[j], w1v.z, g8[6]); g8[7] = fmaf(dl[j], w1v.w, g8[7]);
                 }
             }
-        }
-        {
-            float s1 = 0.f, s2 = 0.f;
+            const float nn[8] = {n0.x, n0.y, n0.z, n0.w, n1v.x, n1v.y, n1v.z, n1v.w};
 #pragma unroll
-            for (int k = 0; k < H; ++k) { s1 += g[k]; s2 = fmaf(g[k], n3[k], s2); }
-            s1 *= (1.f / H); s2 *= (1.f / H);
+            for (int i = 0; i < 8; ++i) g8[i] = to_tf32(rstd3 * (g8[i] - m1 - nn[i] * m2));
+            *reinterpret_cast<float4*>(A12 + poff(LBO_A, tid, 8 * c)) = make_float4(g8[0], g8[1], g8[2], g8[3]);       // dZ3 row
+            *reinterpret_cast<float4*>(A12 + poff(LBO_A, tid, 8 * c + 4)) = make_float4(g8[4], g8[5], g8[6], g8[7]);
+            uint8_t* at = A3 + poff(LBO_A, 8 * c, tid);                                                                // dZ3^T
 #pragma unroll
-            for (int k = 0; k < H; ++k) g[k] = rstd3 * (g[k] - s1 - n3[k] * s2);
-        }
-        // A12 is free (GEMM1 completed): dZ3 row; A3 rows 0..63: dZ3^T
-#pragma unroll
-        for (int j4 = 0; j4 < H; j4 += 4) {
-            float4 v;
-            v.x = to_tf32(g[j4]); v.y = to_tf32(g[j4 + 1]); v.z = to_tf32(g[j4 + 2]); v.w = to_tf32(g[j4 + 3]);
-            *reinterpret_cast<float4*>(A12 + poff(LBO_A, tid, j4)) = v;
-            pst(A3, LBO_A, j4, tid, v.x); pst(A3, LBO_A, j4 + 1, tid, v.y); pst(A3, LBO_A, j4 + 2, tid, v.z); pst(A3, LBO_A, j4 + 3, tid, v.w);
+            for (int i = 0; i < 8; ++i) *reinterpret_cast<float*>(at + 16 * i) = g8[i];
         }
         *reinterpret_cast<float4*>(DLs + tid * 8) = make_float4(dl[0], dl[1], dl[2], dl[3]);
         *reinterpret_cast<float4*>(DLs + tid * 8 + 4) = make_float4(dl[4], dl[5], dl[6], dl[7]);
@@ -353,34 +363,31 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, uint8_t* smem, 
         }
         mbar_wait(&bars[1], par);
         tcgen05_fence_after();
-        // ---- dN1 -> LayerNorm-1 backward -> activation backward -> dZ1 ----
-        {
-            float lo[32], hi[32];
-            tmem_ld_row32_nowait(tmem_row, lo);
-            tmem_ld_row32_nowait(tmem_row + 32, hi);
-            tmem_ld_wait();
+        // ---- dN1 (TMEM) -> LayerNorm-1 backward -> activation backward -> dZ1^T (two passes over TMEM) ----
+        float t1 = 0.f, t2 = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+            float g8[8];
+            tmem_ld_row8(tmem_row + 8 * c, g8);
+            const uint8_t* bt = B3 + poff(LBO_B3, 8 * c, tid);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) { g[j] = lo[j]; g[32 + j] = hi[j]; }
+            for (int i = 0; i < 8; ++i) { t1 += g8[i]; t2 = fmaf(g8[i], *reinterpret_cast<const float*>(bt + 16 * i), t2); }
         }
-        {
-            float s1 = 0.f, s2 = 0.f;
+        t1 *= (1.f / H); t2 *= (1.f / H);
+        const float std1 = 1.0f / rstd1;
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+            float g8[8];
+            tmem_ld_row8(tmem_row + 8 * c, g8);
+            const uint8_t* bt = B3 + poff(LBO_B3, 8 * c, tid);
+            uint8_t* at = A3 + poff(LBO_A, 64 + 8 * c, tid);
 #pragma unroll
-            for (int k = 0; k < H; ++k) { const float n1k = pld(B3, LBO_B3, k, tid); s1 += g[k]; s2 = fmaf(g[k], n1k, s2); }
-            s1 *= (1.f / H); s2 *= (1.f / H);
-            const float std1 = 1.0f / rstd1;
-#pragma unroll
-            for (int k = 0; k < H; ++k) {
-                const float n1k = pld(B3, LBO_B3, k, tid);   // own column of n1^T (TF32-rounded)
-                const float da = rstd1 * (g[k] - s1 - n1k * s2);
-                const float aval = fmaf(n1k, std1, mu1);     // activation output (tanh / elu derivative)
-                g[k] = da * act_bwd(aval, (posmask >> k) & 1ull, a.activation_id);
+            for (int i = 0; i < 8; ++i) {
+                const float n1k = *reinterpret_cast<const float*>(bt + 16 * i);   // own column of n1^T
+                const float da = rstd1 * (g8[i] - t1 - n1k * t2);
+                const float aval = fmaf(n1k, std1, mu1);                          // activation output
+                *reinterpret_cast<float*>(at + 16 * i) = to_tf32(da * act_bwd(aval, (posmask >> (8 * c + i)) & 1ull, a.activation_id));
             }
-        }
-        // A3 rows 64..127: dZ1^T
-#pragma unroll
-        for (int j4 = 0; j4 < H; j4 += 4) {
-            pst(A3, LBO_A, 64 + j4, tid, to_tf32(g[j4])); pst(A3, LBO_A, 64 + j4 + 1, tid, to_tf32(g[j4 + 1]));
-            pst(A3, LBO_A, 64 + j4 + 2, tid, to_tf32(g[j4 + 2])); pst(A3, LBO_A, 64 + j4 + 3, tid, to_tf32(g[j4 + 3]));
         }
         fence_proxy_async();
         tcgen05_fence_before();
@@ -480,7 +487,7 @@ int launch_ppo_fwdbwd_tc(const OrlPpoArgs& a, cudaStream_t st) {
         return ORL_ERR_UNSUPPORTED;
     }
     const size_t smem = 16 * LBO_A + 32 * LBO_A + 32 * LBO_B3 + 2 * 16 * LBO_W + 16 * LBO_A +
-                        sizeof(float) * (8 * H + H + H + MAX_OUT * H + MAX_OUT + T_M * 8 + 32) + 3 * 8 + 16 + 128;
+                        sizeof(float) * (8 * H + H + H + MAX_OUT * H + 2 * MAX_OUT + T_M * 8 + 32) + 3 * 8 + 16 + 128;
     static bool attr_set = false;
     if (!attr_set) {
         int e = check_cuda(cudaFuncSetAttribute(ppo_fwdbwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
