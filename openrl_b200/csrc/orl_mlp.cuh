@@ -266,7 +266,7 @@ template <int M, int NT>
 __device__ __forceinline__ void head_dots(const SmemWeights& w, const float* __restrict__ N3s, int n,
                                           float (&out)[MAX_OUT]) {
     constexpr int PPR = NT / M;
-    static_assert(PPR == 1 || PPR == 2 || PPR == 4 || PPR == 8, "threads per row");
+    static_assert(PPR == 1 || PPR == 2 || PPR == 4 || PPR == 8 || PPR == 16, "threads per row");
     const int row = threadIdx.x / PPR, part = threadIdx.x % PPR;
 #pragma unroll
     for (int j = 0; j < MAX_OUT; ++j) out[j] = 0.f;

@@ -2,9 +2,11 @@
 // TMEM) — the "fast mode" sibling of ppo_fwdbwd_kernel (orl_ppo.cu), producing the same folded
 // partial gradients and loss sums.  Selected with ORL_PPO_TF32; obs widths <= 8 (CartPole, GridWorld).
 //
-// CTA = 128 threads = 128 tile rows: a thread owns one minibatch row, so every row-wise operation
-// (fc1 with K = d <= 8, LayerNorm forward/backward, head, loss) is thread-local in registers, and the
-// three 64-wide GEMMs of the row tile go to the tensor core, issued by one elected thread:
+// CTA = 256 threads = 128 tile rows x 2 column halves: warps w and w+4 own the same 32 rows (the TMEM
+// lane quadrant w%4) and columns [0,32) / [32,64), so every row-wise operation (fc1 with K = d <= 8,
+// LayerNorm forward/backward, head, loss) is thread-local apart from a handful of two-float
+// exchanges through shared memory, and the three 64-wide GEMMs of the row tile go to the tensor
+// core, issued by one elected thread:
 //     GEMM1  Z3 [128x64]  = n1 [128x64]  . W3f^T            (M=128, N=64, K=64)    fwd fc3
 //     GEMM2  dN1[128x64]  = dZ3[128x64]  . W3f              (M=128, N=64, K=64)    bwd-data fc3
 //     GEMM3  G  [128x80] += [dZ3^T;dZ1^T][128x128] . [n1^T;X^T;1^T]^T  (M=128, N=80, K=128 rows)
@@ -27,7 +29,7 @@ namespace {
 using namespace orl;
 using namespace orl::tc;
 
-constexpr int T_M = 128, T_NT = 128;
+constexpr int T_M = 128, T_NT = 256;   // two threads per row: thread = (row, column half)
 constexpr int NB3 = 80;                       // rows of B3: 64 (n1^T) + 8 (X^T) + 8 (ones / zero)
 constexpr uint32_t LBO_A = 128 * 16 + 16;     // panel stride of 128-row tiles (padded)
 constexpr uint32_t LBO_B3 = NB3 * 16 + 16;
@@ -43,13 +45,27 @@ __device__ __forceinline__ uint64_t kdesc(const uint8_t* tile, uint32_t lbo, int
 
 struct AdvNormTc { float m0, s0, m1, s1; bool two; };
 
-template <bool POLICY>
+// NOUT: head width known at compile time (1 critic, 2, 5) or 8 = generic (runtime n <= 8)
+#define FOR_OUT(j) _Pragma("unroll") for (int j = 0; j < NOUT; ++j) if (NOUT != 8 || j < n)
+
+// pair exchange: both column halves of a row publish `cnt` partial sums and read the other's
+#define PAIR_SUM2(v0, v1)                                                          \
+    do {                                                                           \
+        xch[(half * T_M + row) * 8 + 0] = (v0); xch[(half * T_M + row) * 8 + 1] = (v1); \
+        __syncthreads();                                                           \
+        const float o0_ = xch[((half ^ 1) * T_M + row) * 8 + 0], o1_ = xch[((half ^ 1) * T_M + row) * 8 + 1]; \
+        (v0) += o0_; (v1) += o1_;                                                  \
+        __syncthreads();                                                           \
+    } while (0)
+
+template <bool POLICY, int NOUT>
 __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, uint8_t* smem, int cta, int G, int stride) {
     const int d = POLICY ? a.obs_dim : a.critic_obs_dim;
-    const int n = POLICY ? a.n_actions : 1;
+    const int n = POLICY ? (NOUT == 8 ? a.n_actions : NOUT) : 1;
     const float* params = POLICY ? a.policy_params : a.critic_params;
     const float* obs = POLICY ? a.policy_obs : a.critic_obs;
     const int tid = threadIdx.x, warp = tid >> 5;
+    const int row = tid & 127, half = tid >> 7, c0 = 4 * half;   // this thread: tile row, column chunks [c0, c0+4)
     const NetOffsets po = net_offsets(d, n);
 
     // ---- shared memory carve-up (all tensor-core tiles 128-byte aligned) ----
@@ -66,7 +82,8 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, uint8_t* smem, 
     float* bhf = whf + MAX_OUT * H;
     float* swh = bhf + MAX_OUT;                  // [8] row sums of whf
     float* DLs = swh + MAX_OUT;                  // [128][8]
-    float* red = DLs + T_M * 8;                  // [32]
+    float* xch = DLs + T_M * 8;                  // [2][128][8] pair exchange
+    float* red = xch + 2 * T_M * 8;              // [32]
     uint64_t* bars = reinterpret_cast<uint64_t*>(red + 32);  // 3 mbarriers
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 3);
 
@@ -94,7 +111,7 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, uint8_t* smem, 
         swh[j] = rs;
     }
     // constant rows of B3: ones row 72, zero rows 64+d..71 and 73..79 (this thread's column m = tid)
-    for (int r = 64; r < NB3; ++r) pst(B3, LBO_B3, r, tid, r == 72 ? 1.0f : 0.f);
+    if (half == 0) for (int r = 64; r < NB3; ++r) pst(B3, LBO_B3, r, row, r == 72 ? 1.0f : 0.f);
     if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); }
     if (warp == 0) tmem_alloc(tmem_holder, 256);
     fence_proxy_async();
@@ -102,7 +119,7 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, uint8_t* smem, 
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem = *tmem_holder;
-    const uint32_t tmem_row = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t tmem_row = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t idesc64 = make_idesc_tf32(128, 64, false, false);
     const uint32_t idesc80 = make_idesc_tf32(128, NB3, false, false);
 
@@ -136,7 +153,7 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, uint8_t* smem, 
         vn_mean = s.mean; vn_std = s.std;
     }
 
-    float gh_acc[4] = {0.f, 0.f, 0.f, 0.f};   // GH outputs o = tid + 128*q  (j = o/64, k = o%64), o < n*64
+    float gh_acc[2] = {0.f, 0.f};             // GH outputs o = tid + 256*q  (j = o/64, k = o%64), o < n*64
     float dbh_acc = 0.f;                        // thread t < n: sum_m dL[m][t]
     float loss0 = 0.f, loss1 = 0.f, loss2 = 0.f;
     uint32_t it = 0;
@@ -144,7 +161,7 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, uint8_t* smem, 
     const long long n_tiles = (a.batch_rows + T_M - 1) / T_M;
     for (long long tile = cta; tile < n_tiles; tile += G, ++it) {
         const uint32_t par = it & 1u;
-        const long long r = tile * T_M + tid;
+        const long long r = tile * T_M + row;
         const bool valid = r < a.batch_rows;
         const long long gi = valid ? (a.indices ? a.indices[r] : a.row_begin + r) : -1;
 
@@ -155,10 +172,10 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, uint8_t* smem, 
         float x[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) x[k] = (valid && k < d) ? obs[gi * d + k] : 0.f;
-        unsigned long long posmask = 0ull;
+        unsigned posmask = 0u;   // sign bits of this thread's 32 pre-activations
         float s = 0.f, sq = 0.f;
 #pragma unroll 1
-        for (int c = 0; c < 8; ++c) {
+        for (int c = c0; c < c0 + 4; ++c) {
             float hv[8];
             {
                 const float4 b0 = *reinterpret_cast<const float4*>(b1s + 8 * c), b1v = *reinterpret_cast<const float4*>(b1s + 8 * c + 4);
@@ -174,37 +191,37 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, uint8_t* smem, 
             }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                if (hv[i] > 0.f) posmask |= 1ull << (8 * c + i);
+                if (hv[i] > 0.f) posmask |= 1u << (8 * (c - c0) + i);
                 hv[i] = act_fwd(hv[i], a.activation_id);
                 s += hv[i]; sq = fmaf(hv[i], hv[i], sq);
             }
-            *reinterpret_cast<float4*>(A12 + poff(LBO_A, tid, 8 * c)) = make_float4(hv[0], hv[1], hv[2], hv[3]);
-            *reinterpret_cast<float4*>(A12 + poff(LBO_A, tid, 8 * c + 4)) = make_float4(hv[4], hv[5], hv[6], hv[7]);
+            *reinterpret_cast<float4*>(A12 + poff(LBO_A, row, 8 * c)) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+            *reinterpret_cast<float4*>(A12 + poff(LBO_A, row, 8 * c + 4)) = make_float4(hv[4], hv[5], hv[6], hv[7]);
         }
+        PAIR_SUM2(s, sq);   // also orders this tile after every thread's GH reads of the previous tile
         const float mu1 = s * (1.f / H);
         const float rstd1 = 1.0f / sqrtf(fmaxf(sq * (1.f / H) - mu1 * mu1, 0.f) + LN_EPS);
 
         // previous tile's GEMM3 must have finished reading A3 / B3
         if (it > 0) mbar_wait(&bars[2], (it - 1) & 1u);
-        __syncthreads();   // all threads done with the previous tile's GH reads of N3s / DLs
         // pass 2: normalise -> n1 row (GEMM1 A operand) and n1^T (GEMM3 B operand), TF32-rounded
 #pragma unroll 1
-        for (int c = 0; c < 8; ++c) {
-            const float4 r0 = *reinterpret_cast<const float4*>(A12 + poff(LBO_A, tid, 8 * c));
-            const float4 r1 = *reinterpret_cast<const float4*>(A12 + poff(LBO_A, tid, 8 * c + 4));
+        for (int c = c0; c < c0 + 4; ++c) {
+            const float4 r0 = *reinterpret_cast<const float4*>(A12 + poff(LBO_A, row, 8 * c));
+            const float4 r1 = *reinterpret_cast<const float4*>(A12 + poff(LBO_A, row, 8 * c + 4));
             float4 v0, v1;
             v0.x = to_tf32((r0.x - mu1) * rstd1); v0.y = to_tf32((r0.y - mu1) * rstd1); v0.z = to_tf32((r0.z - mu1) * rstd1); v0.w = to_tf32((r0.w - mu1) * rstd1);
             v1.x = to_tf32((r1.x - mu1) * rstd1); v1.y = to_tf32((r1.y - mu1) * rstd1); v1.z = to_tf32((r1.z - mu1) * rstd1); v1.w = to_tf32((r1.w - mu1) * rstd1);
-            *reinterpret_cast<float4*>(A12 + poff(LBO_A, tid, 8 * c)) = v0;
-            *reinterpret_cast<float4*>(A12 + poff(LBO_A, tid, 8 * c + 4)) = v1;
-            uint8_t* bt = B3 + poff(LBO_B3, 8 * c, tid);
+            *reinterpret_cast<float4*>(A12 + poff(LBO_A, row, 8 * c)) = v0;
+            *reinterpret_cast<float4*>(A12 + poff(LBO_A, row, 8 * c + 4)) = v1;
+            uint8_t* bt = B3 + poff(LBO_B3, 8 * c, row);
             *reinterpret_cast<float*>(bt) = v0.x; *reinterpret_cast<float*>(bt + 16) = v0.y;
             *reinterpret_cast<float*>(bt + 32) = v0.z; *reinterpret_cast<float*>(bt + 48) = v0.w;
             *reinterpret_cast<float*>(bt + 64) = v1.x; *reinterpret_cast<float*>(bt + 80) = v1.y;
             *reinterpret_cast<float*>(bt + 96) = v1.z; *reinterpret_cast<float*>(bt + 112) = v1.w;
         }
 #pragma unroll
-        for (int k = 0; k < 8; ++k) if (k < d) pst(B3, LBO_B3, 64 + k, tid, to_tf32(x[k]));
+        for (int k = 0; k < 8; ++k) if (half == 0 && k < d) pst(B3, LBO_B3, 64 + k, row, to_tf32(x[k]));
         fence_proxy_async();
         tcgen05_fence_before();
         __syncthreads();
@@ -228,40 +245,44 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, uint8_t* smem, 
         // ---- Z3 (TMEM) + b3f -> moments (pass 1, raw to N3s) -> n3 (pass 2, in place) + head dots ----
         float s3 = 0.f, q3 = 0.f;
 #pragma unroll 1
-        for (int c = 0; c < 8; ++c) {
+        for (int c = c0; c < c0 + 4; ++c) {
             float z[8];
             tmem_ld_row8(tmem_row + 8 * c, z);
 #pragma unroll
             for (int i = 0; i < 8; ++i) { z[i] += b3f[8 * c + i]; s3 += z[i]; q3 = fmaf(z[i], z[i], q3); }
-            *reinterpret_cast<float4*>(N3s + poff(LBO_A, tid, 8 * c)) = make_float4(z[0], z[1], z[2], z[3]);
-            *reinterpret_cast<float4*>(N3s + poff(LBO_A, tid, 8 * c + 4)) = make_float4(z[4], z[5], z[6], z[7]);
+            *reinterpret_cast<float4*>(N3s + poff(LBO_A, row, 8 * c)) = make_float4(z[0], z[1], z[2], z[3]);
+            *reinterpret_cast<float4*>(N3s + poff(LBO_A, row, 8 * c + 4)) = make_float4(z[4], z[5], z[6], z[7]);
         }
+        PAIR_SUM2(s3, q3);
         const float mu3 = s3 * (1.f / H);
         const float rstd3 = 1.0f / sqrtf(fmaxf(q3 * (1.f / H) - mu3 * mu3, 0.f) + LN_EPS);
         float out[MAX_OUT];
 #pragma unroll
         for (int j = 0; j < MAX_OUT; ++j) out[j] = 0.f;
 #pragma unroll 1
-        for (int c = 0; c < 8; ++c) {
-            float4 r0 = *reinterpret_cast<const float4*>(N3s + poff(LBO_A, tid, 8 * c));
-            float4 r1 = *reinterpret_cast<const float4*>(N3s + poff(LBO_A, tid, 8 * c + 4));
+        for (int c = c0; c < c0 + 4; ++c) {
+            float4 r0 = *reinterpret_cast<const float4*>(N3s + poff(LBO_A, row, 8 * c));
+            float4 r1 = *reinterpret_cast<const float4*>(N3s + poff(LBO_A, row, 8 * c + 4));
             r0.x = (r0.x - mu3) * rstd3; r0.y = (r0.y - mu3) * rstd3; r0.z = (r0.z - mu3) * rstd3; r0.w = (r0.w - mu3) * rstd3;
             r1.x = (r1.x - mu3) * rstd3; r1.y = (r1.y - mu3) * rstd3; r1.z = (r1.z - mu3) * rstd3; r1.w = (r1.w - mu3) * rstd3;
-            *reinterpret_cast<float4*>(N3s + poff(LBO_A, tid, 8 * c)) = r0;
-            *reinterpret_cast<float4*>(N3s + poff(LBO_A, tid, 8 * c + 4)) = r1;
-#pragma unroll
-            for (int j = 0; j < MAX_OUT; ++j) {
-                if (j < n) {
-                    const float4 w0 = *reinterpret_cast<const float4*>(whf + j * H + 8 * c), w1v = *reinterpret_cast<const float4*>(whf + j * H + 8 * c + 4);
-                    out[j] = fmaf(r0.x, w0.x, fmaf(r0.y, w0.y, fmaf(r0.z, w0.z, fmaf(r0.w, w0.w, out[j]))));
-                    out[j] = fmaf(r1.x, w1v.x, fmaf(r1.y, w1v.y, fmaf(r1.z, w1v.z, fmaf(r1.w, w1v.w, out[j]))));
-                }
+            *reinterpret_cast<float4*>(N3s + poff(LBO_A, row, 8 * c)) = r0;
+            *reinterpret_cast<float4*>(N3s + poff(LBO_A, row, 8 * c + 4)) = r1;
+            FOR_OUT(j) {
+                const float4 w0 = *reinterpret_cast<const float4*>(whf + j * H + 8 * c), w1v = *reinterpret_cast<const float4*>(whf + j * H + 8 * c + 4);
+                out[j] = fmaf(r0.x, w0.x, fmaf(r0.y, w0.y, fmaf(r0.z, w0.z, fmaf(r0.w, w0.w, out[j]))));
+                out[j] = fmaf(r1.x, w1v.x, fmaf(r1.y, w1v.y, fmaf(r1.z, w1v.z, fmaf(r1.w, w1v.w, out[j]))));
             }
+        }
+        {   // pair exchange of the partial head dots
+            FOR_OUT(j) xch[(half * T_M + row) * 8 + j] = out[j];
+            __syncthreads();
+            FOR_OUT(j) out[j] += xch[((half ^ 1) * T_M + row) * 8 + j];
+            __syncthreads();
         }
         // dot[j] = sum_k Whf[j][k] n3[k] (needed by the LayerNorm-3 backward); logits add the folded bias
         float dot[MAX_OUT];
 #pragma unroll
-        for (int j = 0; j < MAX_OUT; ++j) { dot[j] = out[j]; out[j] += (j < n) ? bhf[j] : 0.f; }
+        for (int j = 0; j < MAX_OUT; ++j) { dot[j] = out[j]; out[j] += (j < NOUT && j < n) ? bhf[j] : 0.f; }
 
         // ---- head loss + dL/dhead ----
         float dl[MAX_OUT];
@@ -293,9 +314,7 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, uint8_t* smem, 
                 float ent = 0.f;
 #pragma unroll
                 for (int j = 0; j < MAX_OUT; ++j) if (j < n) ent -= pr[j] * nl[j];
-                loss0 += -fminf(surr1, surr2) * wrow;
-                loss1 += ent * wrow;
-                loss2 += ratio;
+                if (half == 0) { loss0 += -fminf(surr1, surr2) * wrow; loss1 += ent * wrow; loss2 += ratio; }
                 const float dlp = -sel * adv * ratio * wrow, went = a.entropy_coef * wrow;
 #pragma unroll
                 for (int j = 0; j < MAX_OUT; ++j)
@@ -318,40 +337,38 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, uint8_t* smem, 
                     if (l_o > l_c) { l = l_o; dv = -go; } else if (l_c > l_o) { l = l_c; dv = dc; } else { l = l_o; dv = 0.5f * (-go) + 0.5f * dc; }
                 }
                 const float wrow = val_masks ? active * inv_act : inv_rows;
-                loss0 += l * wrow;
+                if (half == 0) loss0 += l * wrow;
                 dl[0] = a.value_loss_coef * wrow * dv;
             }
         }
         // ---- dn3 = dL . Whf ; LayerNorm-3 backward -> dZ3 (single pass: the two row means are
         //      mean(dn3) = sum_j dL[j] rowsum(Whf[j]) / 64 and mean(dn3 n3) = sum_j dL[j] dot[j] / 64) ----
         float m1 = 0.f, m2 = 0.f;
-#pragma unroll
-        for (int j = 0; j < MAX_OUT; ++j) if (j < n) { m1 = fmaf(dl[j], swh[j], m1); m2 = fmaf(dl[j], dot[j], m2); }
+        FOR_OUT(j) { m1 = fmaf(dl[j], swh[j], m1); m2 = fmaf(dl[j], dot[j], m2); }
         m1 *= (1.f / H); m2 *= (1.f / H);
 #pragma unroll 1
-        for (int c = 0; c < 8; ++c) {
-            const float4 n0 = *reinterpret_cast<const float4*>(N3s + poff(LBO_A, tid, 8 * c));
-            const float4 n1v = *reinterpret_cast<const float4*>(N3s + poff(LBO_A, tid, 8 * c + 4));
+        for (int c = c0; c < c0 + 4; ++c) {
+            const float4 n0 = *reinterpret_cast<const float4*>(N3s + poff(LBO_A, row, 8 * c));
+            const float4 n1v = *reinterpret_cast<const float4*>(N3s + poff(LBO_A, row, 8 * c + 4));
             float g8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int j = 0; j < MAX_OUT; ++j) {
-                if (j < n) {
-                    const float4 w0 = *reinterpret_cast<const float4*>(whf + j * H + 8 * c), w1v = *reinterpret_cast<const float4*>(whf + j * H + 8 * c + 4);
-                    g8[0] = fmaf(dl[j], w0.x, g8[0]); g8[1] = fmaf(dl[j], w0.y, g8[1]); g8[2] = fmaf(dl[j], w0.z, g8[2]); g8[3] = fmaf(dl[j], w0.w, g8[3]);
-                    g8[4] = fmaf(dl[j], w1v.x, g8[4]); g8[5] = fmaf(dl[j], w1v.y, g8[5]); g8[6] = fmaf(dl[j], w1v.z, g8[6]); g8[7] = fmaf(dl[j], w1v.w, g8[7]);
-                }
+            FOR_OUT(j) {
+                const float4 w0 = *reinterpret_cast<const float4*>(whf + j * H + 8 * c), w1v = *reinterpret_cast<const float4*>(whf + j * H + 8 * c + 4);
+                g8[0] = fmaf(dl[j], w0.x, g8[0]); g8[1] = fmaf(dl[j], w0.y, g8[1]); g8[2] = fmaf(dl[j], w0.z, g8[2]); g8[3] = fmaf(dl[j], w0.w, g8[3]);
+                g8[4] = fmaf(dl[j], w1v.x, g8[4]); g8[5] = fmaf(dl[j], w1v.y, g8[5]); g8[6] = fmaf(dl[j], w1v.z, g8[6]); g8[7] = fmaf(dl[j], w1v.w, g8[7]);
             }
             const float nn[8] = {n0.x, n0.y, n0.z, n0.w, n1v.x, n1v.y, n1v.z, n1v.w};
 #pragma unroll
             for (int i = 0; i < 8; ++i) g8[i] = to_tf32(rstd3 * (g8[i] - m1 - nn[i] * m2));
-            *reinterpret_cast<float4*>(A12 + poff(LBO_A, tid, 8 * c)) = make_float4(g8[0], g8[1], g8[2], g8[3]);       // dZ3 row
-            *reinterpret_cast<float4*>(A12 + poff(LBO_A, tid, 8 * c + 4)) = make_float4(g8[4], g8[5], g8[6], g8[7]);
-            uint8_t* at = A3 + poff(LBO_A, 8 * c, tid);                                                                // dZ3^T
+            *reinterpret_cast<float4*>(A12 + poff(LBO_A, row, 8 * c)) = make_float4(g8[0], g8[1], g8[2], g8[3]);       // dZ3 row
+            *reinterpret_cast<float4*>(A12 + poff(LBO_A, row, 8 * c + 4)) = make_float4(g8[4], g8[5], g8[6], g8[7]);
+            uint8_t* at = A3 + poff(LBO_A, 8 * c, row);                                                                // dZ3^T
 #pragma unroll
             for (int i = 0; i < 8; ++i) *reinterpret_cast<float*>(at + 16 * i) = g8[i];
         }
-        *reinterpret_cast<float4*>(DLs + tid * 8) = make_float4(dl[0], dl[1], dl[2], dl[3]);
-        *reinterpret_cast<float4*>(DLs + tid * 8 + 4) = make_float4(dl[4], dl[5], dl[6], dl[7]);
+        if (half == 0) {
+            *reinterpret_cast<float4*>(DLs + row * 8) = make_float4(dl[0], dl[1], dl[2], dl[3]);
+            *reinterpret_cast<float4*>(DLs + row * 8 + 4) = make_float4(dl[4], dl[5], dl[6], dl[7]);
+        }
         fence_proxy_async();
         tcgen05_fence_before();
         __syncthreads();
@@ -366,27 +383,28 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, uint8_t* smem, 
         // ---- dN1 (TMEM) -> LayerNorm-1 backward -> activation backward -> dZ1^T (two passes over TMEM) ----
         float t1 = 0.f, t2 = 0.f;
 #pragma unroll 1
-        for (int c = 0; c < 8; ++c) {
+        for (int c = c0; c < c0 + 4; ++c) {
             float g8[8];
             tmem_ld_row8(tmem_row + 8 * c, g8);
-            const uint8_t* bt = B3 + poff(LBO_B3, 8 * c, tid);
+            const uint8_t* bt = B3 + poff(LBO_B3, 8 * c, row);
 #pragma unroll
             for (int i = 0; i < 8; ++i) { t1 += g8[i]; t2 = fmaf(g8[i], *reinterpret_cast<const float*>(bt + 16 * i), t2); }
         }
+        PAIR_SUM2(t1, t2);
         t1 *= (1.f / H); t2 *= (1.f / H);
         const float std1 = 1.0f / rstd1;
 #pragma unroll 1
-        for (int c = 0; c < 8; ++c) {
+        for (int c = c0; c < c0 + 4; ++c) {
             float g8[8];
             tmem_ld_row8(tmem_row + 8 * c, g8);
-            const uint8_t* bt = B3 + poff(LBO_B3, 8 * c, tid);
-            uint8_t* at = A3 + poff(LBO_A, 64 + 8 * c, tid);
+            const uint8_t* bt = B3 + poff(LBO_B3, 8 * c, row);
+            uint8_t* at = A3 + poff(LBO_A, 64 + 8 * c, row);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const float n1k = *reinterpret_cast<const float*>(bt + 16 * i);   // own column of n1^T
                 const float da = rstd1 * (g8[i] - t1 - n1k * t2);
                 const float aval = fmaf(n1k, std1, mu1);                          // activation output
-                *reinterpret_cast<float*>(at + 16 * i) = to_tf32(da * act_bwd(aval, (posmask >> (8 * c + i)) & 1ull, a.activation_id));
+                *reinterpret_cast<float*>(at + 16 * i) = to_tf32(da * act_bwd(aval, (posmask >> (8 * (c - c0) + i)) & 1u, a.activation_id));
             }
         }
         fence_proxy_async();
@@ -400,7 +418,7 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, uint8_t* smem, 
         }
         // ---- GH += dL^T n3 (FFMA reduction over the tile rows, n3 read back from N3s) ----
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < 2; ++q) {
             const int o = tid + T_NT * q;
             if (o < n * H) {
                 const int j = o >> 6, k = o & 63;
@@ -424,45 +442,43 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, uint8_t* smem, 
     if (it > 0) {
         mbar_wait(&bars[2], (it - 1) & 1u);
         tcgen05_fence_after();
-        float lo[32], hi[32], ex[16];
-        tmem_ld_row32_nowait(tmem_row + 64, lo);
-        tmem_ld_row32_nowait(tmem_row + 96, hi);
-        tmem_ld_wait();
-        {
+        float v32[32];
+        tmem_ld_row32(tmem_row + 64 + 32 * half, v32);   // G columns [32*half, 32*half+32) of this row
+        if (row < 64) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) part[fo.g3 + row * H + 32 * half + c] = v32[c];
+        }
+        if (half == 0) {
             uint32_t r16[16];
             asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                          : "=r"(r16[0]), "=r"(r16[1]), "=r"(r16[2]), "=r"(r16[3]), "=r"(r16[4]), "=r"(r16[5]), "=r"(r16[6]), "=r"(r16[7]),
                            "=r"(r16[8]), "=r"(r16[9]), "=r"(r16[10]), "=r"(r16[11]), "=r"(r16[12]), "=r"(r16[13]), "=r"(r16[14]), "=r"(r16[15])
                          : "r"(tmem_row + 128));
             tmem_ld_wait();
+            if (row < 64) {
+                part[fo.db3 + row] = __uint_as_float(r16[8]);
+            } else {
+                const int j = row - 64;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) ex[i] = __uint_as_float(r16[i]);
-        }
-        if (tid < 64) {
-#pragma unroll
-            for (int c = 0; c < 32; ++c) { part[fo.g3 + tid * H + c] = lo[c]; part[fo.g3 + tid * H + 32 + c] = hi[c]; }
-            part[fo.db3 + tid] = ex[8];
-        } else {
-            const int j = tid - 64;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) if (c < d) part[fo.g1 + j * d + c] = ex[c];
-            part[fo.db1 + j] = ex[8];
+                for (int c = 0; c < 8; ++c) if (c < d) part[fo.g1 + j * d + c] = __uint_as_float(r16[c]);
+                part[fo.db1 + j] = __uint_as_float(r16[8]);
+            }
         }
     } else {
         for (int i = tid; i < fo.gh; i += T_NT) part[i] = 0.f;   // G1, db1, G3, db3 of an idle CTA
     }
 #pragma unroll
-    for (int q = 0; q < 4; ++q) { const int o = tid + T_NT * q; if (o < n * H) part[fo.gh + o] = gh_acc[q]; }
+    for (int q = 0; q < 2; ++q) { const int o = tid + T_NT * q; if (o < n * H) part[fo.gh + o] = gh_acc[q]; }
     if (tid < n) part[fo.dbh + tid] = dbh_acc;
     {
         float v[3] = {loss0, loss1, loss2};
         const int lane = tid & 31;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) { const float sv = warp_sum(v[k]); if (lane == 0) red[k * 4 + warp] = sv; }
+        for (int k = 0; k < 3; ++k) { const float sv = warp_sum(v[k]); if (lane == 0) red[k * 8 + warp] = sv; }
         __syncthreads();
         if (tid < N_LOSS_TC) {
             float sv = 0.f;
-            if (tid < 3) sv = red[tid * 4] + red[tid * 4 + 1] + red[tid * 4 + 2] + red[tid * 4 + 3];
+            if (tid < 3) for (int wv = 0; wv < T_NT / 32; ++wv) sv += red[tid * 8 + wv];
             part[stride - N_LOSS_TC + tid] = sv;
         }
     }
@@ -474,8 +490,13 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, uint8_t* smem, 
 __global__ void __launch_bounds__(T_NT, 1) ppo_fwdbwd_tc_kernel(const OrlPpoArgs a, int stride) {
     extern __shared__ __align__(1024) uint8_t smem_tc[];
     const int G = a.grid_per_net;
-    if ((int)blockIdx.x < G) tc_net_pass<true>(a, smem_tc, blockIdx.x, G, stride);
-    else tc_net_pass<false>(a, smem_tc, blockIdx.x - G, G, stride);
+    if ((int)blockIdx.x < G) {
+        if (a.n_actions == 2) tc_net_pass<true, 2>(a, smem_tc, blockIdx.x, G, stride);
+        else if (a.n_actions == 5) tc_net_pass<true, 5>(a, smem_tc, blockIdx.x, G, stride);
+        else tc_net_pass<true, 8>(a, smem_tc, blockIdx.x, G, stride);
+    } else {
+        tc_net_pass<false, 1>(a, smem_tc, blockIdx.x - G, G, stride);
+    }
 }
 
 }  // namespace
@@ -487,7 +508,7 @@ int launch_ppo_fwdbwd_tc(const OrlPpoArgs& a, cudaStream_t st) {
         return ORL_ERR_UNSUPPORTED;
     }
     const size_t smem = 16 * LBO_A + 32 * LBO_A + 32 * LBO_B3 + 2 * 16 * LBO_W + 16 * LBO_A +
-                        sizeof(float) * (8 * H + H + H + MAX_OUT * H + 2 * MAX_OUT + T_M * 8 + 32) + 3 * 8 + 16 + 128;
+                        sizeof(float) * (8 * H + H + H + MAX_OUT * H + 2 * MAX_OUT + T_M * 8 + 2 * T_M * 8 + 32) + 3 * 8 + 16 + 128;
     static bool attr_set = false;
     if (!attr_set) {
         int e = check_cuda(cudaFuncSetAttribute(ppo_fwdbwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),

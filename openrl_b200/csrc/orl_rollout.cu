@@ -14,8 +14,7 @@
 namespace {
 using namespace orl;
 
-constexpr int R_M = 32;    // rows per CTA
-constexpr int R_NT = 128;  // threads per CTA
+constexpr int R_NT = 128;  // threads per CTA; rows per CTA R_M is a template parameter (8 / 16 / 32)
 
 
 struct EnvPtrs {
@@ -106,6 +105,7 @@ __device__ __forceinline__ int sample_categorical(const float (&p)[MAX_OUT], int
     return best;
 }
 
+template <int R_M>
 __global__ void __launch_bounds__(R_NT) rollout_kernel(const OrlRolloutArgs a) {
     extern __shared__ __align__(16) float smem[];
     const int N = a.n_envs, A = a.n_agents, B = N * A, d = a.obs_dim, n = a.n_actions;
@@ -299,7 +299,7 @@ extern "C" int orl_env_step(int env_kind, int n_envs, int n_agents, double* env_
 extern "C" int orl_rollout(const OrlRolloutArgs* args, void* stream) {
     ORL_CHECK_ARG(args, "args");
     const OrlRolloutArgs& a = *args;
-    ORL_CHECK_ARG(a.n_envs > 0 && a.n_agents > 0 && a.n_agents <= R_M, "n_envs / n_agents");
+    ORL_CHECK_ARG(a.n_envs > 0 && a.n_agents > 0 && a.n_agents <= 32, "n_envs / n_agents");
     ORL_CHECK_ARG(a.obs_dim > 0 && a.obs_dim <= 64, "obs_dim must be in 1..64");
     ORL_CHECK_ARG(a.n_actions > 0 && a.n_actions <= orl::MAX_OUT, "n_actions must be in 1..8");
     ORL_CHECK_ARG(a.t_begin >= 0 && a.t_begin < a.t_end && a.t_end <= a.episode_length, "step range");
@@ -319,18 +319,30 @@ extern "C" int orl_rollout(const OrlRolloutArgs* args, void* stream) {
         orl::set_last_error("orl_rollout: unsupported env_kind %d", a.env_kind);
         return ORL_ERR_UNSUPPORTED;
     }
-    const int envs_per_cta = R_M / a.n_agents;
+    // rows per CTA: the step chain is latency-bound, so prefer many small CTAs (>= ~4 per SM) and
+    // only grow the tile when there are enough rows to keep that many CTAs anyway
+    const long long B = (long long)a.n_envs * a.n_agents;
+    const long long want = 4LL * orl::sm_count();
+    int rm = 32;
+    if (B / 32 < want) rm = 16;
+    if (B / 16 < want) rm = 8;
+    while (rm < a.n_agents) rm *= 2;
+    const int envs_per_cta = rm / a.n_agents;
     const int grid = (a.n_envs + envs_per_cta - 1) / envs_per_cta;
     const int ldx = orl::pad4(a.obs_dim) + 4;
-    const size_t smem = sizeof(float) * (orl::smem_weights_floats(a.obs_dim, false) + R_M * ldx + 2 * R_M * orl::LDA + R_M);
+    const size_t smem = sizeof(float) * (orl::smem_weights_floats(a.obs_dim, false) + rm * ldx + 2 * rm * orl::LDA + rm);
     static bool attr_set = false;
     if (!attr_set) {
-        int e = orl::check_cuda(cudaFuncSetAttribute(rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
-                                "cudaFuncSetAttribute(rollout)");
+        int e = orl::check_cuda(cudaFuncSetAttribute(rollout_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), "attr");
+        if (!e) e = orl::check_cuda(cudaFuncSetAttribute(rollout_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), "attr");
+        if (!e) e = orl::check_cuda(cudaFuncSetAttribute(rollout_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), "attr");
         if (e) return e;
         attr_set = true;
     }
-    rollout_kernel<<<grid, R_NT, smem, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (rm == 8) rollout_kernel<8><<<grid, R_NT, smem, st>>>(a);
+    else if (rm == 16) rollout_kernel<16><<<grid, R_NT, smem, st>>>(a);
+    else rollout_kernel<32><<<grid, R_NT, smem, st>>>(a);
     ORL_LAUNCH_CHECK("rollout_kernel");
     if (a.rng_counter) {
         bump_counter_kernel<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a.rng_counter, (uint64_t)(a.t_end - a.t_begin));
