@@ -116,3 +116,132 @@ __device__ __forceinline__ void gridworld_reset(int& x, int& y, int env, int nre
 }
 
 }  // namespace orl
+
+// ---- MPE simple_spread (3 agents, 3 landmarks) ------------------------------------------------
+// Reference: World.step + forces + integrate  openrl/envs/mpe/core.py:216-344,
+// MultiAgentEnv.step/_set_action/reset        openrl/envs/mpe/multiagent_env.py:167-243,274-339,
+// Scenario.reset_world/reward/observation     openrl/envs/mpe/scenarios/simple_spread.py:46-125.
+// float64 state like the reference (numpy): env_f64 [18][N] = agent pos (3x2), agent vel (3x2),
+// landmark pos (3x2); env_i32 [N] = current_step; env_u64 = the env's PCG64 np_random.
+// One thread steps one env (its 3 agents).
+namespace orl {
+
+struct MpeState { double pos[3][2], vel[3][2], lm[3][2]; };
+
+__device__ __forceinline__ void mpe_load(const double* __restrict__ f, int e, int N, MpeState& s) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            s.pos[a][c] = f[(size_t)(a * 2 + c) * N + e];
+            s.vel[a][c] = f[(size_t)(6 + a * 2 + c) * N + e];
+            s.lm[a][c] = f[(size_t)(12 + a * 2 + c) * N + e];
+        }
+}
+__device__ __forceinline__ void mpe_store(double* __restrict__ f, int e, int N, const MpeState& s) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            f[(size_t)(a * 2 + c) * N + e] = s.pos[a][c];
+            f[(size_t)(6 + a * 2 + c) * N + e] = s.vel[a][c];
+            f[(size_t)(12 + a * 2 + c) * N + e] = s.lm[a][c];
+        }
+}
+__device__ __forceinline__ void mpe_reset(MpeState& s, Pcg64& g) {  // simple_spread.py:46-62
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        s.pos[a][0] = pcg_uniform(g, -1.0, 2.0); s.pos[a][1] = pcg_uniform(g, -1.0, 2.0);
+        s.vel[a][0] = 0.0; s.vel[a][1] = 0.0;
+    }
+#pragma unroll
+    for (int l = 0; l < 3; ++l) {
+        s.lm[l][0] = __dmul_rn(0.8, pcg_uniform(g, -1.0, 2.0)); s.lm[l][1] = __dmul_rn(0.8, pcg_uniform(g, -1.0, 2.0));
+    }
+}
+__device__ __forceinline__ double mpe_dist(const double (&p)[2], const double (&q)[2]) {
+    const double dx = __dsub_rn(p[0], q[0]), dy = __dsub_rn(p[1], q[1]);
+    return sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+}
+// numpy.logaddexp(0, v)
+__device__ __forceinline__ double logaddexp0(double v) {
+    if (v == 0.0) return 0.6931471805599453;
+    return v < 0.0 ? log1p(exp(v)) : __dadd_rn(v, log1p(exp(-v)));
+}
+__device__ __forceinline__ void mpe_world_step(MpeState& s, const int (&act)[3]) {
+    const double dt = 0.1, damping = 0.25, contact_force = 1e2, k = 1e-3, dist_min = 0.15 + 0.15;
+    double f[3][2];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {  // _set_action + apply_action_force (mass 1, sensitivity 5)
+        const double u0 = (act[a] == 1 ? 1.0 : 0.0) - (act[a] == 2 ? 1.0 : 0.0);
+        const double u1 = (act[a] == 3 ? 1.0 : 0.0) - (act[a] == 4 ? 1.0 : 0.0);
+        f[a][0] = __dmul_rn(u0, 5.0); f[a][1] = __dmul_rn(u1, 5.0);
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = a + 1; b < 3; ++b) {  // apply_environment_force: agent-agent contacts only
+            const double dx = __dsub_rn(s.pos[a][0], s.pos[b][0]), dy = __dsub_rn(s.pos[a][1], s.pos[b][1]);
+            const double dist = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+            const double pen = __dmul_rn(logaddexp0(__ddiv_rn(-__dsub_rn(dist, dist_min), k)), k);
+            const double fx = __dmul_rn(__ddiv_rn(__dmul_rn(contact_force, dx), dist), pen);
+            const double fy = __dmul_rn(__ddiv_rn(__dmul_rn(contact_force, dy), dist), pen);
+            f[a][0] = __dadd_rn(fx, f[a][0]); f[a][1] = __dadd_rn(fy, f[a][1]);
+            f[b][0] = __dadd_rn(-fx, f[b][0]); f[b][1] = __dadd_rn(-fy, f[b][1]);
+        }
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {  // integrate_state
+            double v = __dmul_rn(s.vel[a][c], 1.0 - damping);
+            v = __dadd_rn(v, __dmul_rn(f[a][c], dt));
+            s.vel[a][c] = v;
+            s.pos[a][c] = __dadd_rn(s.pos[a][c], __dmul_rn(v, dt));
+        }
+}
+// shared reward: sum over agents of (-sum_l min_a dist(a,l) - #collisions incl. self)
+__device__ __forceinline__ double mpe_shared_reward(const MpeState& s) {
+    double lm_term = 0.0;  // rew -= min(dists) per landmark, starting from integer 0
+    double rew_base;
+    {
+        double r = 0.0;
+#pragma unroll
+        for (int l = 0; l < 3; ++l) {
+            const double d0 = mpe_dist(s.pos[0], s.lm[l]), d1 = mpe_dist(s.pos[1], s.lm[l]), d2 = mpe_dist(s.pos[2], s.lm[l]);
+            r = __dsub_rn(r, fmin(fmin(d0, d1), d2));
+        }
+        rew_base = r;
+    }
+    (void)lm_term;
+    double total = 0.0;
+#pragma unroll
+    for (int ag = 0; ag < 3; ++ag) {
+        double r = rew_base;
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+            if (mpe_dist(s.pos[a], s.pos[ag]) < 0.3) r = __dsub_rn(r, 1.0);
+        total = (ag == 0) ? r : __dadd_rn(total, r);
+    }
+    return total;
+}
+// observation of agent a (18 values) as float32
+__device__ __forceinline__ void mpe_obs(const MpeState& s, int a, float (&o)[18]) {
+    o[0] = (float)s.vel[a][0]; o[1] = (float)s.vel[a][1]; o[2] = (float)s.pos[a][0]; o[3] = (float)s.pos[a][1];
+#pragma unroll
+    for (int l = 0; l < 3; ++l) {
+        o[4 + 2 * l] = (float)__dsub_rn(s.lm[l][0], s.pos[a][0]);
+        o[5 + 2 * l] = (float)__dsub_rn(s.lm[l][1], s.pos[a][1]);
+    }
+    int w = 10;
+#pragma unroll
+    for (int ot = 0; ot < 3; ++ot) {
+        if (ot != a) {
+            o[w] = (float)__dsub_rn(s.pos[ot][0], s.pos[a][0]);
+            o[w + 1] = (float)__dsub_rn(s.pos[ot][1], s.pos[a][1]);
+            w += 2;
+        }
+    }
+    o[14] = 0.f; o[15] = 0.f; o[16] = 0.f; o[17] = 0.f;
+}
+
+}  // namespace orl

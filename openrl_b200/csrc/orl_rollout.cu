@@ -80,6 +80,53 @@ __device__ __forceinline__ void env_step_single(const EnvPtrs& E, int kind, int 
     }
 }
 
+// One simple_spread env.step (3 agents) with auto-reset at world_length = 25.
+__device__ __forceinline__ void env_step_mpe(const EnvPtrs& E, int e, int N, const int (&acts)[3], float (&ob)[3][18],
+                                             float& reward, bool& done) {
+    MpeState s;
+    mpe_load(E.f64, e, N, s);
+    int step = E.i32[e] + 1;
+    mpe_world_step(s, acts);
+    const double r = mpe_shared_reward(s);
+    reward = (float)r;
+    done = step >= 25;
+    float ret = E.ep_return[e] + reward;
+    int len = E.ep_length[e] + 1;
+    if (done) {
+        Pcg64 g = pcg_load(E.u64, e, N);
+        mpe_reset(s, g);
+        pcg_store(E.u64, e, N, g);
+        step = 0;
+        atomicAdd(E.episode_stats + 0, (double)ret);
+        atomicAdd(E.episode_stats + 1, (double)len);
+        atomicAdd(E.episode_stats + 2, 1.0);
+        ret = 0.f; len = 0;
+    }
+    E.ep_return[e] = ret; E.ep_length[e] = len;
+    E.i32[e] = step;
+    mpe_store(E.f64, e, N, s);
+#pragma unroll
+    for (int ag = 0; ag < 3; ++ag) mpe_obs(s, ag, ob[ag]);
+}
+
+__global__ void env_step_mpe_kernel(int N, EnvPtrs E, const float* __restrict__ actions, float* __restrict__ obs_out,
+                                    float* __restrict__ critic_obs_out, float* __restrict__ rewards_out,
+                                    float* __restrict__ dones_out) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= N) return;
+    const int acts[3] = {(int)actions[e * 3], (int)actions[e * 3 + 1], (int)actions[e * 3 + 2]};
+    float ob[3][18], reward; bool done;
+    env_step_mpe(E, e, N, acts, ob, reward, done);
+    for (int ag = 0; ag < 3; ++ag) {
+        for (int k = 0; k < 18; ++k) {
+            obs_out[((size_t)e * 3 + ag) * 18 + k] = ob[ag][k];
+            if (critic_obs_out) for (int dst = 0; dst < 3; ++dst) critic_obs_out[((size_t)e * 3 + dst) * 54 + ag * 18 + k] = ob[ag][k];
+        }
+        rewards_out[e * 3 + ag] = reward;
+        dones_out[e * 3 + ag] = done ? 1.f : 0.f;
+    }
+}
+
 __global__ void env_step_kernel(int kind, int N, EnvPtrs E, const float* __restrict__ actions, float* __restrict__ obs_out,
                                 float* __restrict__ rewards_out, float* __restrict__ dones_out, float* __restrict__ final_obs_out) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -105,7 +152,7 @@ __device__ __forceinline__ int sample_categorical(const float (&p)[MAX_OUT], int
     return best;
 }
 
-template <int R_M>
+template <int R_M, int ENV>
 __global__ void __launch_bounds__(R_NT) rollout_kernel(const OrlRolloutArgs a) {
     extern __shared__ __align__(16) float smem[];
     const int N = a.n_envs, A = a.n_agents, B = N * A, d = a.obs_dim, n = a.n_actions;
@@ -185,18 +232,43 @@ __global__ void __launch_bounds__(R_NT) rollout_kernel(const OrlRolloutArgs a) {
         __syncthreads();
 
         // ---- env.step for the envs of this CTA (one thread per env) ----
-        if (a.env_kind != ORL_ENV_NONE && tid < n_env_here) {
+        if (ENV == ORL_ENV_MPE_SPREAD && tid < n_env_here) {
+          if constexpr (ENV == ORL_ENV_MPE_SPREAD) {
+            const int e = env0 + tid;
+            EnvPtrs E{a.env_f64, a.env_u64, a.env_i32, a.env_table, a.env_table_len, a.rng_seed,
+                      a.ep_return, a.ep_length, a.episode_stats};
+            const int acts[3] = {act_s[tid * 3], act_s[tid * 3 + 1], act_s[tid * 3 + 2]};
+            float ob[3][18], reward; bool done;
+            env_step_mpe(E, e, N, acts, ob, reward, done);
+            const size_t r1 = (size_t)(t + 1) * B + (size_t)e * 3;
+#pragma unroll
+            for (int ag = 0; ag < 3; ++ag) {
+#pragma unroll
+                for (int k = 0; k < 18; ++k) {
+                    Xs[(tid * 3 + ag) * ldx + k] = ob[ag][k];
+                    a.policy_obs[(r1 + ag) * 18 + k] = ob[ag][k];
+#pragma unroll
+                    for (int dst = 0; dst < 3; ++dst) a.critic_obs[(r1 + dst) * 54 + ag * 18 + k] = ob[ag][k];
+                }
+                a.rewards[(size_t)t * B + (size_t)e * 3 + ag] = reward;
+                a.masks[r1 + ag] = done ? 0.f : 1.f;
+                a.active_masks[r1 + ag] = 1.f;  // all agents finish together (onpolicy_driver.py:118-124)
+            }
+          }
+        } else if (ENV != ORL_ENV_NONE && ENV != ORL_ENV_MPE_SPREAD && tid < n_env_here) {
+          if constexpr (ENV == ORL_ENV_CARTPOLE || ENV == ORL_ENV_GRIDWORLD) {
             const int e = env0 + tid;
             EnvPtrs E{a.env_f64, a.env_u64, a.env_i32, a.env_table, a.env_table_len, a.rng_seed,
                       a.ep_return, a.ep_length, a.episode_stats};
             float ob[4], fin[4], reward; bool done;
-            env_step_single(E, a.env_kind, e, N, act_s[tid], ob, reward, done, fin);
+            env_step_single(E, ENV, e, N, act_s[tid], ob, reward, done, fin);
             const size_t o1 = ((size_t)(t + 1) * B + e);
 #pragma unroll
             for (int k = 0; k < 4; ++k) { Xs[tid * ldx + k] = ob[k]; a.policy_obs[o1 * 4 + k] = ob[k]; }
             a.rewards[(size_t)t * B + e] = reward;
             a.masks[o1] = done ? 0.f : 1.f;
             a.active_masks[o1] = 1.f;  // onpolicy_driver.py:118-124 with A == 1
+          }
         }
         __syncthreads();
     }
@@ -205,9 +277,27 @@ __global__ void __launch_bounds__(R_NT) rollout_kernel(const OrlRolloutArgs a) {
 __global__ void bump_counter_kernel(uint64_t* c, uint64_t by) { *c += by; }
 
 __global__ void env_reset_kernel(int env_kind, int N, double* env_f64, uint64_t* env_u64, int32_t* env_i32,
-                                 const int32_t* env_table, int env_table_len, uint64_t seed, float* obs_out) {
+                                 const int32_t* env_table, int env_table_len, uint64_t seed, float* obs_out,
+                                 float* critic_obs_out) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= N) return;
+    if (env_kind == ORL_ENV_MPE_SPREAD) {
+        MpeState s;
+        Pcg64 g = pcg_load(env_u64, e, N);
+        mpe_reset(s, g);
+        pcg_store(env_u64, e, N, g);
+        mpe_store(env_f64, e, N, s);
+        env_i32[e] = 0;
+        for (int ag = 0; ag < 3; ++ag) {
+            float o[18];
+            mpe_obs(s, ag, o);
+            for (int k = 0; k < 18; ++k) {
+                obs_out[((size_t)e * 3 + ag) * 18 + k] = o[k];
+                if (critic_obs_out) for (int dst = 0; dst < 3; ++dst) critic_obs_out[((size_t)e * 3 + dst) * 54 + ag * 18 + k] = o[k];
+            }
+        }
+        return;
+    }
     if (env_kind == ORL_ENV_CARTPOLE) {
         double s[4];
         Pcg64 g = pcg_load(env_u64, e, N);
@@ -268,13 +358,13 @@ extern "C" int orl_env_reset(int env_kind, int n_envs, int n_agents, double* env
                              float* policy_obs_out, float* critic_obs_out, void* stream) {
     ORL_CHECK_ARG(n_envs > 0 && n_agents > 0, "n_envs/n_agents");
     ORL_CHECK_ARG(policy_obs_out, "policy_obs_out");
-    (void)critic_obs_out;
     if (env_kind == ORL_ENV_CARTPOLE) ORL_CHECK_ARG(env_f64 && env_u64 && env_i32 && n_agents == 1, "cartpole state");
     else if (env_kind == ORL_ENV_GRIDWORLD) ORL_CHECK_ARG(env_i32 && n_agents == 1, "gridworld state");
+    else if (env_kind == ORL_ENV_MPE_SPREAD) ORL_CHECK_ARG(env_f64 && env_u64 && env_i32 && n_agents == 3, "simple_spread state");
     else { orl::set_last_error("orl_env_reset: unsupported env_kind %d", env_kind); return ORL_ERR_UNSUPPORTED; }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     env_reset_kernel<<<(n_envs + 127) / 128, 128, 0, st>>>(env_kind, n_envs, env_f64, env_u64, env_i32, env_table,
-                                                          env_table_len, rng_seed, policy_obs_out);
+                                                          env_table_len, rng_seed, policy_obs_out, critic_obs_out);
     ORL_LAUNCH_CHECK("env_reset_kernel");
     return 0;
 }
@@ -284,8 +374,18 @@ extern "C" int orl_env_step(int env_kind, int n_envs, int n_agents, double* env_
                             const int32_t* env_table, int env_table_len, uint64_t rng_seed, float* ep_return,
                             int32_t* ep_length, double* episode_stats, const float* actions, float* obs_out,
                             float* rewards_out, float* dones_out, float* final_obs_out, void* stream) {
-    ORL_CHECK_ARG(n_envs > 0 && n_agents == 1, "n_envs / n_agents");
+    ORL_CHECK_ARG(n_envs > 0, "n_envs");
     ORL_CHECK_ARG(actions && obs_out && rewards_out && dones_out && ep_return && ep_length && episode_stats, "null buffer");
+    if (env_kind == ORL_ENV_MPE_SPREAD) {
+        ORL_CHECK_ARG(n_agents == 3 && env_f64 && env_u64 && env_i32, "simple_spread state");
+        EnvPtrs Em{env_f64, env_u64, env_i32, env_table, env_table_len, rng_seed, ep_return, ep_length, episode_stats};
+        // final_obs_out doubles as the critic observation output (B, 54) for this env kind
+        env_step_mpe_kernel<<<(n_envs + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+            n_envs, Em, actions, obs_out, final_obs_out, rewards_out, dones_out);
+        ORL_LAUNCH_CHECK("env_step_mpe_kernel");
+        return 0;
+    }
+    ORL_CHECK_ARG(n_agents == 1, "n_agents");
     if (env_kind == ORL_ENV_CARTPOLE) ORL_CHECK_ARG(env_f64 && env_u64 && env_i32, "cartpole state");
     else if (env_kind == ORL_ENV_GRIDWORLD) ORL_CHECK_ARG(env_i32, "gridworld state");
     else { orl::set_last_error("orl_env_step: unsupported env_kind %d", env_kind); return ORL_ERR_UNSUPPORTED; }
@@ -315,6 +415,10 @@ extern "C" int orl_rollout(const OrlRolloutArgs* args, void* stream) {
         ORL_CHECK_ARG(a.n_agents == 1 && a.obs_dim == 4 && a.n_actions == 5, "GridWorld shapes");
         ORL_CHECK_ARG(a.env_i32 && a.rewards && a.masks && a.active_masks && a.ep_return && a.ep_length &&
                           a.episode_stats, "GridWorld state buffers");
+    } else if (a.env_kind == ORL_ENV_MPE_SPREAD) {
+        ORL_CHECK_ARG(a.n_agents == 3 && a.obs_dim == 18 && a.critic_obs_dim == 54 && a.n_actions == 5, "simple_spread shapes");
+        ORL_CHECK_ARG(a.env_f64 && a.env_u64 && a.env_i32 && a.rewards && a.masks && a.active_masks && a.ep_return &&
+                          a.ep_length && a.episode_stats && a.critic_obs, "simple_spread state buffers");
     } else {
         orl::set_last_error("orl_rollout: unsupported env_kind %d", a.env_kind);
         return ORL_ERR_UNSUPPORTED;
@@ -331,18 +435,29 @@ extern "C" int orl_rollout(const OrlRolloutArgs* args, void* stream) {
     const int grid = (a.n_envs + envs_per_cta - 1) / envs_per_cta;
     const int ldx = orl::pad4(a.obs_dim) + 4;
     const size_t smem = sizeof(float) * (orl::smem_weights_floats(a.obs_dim, false) + rm * ldx + 2 * rm * orl::LDA + rm);
-    static bool attr_set = false;
-    if (!attr_set) {
-        int e = orl::check_cuda(cudaFuncSetAttribute(rollout_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), "attr");
-        if (!e) e = orl::check_cuda(cudaFuncSetAttribute(rollout_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), "attr");
-        if (!e) e = orl::check_cuda(cudaFuncSetAttribute(rollout_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), "attr");
-        if (e) return e;
-        attr_set = true;
-    }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (rm == 8) rollout_kernel<8><<<grid, R_NT, smem, st>>>(a);
-    else if (rm == 16) rollout_kernel<16><<<grid, R_NT, smem, st>>>(a);
-    else rollout_kernel<32><<<grid, R_NT, smem, st>>>(a);
+#define ORL_LAUNCH_ROLLOUT(RM, EK)                                                                                   \
+    do {                                                                                                             \
+        static bool attr_done = false;                                                                               \
+        if (!attr_done) {                                                                                            \
+            int e_ = orl::check_cuda(cudaFuncSetAttribute(rollout_kernel<RM, EK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), "attr"); \
+            if (e_) return e_;                                                                                       \
+            attr_done = true;                                                                                        \
+        }                                                                                                            \
+        rollout_kernel<RM, EK><<<grid, R_NT, smem, st>>>(a);                                                         \
+    } while (0)
+#define ORL_LAUNCH_ROLLOUT_RM(EK)                                                        \
+    do {                                                                                 \
+        if (rm == 8) ORL_LAUNCH_ROLLOUT(8, EK);                                          \
+        else if (rm == 16) ORL_LAUNCH_ROLLOUT(16, EK);                                   \
+        else ORL_LAUNCH_ROLLOUT(32, EK);                                                 \
+    } while (0)
+    switch (a.env_kind) {
+        case ORL_ENV_NONE: ORL_LAUNCH_ROLLOUT_RM(ORL_ENV_NONE); break;
+        case ORL_ENV_CARTPOLE: ORL_LAUNCH_ROLLOUT_RM(ORL_ENV_CARTPOLE); break;
+        case ORL_ENV_GRIDWORLD: ORL_LAUNCH_ROLLOUT_RM(ORL_ENV_GRIDWORLD); break;
+        default: ORL_LAUNCH_ROLLOUT_RM(ORL_ENV_MPE_SPREAD); break;
+    }
     ORL_LAUNCH_CHECK("rollout_kernel");
     if (a.rng_counter) {
         bump_counter_kernel<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a.rng_counter, (uint64_t)(a.t_end - a.t_begin));

@@ -58,7 +58,8 @@ class OnPolicyDriver:
 
     def reset_and_buffer_init(self):
         d = self.buffer.data
-        self.envs.reset_into(d.policy_obs[0].view(-1, d.obs_dim))  # rl_driver.py:118-131, no host copy
+        cri = None if d.critic_obs is d.policy_obs else d.critic_obs[0].view(-1, d.critic_obs_dim)
+        self.envs.reset_into(d.policy_obs[0].view(-1, d.obs_dim), cri)  # rl_driver.py:118-131, no host copy
         d.masks[0].fill_(1.0)
         d.active_masks[0].fill_(1.0)
 
@@ -117,11 +118,12 @@ class OnPolicyDriver:
         a = lib.OrlRolloutArgs()
         a.env_kind, a.n_envs, a.n_agents = env.kind, env.parallel_env_num, env.agent_num
         a.episode_length, a.t_begin, a.t_end = self.episode_length, t_begin, t_end
-        a.obs_dim, a.critic_obs_dim, a.n_actions = d.obs_dim, 0, d.n_actions
+        separate_critic = d.critic_obs is not d.policy_obs
+        a.obs_dim, a.critic_obs_dim, a.n_actions = d.obs_dim, (d.critic_obs_dim if separate_critic else 0), d.n_actions
         a.activation_id, a.deterministic = pol.activation_id, 0
         a.env_table_len = env.env_table_len
         a.policy_params = lib.ptr(pol.flat_params)
-        a.policy_obs, a.critic_obs = lib.ptr(d.policy_obs), None
+        a.policy_obs, a.critic_obs = lib.ptr(d.policy_obs), (lib.ptr(d.critic_obs) if separate_critic else None)
         a.actions, a.action_log_probs, a.rewards = lib.ptr(d.actions), lib.ptr(d.action_log_probs), lib.ptr(d.rewards)
         a.masks, a.active_masks = lib.ptr(d.masks), lib.ptr(d.active_masks)
         a.action_masks = None if d.action_masks_trivial else lib.ptr(d.action_masks)

@@ -14,7 +14,15 @@ def _gridworld_space():
     return spaces.Box(low=np.array([0, 0, 0, 0]), high=np.array([9, 9, 9, 9]), dtype=np.int64)
 
 
+def _mpe_space():
+    # MultiAgentEnv.observation_space (multiagent_env.py:146-151): Dict{"policy": Box(18), "critic": Box(54)}
+    return spaces.Dict({"policy": spaces.Box(-np.inf, np.inf, (18,), np.float32),
+                        "critic": spaces.Box(-np.inf, np.inf, (54,), np.float32)})
+
+
 ENV_SPECS = {
+    "simple_spread": dict(kind=lib.ENV_MPE_SPREAD, agents=3, obs_dim=18, critic_obs_dim=54, n_actions=5,
+                          f64_rows=18, observation_space=_mpe_space),
     "CartPole-v1": dict(kind=lib.ENV_CARTPOLE, agents=1, obs_dim=4, n_actions=2, observation_space=_cartpole_space),
     "GridWorldEnv": dict(kind=lib.ENV_GRIDWORLD, agents=1, obs_dim=4, n_actions=5, observation_space=_gridworld_space),
 }

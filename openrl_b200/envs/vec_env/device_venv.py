@@ -46,6 +46,7 @@ class DeviceVecEnv:
         self.parallel_env_num = int(env_num)
         self.agent_num = spec["agents"]
         self.obs_dim = spec["obs_dim"]
+        self.critic_obs_dim = spec.get("critic_obs_dim", 0)  # 0: critic observes the policy observation
         self.n_actions = spec["n_actions"]
         self.observation_space = spec["observation_space"]()
         self.action_space = spaces.Discrete(self.n_actions)
@@ -54,7 +55,7 @@ class DeviceVecEnv:
         self._lib = lib.load()
         N = self.parallel_env_num
         dev = self.device
-        self.env_f64 = torch.zeros(4, N, dtype=torch.float64, device=dev)
+        self.env_f64 = torch.zeros(spec.get("f64_rows", 4), N, dtype=torch.float64, device=dev)
         self.env_u64 = torch.zeros(4, N, dtype=torch.int64, device=dev)  # bit pattern of uint64
         self.env_i32 = torch.zeros(4, N, dtype=torch.int32, device=dev)
         self.ep_return = torch.zeros(N, dtype=torch.float32, device=dev)
@@ -68,13 +69,15 @@ class DeviceVecEnv:
             self.env_table = t.to(dev)
             self.env_table_len = int(t.shape[1])
         self._obs = torch.zeros(N * self.agent_num, self.obs_dim, dtype=torch.float32, device=dev)
+        self._critic_obs = (torch.zeros(N * self.agent_num, self.critic_obs_dim, dtype=torch.float32, device=dev)
+                            if self.critic_obs_dim else None)
         self._start_time = time.time()
         self._total_step = 0
         self._seed_streams(seed)
 
     # -- seeding / reset -------------------------------------------------------------------
     def _seed_streams(self, seed):
-        if self.kind == lib.ENV_CARTPOLE:
+        if self.kind in (lib.ENV_CARTPOLE, lib.ENV_MPE_SPREAD):
             st = _pcg64_streams(seed, self.parallel_env_num, self.env_index_offset)
             self.env_u64.copy_(torch.from_numpy(st.view(np.int64)))
         self.rng_seed = int(seed if seed is not None else np.random.SeedSequence().entropy % (1 << 63))
@@ -82,21 +85,32 @@ class DeviceVecEnv:
     def reset(self, seed=None, options=None):
         if seed is not None:
             self._seed_streams(int(seed))
-        self.reset_into(self._obs)
-        obs = self._obs.view(self.parallel_env_num, self.agent_num, self.obs_dim).cpu().numpy()
-        return obs, [{} for _ in range(self.parallel_env_num)]
+        self.reset_into(self._obs, self._critic_obs)
+        return self._host_obs(), [{} for _ in range(self.parallel_env_num)]
 
-    def reset_into(self, obs_out):
-        """Device-side reset writing the (B, d) observations into `obs_out` (no host copy)."""
+    def _host_obs(self):
+        N, A = self.parallel_env_num, self.agent_num
+        pol = self._obs.view(N, A, self.obs_dim).cpu().numpy()
+        if self._critic_obs is None:
+            return pol
+        return {"policy": pol, "critic": self._critic_obs.view(N, A, self.critic_obs_dim).cpu().numpy()}
+
+    def reset_into(self, obs_out, critic_obs_out=None):
+        """Device-side reset writing the (B, d) observations (and (B, d_c) critic observations) into
+        the given tensors (no host copy)."""
         L = self._lib
+        if self._critic_obs is not None and critic_obs_out is None:
+            critic_obs_out = self._critic_obs
         lib.check(L.orl_env_reset(self.kind, self.parallel_env_num, self.agent_num, lib.ptr(self.env_f64),
                                   lib.ptr(self.env_u64), lib.ptr(self.env_i32), lib.ptr(self.env_table),
-                                  self.env_table_len, self.rng_seed, lib.ptr(obs_out), None, lib.current_stream()),
-                  "orl_env_reset")
+                                  self.env_table_len, self.rng_seed, lib.ptr(obs_out), lib.ptr(critic_obs_out),
+                                  lib.current_stream()), "orl_env_reset")
         self.ep_return.zero_()
         self.ep_length.zero_()
         if obs_out.data_ptr() != self._obs.data_ptr():
             self._obs.copy_(obs_out.view_as(self._obs))
+        if critic_obs_out is not None and critic_obs_out.data_ptr() != self._critic_obs.data_ptr():
+            self._critic_obs.copy_(critic_obs_out.view_as(self._critic_obs))
 
     # -- plain step API (evaluation loops; the training loop uses the fused rollout) ---------
     def step(self, actions, extra_data=None):
@@ -104,23 +118,27 @@ class DeviceVecEnv:
         act = torch.as_tensor(np.asarray(actions, dtype=np.float32).reshape(N * A)).to(self.device)
         rew = torch.empty(N * A, dtype=torch.float32, device=self.device)
         done = torch.empty(N * A, dtype=torch.float32, device=self.device)
-        fin = torch.empty(N * A, self.obs_dim, dtype=torch.float32, device=self.device)
+        # last output: terminal observation (single-agent envs) or the critic observation (simple_spread)
+        fin = self._critic_obs if self._critic_obs is not None else torch.empty(N * A, self.obs_dim, dtype=torch.float32, device=self.device)
         lib.check(self._lib.orl_env_step(self.kind, N, A, lib.ptr(self.env_f64), lib.ptr(self.env_u64),
                                          lib.ptr(self.env_i32), lib.ptr(self.env_table), self.env_table_len,
                                          self.rng_seed, lib.ptr(self.ep_return), lib.ptr(self.ep_length),
                                          lib.ptr(self.episode_stats), lib.ptr(act), lib.ptr(self._obs), lib.ptr(rew),
                                          lib.ptr(done), lib.ptr(fin), lib.current_stream()), "orl_env_step")
-        obs = self._obs.view(N, A, self.obs_dim).cpu().numpy()
+        obs = self._host_obs()
         dones = done.view(N, A).cpu().numpy() != 0
         rewards = rew.view(N, A, 1).cpu().numpy().astype(np.float64)
-        fin_h = fin.view(N, A, self.obs_dim).cpu().numpy()
         infos = []
-        for i in range(N):
-            info = {}
-            if dones[i].all():
-                info["final_observation"] = fin_h[i]
-                info["final_info"] = {}
-            infos.append(info)
+        if self._critic_obs is None:
+            fin_h = fin.view(N, A, self.obs_dim).cpu().numpy()
+            for i in range(N):
+                info = {}
+                if dones[i].all():
+                    info["final_observation"] = fin_h[i]
+                    info["final_info"] = {}
+                infos.append(info)
+        else:  # MPE: a list of per-agent dicts (multiagent_env.py:184-188)
+            infos = [[{"individual_reward": float(rewards[i, a, 0]) / A} for a in range(A)] for i in range(N)]
         return obs, rewards, dones, infos
 
     def random_action(self, infos=None):

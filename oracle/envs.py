@@ -124,3 +124,116 @@ class GridWorldVec:
 
 
 ENVS = {"CartPole-v1": CartPoleVec, "GridWorldEnv": GridWorldVec}
+
+
+class SimpleSpreadVec:
+    """MPE simple_spread (3 agents, 3 landmarks, world_length 25), float64, as the reference:
+      World.step / apply_action_force / apply_environment_force / integrate_state /
+      get_entity_collision_force      openrl/envs/mpe/core.py:216-344
+      MultiAgentEnv.step/_set_action/reset/construct_obs   openrl/envs/mpe/multiagent_env.py:167-243,274-339
+      Scenario.reset_world / reward / observation           openrl/envs/mpe/scenarios/simple_spread.py:46-125
+    Vec semantics (auto-reset when all agents are done, seeds seed + i*10086): sync_venv.py:129-247.
+    Returns obs dict {"policy": (N,3,18), "critic": (N,3,54)} float64 like the reference."""
+    obs_dim = 18
+    critic_obs_dim = 54
+    n_actions = 5
+    agent_num = 3
+    DT, DAMPING, CONTACT_FORCE, CONTACT_MARGIN = 0.1, 0.25, 1e2, 1e-3
+    AGENT_SIZE, SENSITIVITY, WORLD_LENGTH = 0.15, 5.0, 25
+
+    def __init__(self, env_num):
+        self.N = env_num
+        self.rng = [pcg64_np_random(None) for _ in range(env_num)]
+        self.pos = np.zeros((env_num, 3, 2))
+        self.vel = np.zeros((env_num, 3, 2))
+        self.lm = np.zeros((env_num, 3, 2))
+        self.step_count = np.zeros(env_num, np.int64)
+
+    def _reset_one(self, i):
+        for a in range(3):
+            self.pos[i, a] = self.rng[i].uniform(-1, +1, 2)
+            self.vel[i, a] = 0.0
+        for l in range(3):
+            self.lm[i, l] = 0.8 * self.rng[i].uniform(-1, +1, 2)
+        self.step_count[i] = 0
+
+    def _obs_one(self, i):
+        obs = []
+        for a in range(3):
+            parts = [self.vel[i, a], self.pos[i, a]]
+            parts += [self.lm[i, l] - self.pos[i, a] for l in range(3)]
+            parts += [self.pos[i, o] - self.pos[i, a] for o in range(3) if o != a]
+            parts += [np.zeros(2), np.zeros(2)]
+            obs.append(np.concatenate(parts))
+        return obs
+
+    def _obs(self):
+        pol = np.zeros((self.N, 3, 18))
+        cri = np.zeros((self.N, 3, 54))
+        for i in range(self.N):
+            o = self._obs_one(i)
+            pol[i] = np.stack(o)
+            cri[i] = np.concatenate(o)[None].repeat(3, axis=0)
+        return {"policy": pol, "critic": cri}
+
+    def reset(self, seed=None):
+        for i in range(self.N):
+            if seed is not None:
+                self.rng[i] = pcg64_np_random(seed + i * 10086)
+            self._reset_one(i)
+        return self._obs()
+
+    def _world_step(self, i, actions):
+        p_force = [None, None, None]
+        for a in range(3):
+            onehot = np.zeros(5)
+            onehot[int(actions[a])] = 1
+            u = np.zeros(2)
+            u[0] += onehot[1] - onehot[2]
+            u[1] += onehot[3] - onehot[4]
+            u *= self.SENSITIVITY
+            p_force[a] = 1.0 * u + 0.0
+        for a in range(3):
+            for b in range(a + 1, 3):
+                delta = self.pos[i, a] - self.pos[i, b]
+                dist = np.sqrt(np.sum(np.square(delta)))
+                dist_min = self.AGENT_SIZE + self.AGENT_SIZE
+                k = self.CONTACT_MARGIN
+                penetration = np.logaddexp(0, -(dist - dist_min) / k) * k
+                force = self.CONTACT_FORCE * delta / dist * penetration
+                force_ratio = 1.0 / 1.0
+                p_force[a] = force_ratio * force + p_force[a]
+                p_force[b] = -(1 / force_ratio) * force + p_force[b]
+        for a in range(3):
+            self.vel[i, a] = self.vel[i, a] * (1 - self.DAMPING)
+            self.vel[i, a] += (p_force[a] / 1.0) * self.DT
+            self.pos[i, a] += self.vel[i, a] * self.DT
+
+    def _reward(self, i, agent):
+        rew = 0
+        for l in range(3):
+            dists = [np.sqrt(np.sum(np.square(self.pos[i, a] - self.lm[i, l]))) for a in range(3)]
+            rew -= min(dists)
+        for a in range(3):
+            d = np.sqrt(np.sum(np.square(self.pos[i, a] - self.pos[i, agent])))
+            if d < 2 * self.AGENT_SIZE:
+                rew -= 1
+        return rew
+
+    def step(self, actions):
+        """actions (N,3,1) -> obs dict, rewards (N,3,1) f64, dones (N,3) bool."""
+        rewards = np.zeros((self.N, 3, 1))
+        dones = np.zeros((self.N, 3), bool)
+        for i in range(self.N):
+            self.step_count[i] += 1
+            self._world_step(i, actions[i, :, 0])
+            r = np.sum([[self._reward(i, a)] for a in range(3)])
+            rewards[i, :, 0] = r
+            done = self.step_count[i] >= self.WORLD_LENGTH
+            dones[i] = done
+            if done:
+                self._reset_one(i)
+        return self._obs(), rewards, dones, None
+
+
+ENVS["simple_spread"] = SimpleSpreadVec

@@ -228,6 +228,11 @@ def main():
                    "--use_recurrent_policy", "true", "--use_valuenorm", "true", "--use_adv_normalize", "true",
                    "--log_interval", "1000"],
                   2, "mpe_gru")
+    if a.only in ("", "mpe_mlp"):
+        gen_trace("simple_spread", 4,
+                  ["--seed", "0", "--episode_length", "25", "--ppo_epoch", "2", "--lr", "7e-4", "--critic_lr", "7e-4",
+                   "--use_valuenorm", "true", "--use_adv_normalize", "true", "--log_interval", "1000"],
+                  2, "mpe_mlp")
 
 
 if __name__ == "__main__":
