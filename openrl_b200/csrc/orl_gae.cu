@@ -183,6 +183,147 @@ __global__ void __launch_bounds__(128) gae_scan_kernel(const GaeParams p) {
     }
 }
 
+
+// ---- small-B variant (default GAE branch: use_gae, no proper-time-limits) -----------------------
+// With few columns the streaming kernel above is latency-bound: T dependent steps, each waiting on
+// DRAM.  Here a CTA owns 32 columns and splits the work into (A) a fully parallel pass over all
+// (t, column) elements that loads the inputs with every thread and computes the step-local terms
+// delta_t and k_t = gamma*lambda*m_{t+1} into shared memory, (B) the serial recurrence
+// g_t = delta_t + k_t*g_{t+1} from shared memory (2 dependent float ops per step, one thread per
+// column), (C) a parallel epilogue (returns, advantages, moments, coalesced stores).  Same float32
+// operation order per element as the streaming kernel, hence still bit-exact.
+constexpr int TILE_COLS = 32, TILE_THREADS = 1024, TILE_WARPS = TILE_THREADS / 32, TILE_BATCH = 4;
+
+template <bool DENORM, bool ADV, bool STATS>
+__global__ void __launch_bounds__(TILE_THREADS) gae_tile_kernel(const GaeParams p) {
+    extern __shared__ float tsm[];
+    const int T = p.T, B = p.B;
+    float* sdelta = tsm;                 // [T][32], overwritten by g in phase B
+    float* sk = tsm + (size_t)T * TILE_COLS;
+    const int col0 = blockIdx.x * TILE_COLS;
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    const int col = col0 + lane;
+    const bool valid = col < B;
+    float vn_mean = 0.f, vn_std = 1.f;
+    if (DENORM) { const orl::VnScalars s = orl::vn_mean_std(p.vn_state); vn_mean = s.mean; vn_std = s.std; }
+    auto denorm = [&](float v) -> float { return DENORM ? __fadd_rn(__fmul_rn(v, vn_std), vn_mean) : v; };
+
+    // bootstrap row (USE_GAE: value_preds[T] <- next_value); read next_value BEFORE it may be overwritten
+    float nv = 0.f;
+    if (valid && wrp == 0) nv = __ldg(p.next_value + col);
+    // phase A: every warp takes rows t = wrp, wrp + 32, ...; the loads of TILE_BATCH rows are issued
+    // together so their DRAM latencies overlap
+    for (int t0 = wrp; t0 < T; t0 += TILE_WARPS * TILE_BATCH) {
+        float r[TILE_BATCH], v0[TILE_BATCH], v1[TILE_BATCH], m1[TILE_BATCH];
+#pragma unroll
+        for (int u = 0; u < TILE_BATCH; ++u) {
+            const int t = t0 + u * TILE_WARPS;
+            if (valid && t < T) {
+                const size_t o = (size_t)t * B + col;
+                r[u] = __ldg(p.rewards + o); v0[u] = p.value_preds[o]; m1[u] = __ldg(p.masks + o + B);
+                v1[u] = (t == T - 1) ? __ldg(p.next_value + col) : p.value_preds[o + B];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < TILE_BATCH; ++u) {
+            const int t = t0 + u * TILE_WARPS;
+            if (valid && t < T) {
+                const float v0d = denorm(v0[u]), v1d = denorm(v1[u]);
+                sdelta[t * TILE_COLS + lane] = __fsub_rn(__fadd_rn(r[u], __fmul_rn(__fmul_rn(p.gamma, v1d), m1[u])), v0d);
+                sk[t * TILE_COLS + lane] = __fmul_rn(p.gamma_lambda, m1[u]);
+            }
+        }
+    }
+    __syncthreads();
+    if (wrp == 0 && valid) {
+        p.value_preds[(size_t)T * B + col] = nv;
+        float g = 0.f;
+#pragma unroll 8
+        for (int t = T - 1; t >= 0; --t) {
+            g = __fadd_rn(sdelta[t * TILE_COLS + lane], __fmul_rn(sk[t * TILE_COLS + lane], g));
+            sdelta[t * TILE_COLS + lane] = g;
+        }
+    }
+    __syncthreads();
+    // phase C
+    double s_adv = 0, s_adv2 = 0, s_act_adv = 0, s_act_adv2 = 0, s_act_n = 0, s_ret = 0, s_ret2 = 0;
+    for (int t0 = wrp; t0 < T; t0 += TILE_WARPS * TILE_BATCH) {
+        float v0[TILE_BATCH], am[TILE_BATCH];
+#pragma unroll
+        for (int u = 0; u < TILE_BATCH; ++u) {
+            const int t = t0 + u * TILE_WARPS;
+            if (valid && t < T) {
+                const size_t o = (size_t)t * B + col;
+                v0[u] = p.value_preds[o];
+                am[u] = (STATS && p.active_masks) ? __ldg(p.active_masks + o) : 1.0f;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < TILE_BATCH; ++u) {
+            const int t = t0 + u * TILE_WARPS;
+            if (valid && t < T) {
+                const size_t o = (size_t)t * B + col;
+                const float v0d = denorm(v0[u]);
+                const float g = sdelta[t * TILE_COLS + lane];
+                const float ret = __fadd_rn(g, v0d);
+                p.returns[o] = ret;
+                if (ADV || STATS) {
+                    const float a = __fsub_rn(ret, v0d);
+                    if (ADV) p.advantages[o] = a;
+                    if (STATS) {
+                        const double ad = (double)a, rd = (double)ret;
+                        s_adv += ad; s_adv2 += ad * ad; s_ret += rd; s_ret2 += rd * rd;
+                        if (am[u] != 0.0f) { s_act_adv += ad; s_act_adv2 += ad * ad; s_act_n += 1.0; }
+                    }
+                }
+            }
+        }
+    }
+    if (STATS) {
+        __shared__ double red[7][TILE_THREADS / 32];
+        double vals[7] = {s_adv, s_adv2, s_act_adv, s_act_adv2, s_act_n, s_ret, s_ret2};
+#pragma unroll
+        for (int k = 0; k < 7; ++k) { const double w = orl::warp_sum(vals[k]); if (lane == 0) red[k][wrp] = w; }
+        __syncthreads();
+        if (threadIdx.x < 7) {
+            const int k = threadIdx.x;
+            double tot = 0;
+            for (int w = 0; w < TILE_THREADS / 32; ++w) tot += red[k][w];
+            const int idx = (k == 0) ? ORL_GS_ADV_SUM : (k == 1) ? ORL_GS_ADV_SQSUM : (k == 2) ? ORL_GS_ADV_ACT_SUM
+                          : (k == 3) ? ORL_GS_ADV_ACT_SQSUM : (k == 4) ? ORL_GS_ACT_COUNT : (k == 5) ? ORL_GS_RET_SUM : ORL_GS_RET_SQSUM;
+            if (tot != 0.0) atomicAdd(p.stats + idx, tot);
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) p.stats[ORL_GS_COUNT] = (double)T * (double)B;
+    }
+}
+
+template <bool DENORM>
+int launch_gae_tile(const GaeParams& p, cudaStream_t st) {
+    const int grid = (p.B + TILE_COLS - 1) / TILE_COLS;
+    const size_t smem = (size_t)p.T * TILE_COLS * 2 * sizeof(float);
+    const bool adv = p.advantages != nullptr, stats = p.stats != nullptr;
+    if (stats) {
+        int e = orl::check_cuda(cudaMemsetAsync(p.stats, 0, sizeof(double) * ORL_GAE_NSTATS, st), "memset stats");
+        if (e) return e;
+    }
+#define ORL_GAE_TILE(A_, S_)                                                                                          \
+    do {                                                                                                              \
+        static bool attr_done = false;                                                                                \
+        if (!attr_done) {                                                                                             \
+            int e_ = orl::check_cuda(cudaFuncSetAttribute(gae_tile_kernel<DENORM, A_, S_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), "attr"); \
+            if (e_) return e_;                                                                                        \
+            attr_done = true;                                                                                         \
+        }                                                                                                             \
+        gae_tile_kernel<DENORM, A_, S_><<<grid, TILE_THREADS, smem, st>>>(p);                                         \
+    } while (0)
+    if (adv && stats) ORL_GAE_TILE(true, true);
+    else if (adv) ORL_GAE_TILE(true, false);
+    else if (stats) ORL_GAE_TILE(false, true);
+    else ORL_GAE_TILE(false, false);
+    ORL_LAUNCH_CHECK("gae_tile_kernel");
+    return 0;
+}
+
 template <int VEC, int U, bool USE_GAE, bool PTL, bool DENORM>
 int launch_gae2(const GaeParams& p, cudaStream_t st) {
     const int threads = 128;
@@ -239,5 +380,9 @@ extern "C" int orl_gae(const float* rewards, float* value_preds, const float* ma
     // 128-thread CTAs on every SM); otherwise scalar columns keep more threads in flight.
     const long long min_cols_for_vec = 2LL * orl::sm_count() * 16 * 128;
     if (vec_ok && (long long)(B / 4) >= min_cols_for_vec) return launch_gae<4, 4>(p, flags, st);
+    // few columns: tile kernel (parallel load + short serial chain from shared memory) for the default branch
+    const bool tile_branch = (flags & ORL_GAE_USE_GAE) && !(flags & ORL_GAE_PROPER_TIME_LIMITS);
+    if (tile_branch && (long long)B < 16LL * orl::sm_count() * 128 && (size_t)T * TILE_COLS * 8 <= 160 * 1024)
+        return (flags & ORL_GAE_DENORM) ? launch_gae_tile<true>(p, st) : launch_gae_tile<false>(p, st);
     return launch_gae<1, 8>(p, flags, st);
 }
