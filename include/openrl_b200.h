@@ -96,6 +96,8 @@ int orl_gae(const float* rewards, float* value_preds, const float* masks,
  *              [N][env_table_len][2] start cells for parity runs; else Philox(rng_seed).
  *   NONE     : no device env (host env.step, e.g. MuJoCo): orl_rollout only acts.
  */
+#define ORL_HEAD_CATEGORICAL 0
+#define ORL_HEAD_GAUSSIAN 1
 #define ORL_ENV_NONE 0
 #define ORL_ENV_CARTPOLE 1
 #define ORL_ENV_GRIDWORLD 2
@@ -164,6 +166,12 @@ typedef struct OrlRolloutArgs {
     float* ep_return;           /* (N) running episode return  (VecMonitor-style statistics) */
     int32_t* ep_length;         /* (N) running episode length */
     double* episode_stats;      /* (4) += {sum return, sum length, #episodes, 0} of finished episodes */
+    int32_t head_kind;          /* ORL_HEAD_CATEGORICAL (Discrete(n)) or ORL_HEAD_GAUSSIAN (Box(n), DiagGaussian,
+                                   distributions.py:75-98): then n_actions = action width, actions and
+                                   action_log_probs are (T, B, n) (per-dimension log-probs), exp_noise holds
+                                   N(0,1) draws (torch.normal == noise*std + mean) and the parameter vector ends
+                                   with logstd[n].  Gaussian heads act on host-stepped envs (ORL_ENV_NONE). */
+    int32_t reserved1;
 } OrlRolloutArgs;
 int orl_rollout(const OrlRolloutArgs* args, void* stream);
 
@@ -242,9 +250,11 @@ typedef struct OrlPpoArgs {
     float* grads;                /* (2, orl_ppo_grads_stride): true gradients, parameter layout (written by apply) */
     float* train_info;           /* (6) += {value_loss, critic_grad_norm, policy_loss, dist_entropy,
                                              actor_grad_norm, ratio}  (ppo.py:430-451) */
+    int32_t head_kind;           /* ORL_HEAD_*: with GAUSSIAN actions / old_log_probs are (T*B, n) */
+    int32_t reserved1;
 } OrlPpoArgs;
 /* floats per partial row for given shapes (>= folded gradient size + 8 loss slots, multiple of 4) */
-int orl_ppo_stride(int obs_dim, int critic_obs_dim, int n_actions);
+int orl_ppo_stride(int obs_dim, int critic_obs_dim, int n_actions);   /* valid for both head kinds */
 /* floats per net row of `grads` (>= parameter count of the larger net, multiple of 4) */
 int orl_ppo_grads_stride(int obs_dim, int critic_obs_dim, int n_actions);
 /* number of parameters of one MLP net with head width n (layout in DESIGN.md) */

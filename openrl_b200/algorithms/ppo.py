@@ -44,7 +44,9 @@ class PPOAlgorithm:
                       | (lib.PPO_VALUENORM if (cfg.use_valuenorm and cri.value_normalizer is not None) else 0)
                       | (lib.PPO_ADV_NORMALIZE if cfg.use_adv_normalize else 0)
                       | (lib.PPO_MAX_GRAD_NORM if cfg.use_max_grad_norm else 0))
-        self.use_tf32 = bool(getattr(cfg, "use_tf32", True)) and not cfg.parity_mode and max(self.d, self.dc) <= 8
+        self.head_kind = pol.head_kind
+        self.use_tf32 = (bool(getattr(cfg, "use_tf32", True)) and not cfg.parity_mode and max(self.d, self.dc) <= 8
+                         and self.head_kind == lib.HEAD_CATEGORICAL)
         if self.use_tf32:
             self.flags |= lib.PPO_TF32
         for name in ("use_joint_action_loss", "dual_clip_ppo", "use_policy_vhead", "use_share_model", "use_popart",
@@ -70,6 +72,7 @@ class PPOAlgorithm:
         a = lib.OrlPpoArgs()
         a.obs_dim, a.critic_obs_dim, a.n_actions, a.activation_id = self.d, self.dc, self.n, pol.activation_id
         a.flags, a.grid_per_net = self.flags, self.grid_per_net
+        a.head_kind = self.head_kind
         total = buf.episode_length * buf.n_rollout_threads * buf.num_agents
         a.batch_rows, a.row_begin, a.total_rows = int(batch_rows), int(row_begin), int(total)
         a.indices = lib.ptr(indices)
@@ -77,7 +80,7 @@ class PPOAlgorithm:
         a.actions, a.old_log_probs = lib.ptr(buf.actions), lib.ptr(buf.action_log_probs)
         a.advantages, a.value_preds, a.returns = lib.ptr(buf.advantages), lib.ptr(buf.value_preds), lib.ptr(buf.returns)
         a.active_masks = lib.ptr(buf.active_masks)
-        a.action_masks = None if buf.action_masks_trivial else lib.ptr(buf.action_masks)
+        a.action_masks = None if (buf.action_masks_trivial or buf.continuous) else lib.ptr(buf.action_masks)
         a.gae_stats = lib.ptr(buf.gae_stats)
         vn = cri.value_normalizer
         a.vn_state = None if vn is None else lib.ptr(vn.state)

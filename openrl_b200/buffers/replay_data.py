@@ -31,8 +31,10 @@ class ReplayData:
         else:
             d_p = d_c = obs_space.shape[0]
         self.obs_dim, self.critic_obs_dim = d_p, d_c
-        n = act_space.n
+        self.continuous = act_space.__class__.__name__ == "Box"
+        n = act_space.shape[0] if self.continuous else act_space.n
         self.n_actions = n
+        act_w = n if self.continuous else 1   # per-dimension actions / log-probs for Box (distributions.py:35-37)
         f = lambda *s: torch.zeros(*s, dtype=torch.float32, device=self.device)  # noqa: E731
         self.policy_obs = f(T + 1, N, A, d_p)
         # single-observation envs share one tensor (the reference stores two equal copies)
@@ -44,8 +46,8 @@ class ReplayData:
         self.active_masks = torch.ones_like(self.masks)
         self.action_masks = torch.ones(T + 1, N, A, n, dtype=torch.float32, device=self.device)
         self.action_masks_trivial = True  # all ones: kernels are given NULL
-        self.actions = f(T, N, A, 1)
-        self.action_log_probs = f(T, N, A, 1)
+        self.actions = f(T, N, A, act_w)
+        self.action_log_probs = f(T, N, A, act_w)
         self.rewards = f(T, N, A, 1)
         self.advantages = f(T, N, A, 1)  # raw returns - V, written by the GAE kernel (ppo.py:384-399)
         self.gae_stats = torch.zeros(8, dtype=torch.float64, device=self.device)

@@ -31,23 +31,24 @@ constexpr float LN_EPS = 1e-5f;
 
 struct NetOffsets {
     int d, n;
-    int w1, b1, g1, be1, w3, b3, g3, be3, wh, bh, total;
+    int w1, b1, g1, be1, w3, b3, g3, be3, wh, bh, ls, total;   // ls: logstd[n] (Gaussian head only)
 };
-__host__ __device__ inline NetOffsets net_offsets(int d, int n) {
+__host__ __device__ inline NetOffsets net_offsets(int d, int n, int gaussian = 0) {
     NetOffsets o; o.d = d; o.n = n;
     int p = 0;
     o.w1 = p; p += H * d;  o.b1 = p; p += H;  o.g1 = p; p += H;  o.be1 = p; p += H;
     o.w3 = p; p += H * H;  o.b3 = p; p += H;  o.g3 = p; p += H;  o.be3 = p; p += H;
     o.wh = p; p += n * H;  o.bh = p; p += n;
+    o.ls = p; if (gaussian) p += n;
     o.total = p;
     return o;
 }
 // folded-gradient vector layout of one net: G1[64][d] db1[64] G3[64][64] db3[64] GH[n][64] dbh[n]
-struct FoldOffsets { int g1, db1, g3, db3, gh, dbh, total; };
+struct FoldOffsets { int g1, db1, g3, db3, gh, dbh, dls, total; };   // dls: dL/dlogstd[n], always reserved
 __host__ __device__ inline FoldOffsets fold_offsets(int d, int n) {
     FoldOffsets o; int p = 0;
     o.g1 = p; p += H * d;  o.db1 = p; p += H;  o.g3 = p; p += H * H;  o.db3 = p; p += H;
-    o.gh = p; p += n * H;  o.dbh = p; p += n;  o.total = p;
+    o.gh = p; p += n * H;  o.dbh = p; p += n;  o.dls = p; p += n;  o.total = p;
     return o;
 }
 

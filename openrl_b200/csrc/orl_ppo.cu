@@ -30,7 +30,7 @@ __host__ __device__ inline int ppo_stride(int obs_dim, int critic_obs_dim, int n
 }
 
 __host__ __device__ inline int ppo_grads_stride(int obs_dim, int critic_obs_dim, int n_actions) {
-    const int a = orl::net_offsets(obs_dim, n_actions).total, b = orl::net_offsets(critic_obs_dim, 1).total;
+    const int a = orl::net_offsets(obs_dim, n_actions, 1).total, b = orl::net_offsets(critic_obs_dim, 1).total;
     return ((a > b ? a : b) + 3) & ~3;
 }
 
@@ -186,6 +186,8 @@ __device__ __forceinline__ void ppo_net_pass(const OrlPpoArgs& a, float* smem, i
     const int JBH = n > 4 ? 2 : 1;
     const WgMap maph = wg_map(JBH, 16);
     float g3[4][4] = {}, g1[4][4] = {}, gh[4][4] = {}, db3[4] = {}, db1[4] = {}, dbh[4] = {};
+    const bool gaussian = POLICY && a.head_kind == ORL_HEAD_GAUSSIAN;
+    float dls_acc[MAX_OUT] = {};   // dL/dlogstd partial sums of this thread's rows (Gaussian head)
     float loss0 = 0.f, loss1 = 0.f, loss2 = 0.f;  // policy: policy_loss, entropy, ratio | critic: value_loss
 
     const long long n_tiles = (a.batch_rows + P_M - 1) / P_M;
@@ -227,7 +229,34 @@ __device__ __forceinline__ void ppo_net_pass(const OrlPpoArgs& a, float* smem, i
                 for (int j = 0; j < DLW; ++j) dl[j] = 0.f;
                 if (row < rows_here) {
                     const float active = row_act[row];
-                    if (POLICY) {
+                    if (POLICY && gaussian) {
+                        // DiagGaussian head (act.py:150-158, distributions.py:34-47): per-dimension ratios,
+                        // surrogate summed over the action dimension (ppo.py:307-319)
+                        const long long gi = row_idx[row];
+                        const float* logstd = params + net_offsets(d, n, 1).ls;
+                        const float adv = apply_adv_norm(advn, row_c[row]);
+                        const float lo = 1.0f - a.clip_param, hi = 1.0f + a.clip_param;
+                        const float wrow = pol_masks ? active * inv_act : inv_rows;
+                        const float went_row = pol_masks ? active * inv_act : inv_rows / (float)n;
+#pragma unroll
+                        for (int j = 0; j < MAX_OUT; ++j) {
+                            if (j < n) {
+                                const float mean = out[j], ls = logstd[j], std = expf(ls), var = std * std;
+                                const float act = a.actions[gi * n + j], diff = act - mean;
+                                const float lp = -(diff * diff) / (2.0f * var) - ls - 0.9189385332046727f;
+                                const float ratio = expf(lp - a.old_log_probs[gi * n + j]);
+                                const float surr1 = ratio * adv, surr2 = fminf(fmaxf(ratio, lo), hi) * adv;
+                                const bool inside = ratio >= lo && ratio <= hi;
+                                const float sel = surr1 < surr2 ? 1.f : (surr1 > surr2 ? 0.f : (inside ? 1.f : 0.5f));
+                                loss0 += -fminf(surr1, surr2) * wrow;
+                                loss1 += (1.4189385332046727f + ls) * went_row;   // 0.5 + 0.5 log(2 pi) + log(std)
+                                loss2 += ratio / (float)n;
+                                const float dlp = -sel * adv * ratio * wrow;
+                                dl[j] = dlp * diff / var;                                               // dL/dmean
+                                dls_acc[j] += dlp * (diff * diff / var - 1.0f) - a.entropy_coef * went_row;   // dL/dlogstd
+                            }
+                        }
+                    } else if (POLICY) {
                         const long long gi = row_idx[row];
                         unsigned masked = 0;
                         if (a.action_masks) {
@@ -351,6 +380,23 @@ __device__ __forceinline__ void ppo_net_pass(const OrlPpoArgs& a, float* smem, i
     wgrad_flush(scratch, map3, 16, 16, g3, db3, H, H, part + fo.g3, part + fo.db3);
     wgrad_flush(scratch, maph, JBH, 16, gh, dbh, n, H, part + fo.gh, part + fo.dbh);
     __syncthreads();
+    if (POLICY) {   // dL/dlogstd: block reduction of the per-thread partial sums (zero for categorical heads)
+        const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+        for (int j = 0; j < MAX_OUT; ++j) {
+            const float sv = warp_sum(dls_acc[j]);
+            if (lane == 0) scratch[j * 8 + warp] = sv;
+        }
+        __syncthreads();
+        if (tid < n) {
+            float sv = 0.f;
+            for (int wv = 0; wv < P_NT / 32; ++wv) sv += scratch[tid * 8 + wv];
+            part[fo.dls + tid] = sv;
+        }
+        __syncthreads();
+    } else if (tid < n) {
+        part[fo.dls + tid] = 0.f;
+    }
     {
         float v[3] = {loss0, loss1, loss2};
         const int lane = tid & 31, warp = tid >> 5;
@@ -392,7 +438,7 @@ __global__ void __launch_bounds__(1024) ppo_apply_kernel(const OrlPpoArgs a) {
     const int d = net == 0 ? a.obs_dim : a.critic_obs_dim;
     const int n = net == 0 ? a.n_actions : 1;
     const int stride = ppo_stride(a.obs_dim, a.critic_obs_dim, a.n_actions);
-    const NetOffsets po = net_offsets(d, n);
+    const NetOffsets po = net_offsets(d, n, net == 0 && a.head_kind == ORL_HEAD_GAUSSIAN);
     const FoldOffsets fo = fold_offsets(d, n);
     float* params = net == 0 ? a.policy_params : a.critic_params;
     float* am = net == 0 ? a.policy_adam_m : a.critic_adam_m;
@@ -431,7 +477,8 @@ __global__ void __launch_bounds__(1024) ppo_apply_kernel(const OrlPpoArgs a) {
         } else if (i < po.bh) {
             const int j = (i - po.wh) / H, k = (i - po.wh) % H;
             g = fmaf(f[fo.gh + j * H + k], params[po.g3 + k], f[fo.dbh + j] * params[po.be3 + k]);
-        } else g = f[fo.dbh + (i - po.bh)];
+        } else if (i < po.ls) g = f[fo.dbh + (i - po.bh)];
+        else g = f[fo.dls + (i - po.ls)];
         grads[i] = g;
         sq = fmaf(g, g, sq);
     }
@@ -550,7 +597,14 @@ extern "C" int orl_ppo_fwdbwd(const OrlPpoArgs* args, void* stream) {
                       a.returns && a.active_masks && a.gae_stats && a.mb_stats, "null rollout buffer");
     ORL_CHECK_ARG(!(a.flags & ORL_PPO_VALUENORM) || a.vn_state, "vn_state required with VALUENORM");
     ORL_CHECK_ARG(a.indices || (a.row_begin >= 0 && a.row_begin + a.batch_rows <= a.total_rows), "row range");
-    if (a.flags & ORL_PPO_TF32) return orl::launch_ppo_fwdbwd_tc(a, reinterpret_cast<cudaStream_t>(stream));
+    ORL_CHECK_ARG(a.head_kind == ORL_HEAD_CATEGORICAL || a.head_kind == ORL_HEAD_GAUSSIAN, "head_kind");
+    if (a.flags & ORL_PPO_TF32) {
+        if (a.head_kind != ORL_HEAD_CATEGORICAL) {
+            orl::set_last_error("orl_ppo_fwdbwd: ORL_PPO_TF32 supports categorical heads only");
+            return ORL_ERR_UNSUPPORTED;
+        }
+        return orl::launch_ppo_fwdbwd_tc(a, reinterpret_cast<cudaStream_t>(stream));
+    }
     const size_t smem = fwdbwd_smem_bytes(a.obs_dim, a.critic_obs_dim);
     static bool attr_set = false;
     if (!attr_set) {

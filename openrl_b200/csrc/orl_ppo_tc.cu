@@ -469,7 +469,7 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, uint8_t* smem, 
     }
 #pragma unroll
     for (int q = 0; q < 2; ++q) { const int o = tid + T_NT * q; if (o < n * H) part[fo.gh + o] = gh_acc[q]; }
-    if (tid < n) part[fo.dbh + tid] = dbh_acc;
+    if (tid < n) { part[fo.dbh + tid] = dbh_acc; part[fo.dls + tid] = 0.f; }
     {
         float v[3] = {loss0, loss1, loss2};
         const int lane = tid & 31;

@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(R_NT) rollout_kernel(const OrlRolloutArgs a) {
     const int rows_here = n_env_here * A;
     const int tid = threadIdx.x;
 
-    load_weights_folded<R_NT>(w, a.policy_params, d, n, false);
+    load_weights_folded<R_NT>(w, a.policy_params, d, n, false);   // (the logstd tail, if any, is read directly)
 
     // stage obs of slot t_begin (zero padding for the k tail and for idle rows)
     for (int i = tid; i < R_M * ldx; i += R_NT) {
@@ -192,7 +192,45 @@ __global__ void __launch_bounds__(R_NT) rollout_kernel(const OrlRolloutArgs a) {
         __syncthreads();
         float logit[MAX_OUT];
         head_dots<R_M, R_NT>(w, N3s, n, logit);
-        if (hpart == 0 && hrow < rows_here) {
+        if (hpart == 0 && hrow < rows_here && a.head_kind == ORL_HEAD_GAUSSIAN) {
+            // DiagGaussian (distributions.py:75-98): action = noise*std + mean, per-dimension log-probs
+            const size_t grow = (size_t)t * B + row0 + hrow;
+            const float* logstd = a.policy_params + net_offsets(d, n, 1).ls;
+            uint32_t rr[8];
+            if (!a.exp_noise && !a.deterministic) {
+                const uint64_t step = rng_base + (uint64_t)t;
+                const uint2 key = make_uint2((uint32_t)a.rng_seed, (uint32_t)(a.rng_seed >> 32));
+                const uint4 r0 = philox4x32_10(make_uint4((uint32_t)step, (uint32_t)(step >> 32), (uint32_t)(row0 + hrow), 2u), key);
+                const uint4 r1 = philox4x32_10(make_uint4((uint32_t)step, (uint32_t)(step >> 32), (uint32_t)(row0 + hrow), 3u), key);
+                const uint4 r2 = philox4x32_10(make_uint4((uint32_t)step, (uint32_t)(step >> 32), (uint32_t)(row0 + hrow), 4u), key);
+                const uint4 r3 = philox4x32_10(make_uint4((uint32_t)step, (uint32_t)(step >> 32), (uint32_t)(row0 + hrow), 5u), key);
+                // Box-Muller: 8 normals from 16 uniforms (pairs (r0,r1) and (r2,r3))
+                const uint32_t u1[8] = {r0.x, r0.y, r0.z, r0.w, r2.x, r2.y, r2.z, r2.w};
+                const uint32_t u2[8] = {r1.x, r1.y, r1.z, r1.w, r3.x, r3.y, r3.z, r3.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float rad = sqrtf(-2.0f * logf(u32_to_unit_open(u1[j])));
+                    rr[j] = __float_as_uint(rad * cospif(2.0f * u32_to_unit_open(u2[j])));
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < MAX_OUT; ++j) {
+                if (j < n) {
+                    const float mean = logit[j], ls = logstd[j], std = expf(ls);
+                    float act = mean;
+                    if (!a.deterministic) {
+                        const float eps = a.exp_noise ? a.exp_noise[grow * n + j] : __uint_as_float(rr[j]);
+                        act = __fadd_rn(__fmul_rn(eps, std), mean);
+                    }
+                    const float diff = act - mean;
+                    // Normal.log_prob: -((x-mu)^2)/(2 var) - log(std) - log(sqrt(2 pi))
+                    const float lp = -(diff * diff) / (2.0f * (std * std)) - ls - 0.9189385332046727f;
+                    a.actions[grow * n + j] = act;
+                    a.action_log_probs[grow * n + j] = lp;
+                }
+            }
+        }
+        if (hpart == 0 && hrow < rows_here && a.head_kind != ORL_HEAD_GAUSSIAN) {
             const size_t grow = (size_t)t * B + row0 + hrow;
             if (a.action_masks) {
 #pragma unroll
@@ -405,6 +443,8 @@ extern "C" int orl_rollout(const OrlRolloutArgs* args, void* stream) {
     ORL_CHECK_ARG(a.t_begin >= 0 && a.t_begin < a.t_end && a.t_end <= a.episode_length, "step range");
     ORL_CHECK_ARG(a.activation_id >= 0 && a.activation_id <= 3, "activation_id");
     ORL_CHECK_ARG(a.policy_params && a.policy_obs && a.actions && a.action_log_probs, "null buffer");
+    ORL_CHECK_ARG(a.head_kind == ORL_HEAD_CATEGORICAL || (a.head_kind == ORL_HEAD_GAUSSIAN && a.env_kind == ORL_ENV_NONE),
+                  "Gaussian heads act on host-stepped envs (ORL_ENV_NONE)");
     if (a.env_kind == ORL_ENV_NONE) {
         ORL_CHECK_ARG(a.t_end == a.t_begin + 1, "ORL_ENV_NONE acts for one step per call");
     } else if (a.env_kind == ORL_ENV_CARTPOLE) {

@@ -121,6 +121,7 @@ class OnPolicyDriver:
         separate_critic = d.critic_obs is not d.policy_obs
         a.obs_dim, a.critic_obs_dim, a.n_actions = d.obs_dim, (d.critic_obs_dim if separate_critic else 0), d.n_actions
         a.activation_id, a.deterministic = pol.activation_id, 0
+        a.head_kind = pol.head_kind
         a.env_table_len = env.env_table_len
         a.policy_params = lib.ptr(pol.flat_params)
         a.policy_obs, a.critic_obs = lib.ptr(d.policy_obs), (lib.ptr(d.critic_obs) if separate_critic else None)
@@ -140,8 +141,12 @@ class OnPolicyDriver:
         d = self.buffer.data
         B, n = d.n_rollout_threads * d.num_agents, d.n_actions
         host = torch.empty(self.episode_length, B, n, dtype=torch.float32, pin_memory=True)
+        gaussian = self.trainer.algo_module.models["policy"].head_kind == lib.HEAD_GAUSSIAN
         for t in range(self.episode_length):
-            host[t].exponential_(1)
+            if gaussian:
+                host[t].normal_()       # Normal.sample() == torch.normal(mean, std) == N(0,1)*std + mean
+            else:
+                host[t].exponential_(1)
         self.h2d_bytes += host.numel() * 4
         return host.to(self.device, non_blocking=True)
 
@@ -161,7 +166,10 @@ class OnPolicyDriver:
         T, N = self.episode_length, self.envs.parallel_env_num
         per_step = cb is not None and getattr(cb, "needs_per_step", True)
         s = lib.current_stream()
-        if not per_step:
+        if self.envs.kind == lib.ENV_NONE:
+            if not self._host_rollout(cb):
+                return {}, False
+        elif not per_step:
             self._rollout_launch()
         else:
             noise = self._draw_noise() if self.cfg.parity_mode else None
@@ -188,6 +196,50 @@ class OnPolicyDriver:
             info.update(batch_rew_infos)
             return info, True
         return batch_rew_infos, True
+
+    def _host_rollout(self, cb):
+        """Per-step loop for host-stepped envs (onpolicy_driver.py:154-203): device act -> D2H actions
+        -> host env.step -> one pinned H2D copy -> in-place insert with the reference's mask rules
+        (add2buffer, onpolicy_driver.py:80-152)."""
+        d, env = self.buffer.data, self.envs
+        T, N, A = self.episode_length, env.parallel_env_num, env.agent_num
+        B = N * A
+        pol = self.trainer.algo_module.models["policy"]
+        w = d.actions.shape[-1]
+        for step in range(T):
+            noise = None
+            if self.cfg.parity_mode:
+                noise = torch.empty(B, d.n_actions, dtype=torch.float32)
+                noise.normal_() if pol.head_kind == lib.HEAD_GAUSSIAN else noise.exponential_(1)
+                noise = noise.to(self.device)
+                self.h2d_bytes += noise.numel() * 4
+            a = lib.OrlRolloutArgs()
+            a.env_kind, a.n_envs, a.n_agents, a.episode_length = lib.ENV_NONE, B, 1, 1
+            a.t_begin, a.t_end = 0, 1
+            a.obs_dim, a.critic_obs_dim, a.n_actions = d.obs_dim, 0, d.n_actions
+            a.activation_id, a.deterministic, a.head_kind = pol.activation_id, 0, pol.head_kind
+            a.policy_params = lib.ptr(pol.flat_params)
+            a.policy_obs = lib.ptr(d.policy_obs[step])
+            a.actions, a.action_log_probs = lib.ptr(d.actions[step]), lib.ptr(d.action_log_probs[step])
+            a.exp_noise = lib.ptr(noise)
+            a.rng_seed, a.rng_step_base, a.rng_counter = int(self.cfg.seed) + 0x9E3779B9 * (self.rank + 1), 0, lib.ptr(self.rng_counter)
+            with self._phase("rollout"):
+                lib.check(self._lib.orl_rollout(a, lib.current_stream()), "orl_rollout(act)")
+            self.gpu_launches += 2
+            obs_d, rew_d, done_d, obs, rewards, dones, infos = env.step_staged(d.actions[step].view(B, w))
+            d.policy_obs[step + 1].view(B, d.obs_dim).copy_(obs_d)
+            d.rewards[step].view(B).copy_(rew_d)
+            dones_env = done_d.min(dim=1, keepdim=True).values           # all agents done
+            d.masks[step + 1].view(N, A).copy_((1.0 - dones_env).expand(N, A))
+            active = (1.0 - done_d) + dones_env * done_d                  # active[dones]=0, active[dones_env]=1
+            d.active_masks[step + 1].view(N, A).copy_(active)
+            self.agent.num_time_steps += N
+            if cb is not None:
+                actions = d.actions[step].cpu().numpy()  # noqa: F841
+                cb.update_locals(locals())
+                if cb.on_step() is False:
+                    return False
+        return True
 
     @torch.no_grad()
     def compute_returns(self):

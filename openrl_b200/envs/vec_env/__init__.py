@@ -1,1 +1,2 @@
 from .device_venv import DeviceVecEnv  # noqa: F401
+from .host_venv import HostVecEnv  # noqa: F401

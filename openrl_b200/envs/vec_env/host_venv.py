@@ -1,0 +1,74 @@
+"""Host-stepped vec-env adapter (BASELINE config 5): the env.step stays on the
+host (MuJoCo-class simulators, the reference's own SyncVectorEnv/AsyncVectorEnv, ...) while the
+policy forward, buffer, GAE and update run on the device.
+
+Wraps any object with the reference's BaseVecEnv duck type — `reset(seed=) -> obs | (obs, infos)`,
+`step(actions) -> (obs (N,A,d), rewards (N,A,1), dones (N,A), infos)`, `parallel_env_num`,
+`agent_num`, `observation_space`, `action_space` — and adds pinned staging buffers so that each step
+costs one D2H copy (actions) and one H2D copy (obs, rewards, dones).  `kind = ORL_ENV_NONE` tells
+the driver to run the per-step loop (onpolicy_driver.py:154-203 semantics)."""
+import numpy as np
+import torch
+
+from ... import lib
+
+
+class HostVecEnv:
+    def __init__(self, env, device="cuda:0"):
+        self.env = env
+        self.kind = lib.ENV_NONE
+        self.device = torch.device(device)
+        self.parallel_env_num = env.parallel_env_num
+        self.agent_num = env.agent_num
+        self.observation_space = env.observation_space
+        self.action_space = env.action_space
+        self.env_name = getattr(env, "env_name", type(env).__name__)
+        self.use_monitor = False
+        self.env_table, self.env_table_len = None, 0
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+        N, A = self.parallel_env_num, self.agent_num
+        d = self.observation_space.shape[0]
+        self.obs_dim = d
+        self._stage = torch.empty(N * A * (d + 2), dtype=torch.float32, pin_memory=torch.cuda.is_available())
+
+    def reset(self, seed=None, options=None):
+        out = self.env.reset(seed=seed) if seed is not None else self.env.reset()
+        if isinstance(out, tuple):
+            return out
+        return out, [{} for _ in range(self.parallel_env_num)]
+
+    def reset_into(self, obs_out, critic_obs_out=None):
+        obs, _ = self.reset()
+        obs_out.copy_(torch.as_tensor(np.asarray(obs, dtype=np.float32)).view_as(obs_out), non_blocking=False)
+
+    def step(self, actions, extra_data=None):
+        return self.env.step(actions)
+
+    def step_staged(self, actions_dev):
+        """actions (B, w) device tensor -> (obs, rewards, dones) device tensors via pinned staging."""
+        N, A, d = self.parallel_env_num, self.agent_num, self.obs_dim
+        a = actions_dev.cpu().numpy().reshape(N, A, -1)          # D2H (synchronises the stream)
+        self.d2h_bytes += a.nbytes
+        obs, rewards, dones, infos = self.env.step(a)
+        st = self._stage.numpy()
+        B = N * A
+        st[:B * d] = np.asarray(obs, dtype=np.float32).reshape(-1)
+        st[B * d:B * d + B] = np.asarray(rewards, dtype=np.float32).reshape(-1)
+        st[B * d + B:] = np.asarray(dones, dtype=np.float32).reshape(-1)
+        dev = self._stage.to(self.device, non_blocking=True)      # one H2D copy
+        self.h2d_bytes += st.nbytes
+        return dev[:B * d].view(B, d), dev[B * d:B * d + B], dev[B * d + B:].view(N, A), obs, rewards, dones, infos
+
+    def random_action(self, infos=None):
+        return np.array([[self.action_space.sample() for _ in range(self.agent_num)] for _ in range(self.parallel_env_num)])
+
+    def batch_rewards(self, buffer):
+        return {}
+
+    def statistics(self, buffer):
+        return {}
+
+    def close(self):
+        if hasattr(self.env, "close"):
+            self.env.close()

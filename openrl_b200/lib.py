@@ -107,6 +107,7 @@ class OrlRolloutArgs(ctypes.Structure):
         ("rng_seed", _c.c_uint64), ("rng_step_base", _c.c_uint64), ("rng_counter", _P),
         ("env_f64", _P), ("env_u64", _P), ("env_i32", _P), ("env_table", _P),
         ("ep_return", _P), ("ep_length", _P), ("episode_stats", _P),
+        ("head_kind", _c.c_int32), ("reserved1", _c.c_int32),
     ]
 
 
@@ -126,6 +127,7 @@ class OrlPpoArgs(ctypes.Structure):
         ("adam_beta1", _F), ("adam_beta2", _F), ("adam_eps", _F), ("weight_decay", _F), ("reserved0", _F),
         ("vn_beta", _D),
         ("partials", _P), ("folded", _P), ("grads", _P), ("train_info", _P),
+        ("head_kind", _c.c_int32), ("reserved1", _c.c_int32),
     ]
 
 
@@ -144,6 +146,7 @@ _SIGNATURES.update({
 })
 
 ENV_NONE, ENV_CARTPOLE, ENV_GRIDWORLD, ENV_MPE_SPREAD = 0, 1, 2, 3
+HEAD_CATEGORICAL, HEAD_GAUSSIAN = 0, 1
 GAE_USE_GAE, GAE_PROPER_TIME_LIMITS, GAE_DENORM = 1, 2, 4
 PPO_HUBER, PPO_CLIP_VALUE, PPO_VALUE_ACTIVE_MASKS, PPO_POLICY_ACTIVE_MASKS = 1, 2, 4, 8
 PPO_VALUENORM, PPO_ADV_NORMALIZE, PPO_MAX_GRAD_NORM, PPO_TF32 = 16, 32, 64, 128

@@ -56,12 +56,33 @@ class Categorical(nn.Module):
         self.linear = _init(nn.Linear(num_inputs, num_outputs), gain, use_orthogonal)
 
 
+class AddBias(nn.Module):
+    def __init__(self, bias):
+        super().__init__()
+        self._bias = nn.Parameter(bias.unsqueeze(1))
+
+
+class DiagGaussian(nn.Module):
+    """distributions.py:75-98: mean = fc_mean(x), log-std = a learnable bias initialised to 0."""
+
+    def __init__(self, num_inputs, num_outputs, use_orthogonal=True, gain=0.01):
+        super().__init__()
+        self.fc_mean = _init(nn.Linear(num_inputs, num_outputs), gain, use_orthogonal)
+        self.logstd = AddBias(torch.zeros(num_outputs))
+
+
 class ACTLayer(nn.Module):
     def __init__(self, action_space, inputs_dim, use_orthogonal, gain):
         super().__init__()
-        if action_space.__class__.__name__ != "Discrete":
-            raise NotImplementedError("only Discrete action heads are built so far")
-        self.action_out = Categorical(inputs_dim, action_space.n, use_orthogonal, gain)
+        kind = action_space.__class__.__name__
+        if kind == "Discrete":
+            self.continuous_action = False
+            self.action_out = Categorical(inputs_dim, action_space.n, use_orthogonal, gain)
+        elif kind == "Box":
+            self.continuous_action = True
+            self.action_out = DiagGaussian(inputs_dim, action_space.shape[0], use_orthogonal, gain)
+        else:
+            raise NotImplementedError(f"action space {kind} has no CUDA head yet (Discrete and Box are built)")
 
 
 class ValueNorm(nn.Module):

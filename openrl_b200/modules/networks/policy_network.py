@@ -19,10 +19,13 @@ class PolicyNetwork(nn.Module):
         if len(shape) != 1 or shape[0] > 64:
             raise NotImplementedError("vector observations of width <= 64 only")
         self.obs_dim = shape[0]
-        self.n_actions = action_space.n
         self.activation_id = cfg.activation_id
         self.base = MLPBase(cfg, shape)
         self.act = ACTLayer(action_space, self.base.output_size, cfg.use_orthogonal, cfg.gain)
+        self.head_kind = 1 if self.act.continuous_action else 0          # lib.HEAD_GAUSSIAN / HEAD_CATEGORICAL
+        self.n_actions = action_space.shape[0] if self.act.continuous_action else action_space.n  # head width
+        if self.n_actions > 8:
+            raise NotImplementedError("head widths up to 8 are built")
         self.device = torch.device(device)
         self._flat = FlatParams(self, self.device)
 

@@ -84,8 +84,9 @@ class PPOModule:
         pol = self.models["policy"]
         obs = torch.as_tensor(obs, dtype=torch.float32).to(self.device).contiguous().view(-1, pol.obs_dim)
         rows = obs.shape[0]
-        actions = torch.empty(rows, 1, dtype=torch.float32, device=self.device)
-        logp = torch.empty(rows, 1, dtype=torch.float32, device=self.device)
+        act_w = pol.n_actions if pol.head_kind == lib.HEAD_GAUSSIAN else 1
+        actions = torch.empty(rows, act_w, dtype=torch.float32, device=self.device)
+        logp = torch.empty(rows, act_w, dtype=torch.float32, device=self.device)
         am = None if action_masks is None else torch.as_tensor(action_masks, dtype=torch.float32).to(self.device).contiguous()
         noise = None if exp_noise is None else torch.as_tensor(exp_noise, dtype=torch.float32).to(self.device).contiguous()
         a = lib.OrlRolloutArgs()
@@ -97,6 +98,7 @@ class PPOModule:
         a.actions, a.action_log_probs = lib.ptr(actions), lib.ptr(logp)
         a.action_masks, a.exp_noise = lib.ptr(am), lib.ptr(noise)
         a.rng_seed, a.rng_step_base = int(rng_seed), int(rng_step)
+        a.head_kind = pol.head_kind
         lib.check(self._lib.orl_rollout(a, lib.current_stream()), "orl_rollout(act)")
         return actions, logp
 

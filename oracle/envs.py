@@ -237,3 +237,47 @@ class SimpleSpreadVec:
 
 
 ENVS["simple_spread"] = SimpleSpreadVec
+
+
+class IdentityContinuousVec:
+    """IdentityEnvcontinuous (openrl/envs/toy_envs/identity_env.py:87-152; dim=2, ep_length=4) under
+    SyncVectorEnv + Single2MultiAgentWrapper: obs Box(1) = the hidden integer state, action Box(1),
+    reward = 1 - |state - clip(action, 0, 1)| computed BEFORE the next state is drawn, per-env PCG64."""
+    obs_dim = 1
+    act_dim = 1
+    agent_num = 1
+
+    def __init__(self, env_num):
+        self.N = env_num
+        self.rng = [pcg64_np_random(None) for _ in range(env_num)]
+        self.state = np.zeros(env_num, np.int64)
+        self.cur = np.zeros(env_num, np.int64)
+
+    def _next(self, i):
+        self.state[i] = self.rng[i].integers(0, 2)
+
+    def reset(self, seed=None):
+        for i in range(self.N):
+            if seed is not None:
+                self.rng[i] = pcg64_np_random(seed + i * 10086)
+            self.cur[i] = 0
+            self._next(i)
+        return self.state.astype(np.float32)[:, None, None].copy()
+
+    def step(self, actions):
+        rewards = np.zeros((self.N, 1, 1), np.float64)
+        dones = np.zeros((self.N, 1), bool)
+        for i in range(self.N):
+            a = np.float32(actions[i, 0, 0])
+            rewards[i, 0, 0] = 1 - np.abs(self.state[i] - np.clip(a, 0, 1))
+            self._next(i)
+            self.cur[i] += 1
+            done = self.cur[i] >= 4
+            dones[i, 0] = done
+            if done:  # auto-reset
+                self.cur[i] = 0
+                self._next(i)
+        return self.state.astype(np.float32)[:, None, None].copy(), rewards, dones, None
+
+
+ENVS["IdentityEnvcontinuous"] = IdentityContinuousVec

@@ -228,6 +228,10 @@ def main():
                    "--use_recurrent_policy", "true", "--use_valuenorm", "true", "--use_adv_normalize", "true",
                    "--log_interval", "1000"],
                   2, "mpe_gru")
+    if a.only in ("", "gaussian"):
+        gen_trace("IdentityEnvcontinuous", 4,
+                  ["--seed", "0", "--episode_length", "16", "--ppo_epoch", "2", "--num_mini_batch", "2", "--log_interval", "1000"],
+                  2, "identity_continuous")
     if a.only in ("", "mpe_mlp"):
         gen_trace("simple_spread", 4,
                   ["--seed", "0", "--episode_length", "25", "--ppo_epoch", "2", "--lr", "7e-4", "--critic_lr", "7e-4",

@@ -60,8 +60,10 @@ class Trainer:
         torch.manual_seed(cfg.seed)
         self.env = env if env is not None else oenvs.ENVS[env_id](env_num)
         self.env.reset(seed=cfg.seed)
-        d, n = self.env.obs_dim, self.env.n_actions
-        self.pol = nets.init_policy(cfg, d, "Discrete", n)
+        d = self.env.obs_dim
+        self.box = hasattr(self.env, "act_dim")
+        n = self.env.act_dim if self.box else self.env.n_actions
+        self.pol = nets.init_policy(cfg, d, "Box" if self.box else "Discrete", n)
         self.cri = nets.init_critic(cfg, d)
         self.opt_p, self.opt_c = ppo.make_optimizers(cfg, self.pol, self.cri)
         self.vn = ppo.ValueNormState() if (cfg.use_valuenorm or cfg.use_popart) else None
@@ -71,7 +73,8 @@ class Trainer:
             obs=f(T + 1, N, A, d), value_preds=f(T + 1, N, A, 1), returns=f(T + 1, N, A, 1),
             masks=np.ones((T + 1, N, A, 1), np.float32), bad_masks=np.ones((T + 1, N, A, 1), np.float32),
             active_masks=np.ones((T + 1, N, A, 1), np.float32), action_masks=np.ones((T + 1, N, A, n), np.float32),
-            actions=f(T, N, A, 1), action_log_probs=f(T, N, A, 1), rewards=f(T, N, A, 1))
+            actions=f(T, N, A, n if self.box else 1), action_log_probs=f(T, N, A, n if self.box else 1),
+            rewards=f(T, N, A, 1))
         # RLDriver.reset_and_buffer_init: a second, unseeded reset
         self.buf.obs[0] = self.env.reset()
         self.log = []
@@ -82,9 +85,12 @@ class Trainer:
             with torch.no_grad():
                 obs = torch.from_numpy(np.concatenate(b.obs[step]))
                 am = torch.from_numpy(np.concatenate(b.action_masks[step]))
-                actions, logp, _ = nets.policy_act(self.pol, cfg, obs, am)
+                if self.box:
+                    actions, logp = nets.policy_act_gaussian(self.pol, cfg, obs)
+                else:
+                    actions, logp, _ = nets.policy_act(self.pol, cfg, obs, am)
                 values, _ = nets.critic_forward(self.cri, cfg, obs)
-            actions = actions.numpy().reshape(self.N, 1, 1)
+            actions = actions.numpy().reshape(self.N, 1, -1)
             obs2, rewards, dones, _ = self.env.step(actions)
             dones_env = np.all(dones, axis=1)
             masks = np.ones((self.N, 1, 1), np.float32)
@@ -94,7 +100,7 @@ class Trainer:
             active[dones_env] = 1.0
             b.obs[step + 1] = obs2
             b.actions[step] = actions
-            b.action_log_probs[step] = logp.numpy().reshape(self.N, 1, 1)
+            b.action_log_probs[step] = logp.numpy().reshape(self.N, 1, -1)
             b.value_preds[step] = values.numpy().reshape(self.N, 1, 1)
             b.rewards[step] = rewards
             b.masks[step + 1] = masks

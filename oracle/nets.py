@@ -196,6 +196,44 @@ def policy_eval(p, cfg, obs, actions, action_masks=None, active_masks=None, rnn_
     return logp, ent
 
 
+def gaussian_params(p, feat):
+    """DiagGaussian.forward (distributions.py:75-98): mean = fc_mean(x), std = exp(logstd bias)."""
+    mean = F.linear(feat, p["act.action_out.fc_mean.weight"], p["act.action_out.fc_mean.bias"])
+    logstd = torch.zeros_like(mean) + p["act.action_out.logstd._bias"].t().view(1, -1)
+    return mean, logstd.exp()
+
+
+def policy_act_gaussian(p, cfg, obs, deterministic=False, normal_noise=None):
+    """ACTLayer.forward, continuous branch (act.py:74-77): Normal.sample() == torch.normal(mean, std)
+    == N(0,1) noise * std + mean with the noise drawn by `empty.normal_()` from the global generator;
+    log-probs stay per dimension (distributions.py:35-37)."""
+    feat, _ = policy_features(p, cfg, obs)
+    mean, std = gaussian_params(p, feat)
+    if deterministic:
+        actions = mean
+    else:
+        if normal_noise is None:
+            actions = torch.normal(mean, std)
+        else:
+            actions = normal_noise * std + mean
+    logp = torch.distributions.Normal(mean, std).log_prob(actions)
+    return actions, logp
+
+
+def policy_eval_gaussian(p, cfg, obs, actions, active_masks=None):
+    """ACTLayer.evaluate_actions, continuous branch (act.py:150-158)."""
+    feat, _ = policy_features(p, cfg, obs)
+    mean, std = gaussian_params(p, feat)
+    dist = torch.distributions.Normal(mean, std)
+    logp = dist.log_prob(actions)
+    ent = dist.entropy()
+    if active_masks is not None and cfg.use_policy_active_masks:
+        ent = (ent * active_masks).sum() / active_masks.sum()
+    else:
+        ent = ent.mean()
+    return logp, ent
+
+
 def critic_forward(p, cfg, obs, rnn_states=None, masks=None):
     """ValueNetwork.forward (value_network.py:113-136)."""
     f = mlp_base(p, "base", obs, cfg.layer_N, cfg.activation_id)

@@ -88,8 +88,11 @@ def ppo_update(cfg, pol, cri, opt_p, opt_c, vn, batch):
     opt_c.zero_grad()
     active = batch["active_masks"]
     values, _ = nets.critic_forward(cri, cfg, batch["critic_obs"], batch.get("rnn_states_critic"), batch.get("masks"))
-    logp, ent = nets.policy_eval(pol, cfg, batch["policy_obs"], batch["actions"], batch.get("action_masks"),
-                                 active, batch.get("rnn_states"), batch.get("masks"))
+    if "act.action_out.fc_mean.weight" in pol:  # Box action space
+        logp, ent = nets.policy_eval_gaussian(pol, cfg, batch["policy_obs"], batch["actions"], active)
+    else:
+        logp, ent = nets.policy_eval(pol, cfg, batch["policy_obs"], batch["actions"], batch.get("action_masks"),
+                                     active, batch.get("rnn_states"), batch.get("masks"))
     ratio = torch.exp(logp - batch["old_logp"])
     adv = batch["adv"]
     surr1 = ratio * adv

@@ -4,7 +4,7 @@ absent from /root/reference)."""
 
 
 class EnvSpec:
-    def __init__(self, id, entry_point, max_episode_steps=None, kwargs=None):
+    def __init__(self, id, entry_point=None, max_episode_steps=None, kwargs=None):
         self.id = id
         self.entry_point = entry_point
         self.max_episode_steps = max_episode_steps

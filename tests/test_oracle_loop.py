@@ -19,7 +19,8 @@ def _params(tr):
     return out
 
 
-@pytest.mark.parametrize("tag,env_id", [("cartpole", "CartPole-v1"), ("cartpole_c1", "CartPole-v1")])
+@pytest.mark.parametrize("tag,env_id", [("cartpole", "CartPole-v1"), ("cartpole_c1", "CartPole-v1"),
+                                        ("identity_continuous", "IdentityEnvcontinuous")])
 def test_oracle_reproduces_reference_trace(tag, env_id):
     d = np.load(os.path.join(GOLDEN, f"trace_{tag}.npz"), allow_pickle=True)
     cfg = loop.cfg_from_flags(str(d["meta/flags"]))
