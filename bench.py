@@ -46,6 +46,7 @@ class ClockSampler:
 
     def __init__(self, index=0):
         self.lines, self.proc, self.index = [], None, index
+        self.window = None   # (t0, t1) wall-clock bounds of the timed region
 
     def start(self):
         try:
@@ -58,7 +59,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
     def stop(self):
         if self.proc is None:
@@ -69,7 +70,13 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        lines = self.lines
+        scope = "process lifetime (sampler runs from before warm-up to after the timed region)"
+        if self.window is not None:
+            inside = [x for x in lines if self.window[0] <= x[0] <= self.window[1] + 0.05]
+            if len(inside) >= 3:
+                lines, scope = inside, "timed region"
+        for _, ln in lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -80,8 +87,9 @@ class ClockSampler:
             for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        busy = [x for x in sm if x > 0.5 * max(mx)] if mx else sm   # samples taken under load
+        return {"sm_mhz": statistics.median(busy or sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "scope": scope, "reasons": sorted(reasons)}
 
 
 def build_agent(rank, world, parity=False):
@@ -165,16 +173,17 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        drv.device_iteration()
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        drv.device_iteration()
+    barrier()
     drv.phase_events = []
     l0 = drv.gpu_launches + drv.trainer.gpu_launches
     events = []
     barrier()
+    t_wall0 = time.time()
     for _ in range(args.steps):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -183,6 +192,7 @@ def run_ours(args):
         e1.record()
         events.append((e0, e1))
     barrier()
+    sampler.window = (t_wall0, time.time())
     launches = drv.gpu_launches + drv.trainer.gpu_launches - l0
     total_s = sum(a.elapsed_time(b) for a, b in events) * 1e-3
     phases = {}
@@ -193,7 +203,6 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_s = float(t.item())
-    clocks = sampler.stop() if rank == 0 else None
     env_steps = N_ENVS * T * args.steps * world
     value = env_steps / total_s
 
@@ -216,6 +225,7 @@ def run_ours(args):
     h2d = (tr2.h2d_bytes - h2d0 + dr2.h2d_bytes) / args.steps
     d2h = (tr2.d2h_bytes - d2h0[0] + dr2.d2h_bytes + getattr(env2, "d2h_bytes", 0) - d2h0[1]) / args.steps
 
+    clocks = sampler.stop() if rank == 0 else None
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -241,7 +251,9 @@ def run_ours(args):
         "e2e": {"value": env_steps / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "PPOAgent.train(total_time_steps) incl. construction, per-iteration logging reads"},
         "roofline": {"bound": "hbm", "kernel": "gae_scan_kernel (orl_gae), >=1 GB shape, L2 flushed", "achieved": gae["1GB"]["GBps"],
-                     "peak": hbm_peak, "peak_source": how, "unit": "GB/s", "frac": gae["1GB"]["GBps"] / hbm_peak, "traffic": None,
+                     "peak": hbm_peak, "peak_source": how, "unit": "GB/s", "frac": gae["1GB"]["GBps"] / hbm_peak,
+                     "algorithmic_bytes_per_launch": 128 * (1 << 21) * 24,
+                     "traffic": 4.303432e9 + 2.126753e9, "traffic_source": "ncu --set full, profiles/r1_ncu_summary.md (dram read+write)",
                      "config_shape": {**gae["config"], "frac": gae["config"]["GBps"] / hbm_peak,
                                       "in_step_avg_s": gae_in_step,
                                       "in_step_GBps": N_ENVS * T * 24 / max(gae_in_step, 1e-12) / 1e9}},
