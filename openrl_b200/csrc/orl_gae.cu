@@ -350,8 +350,10 @@ int launch_gae(const GaeParams& p, int flags, cudaStream_t st) {
         return d ? launch_gae2<VEC, U, true, false, true>(p, st) : launch_gae2<VEC, U, true, false, false>(p, st);
     }
     if (t) return d ? launch_gae2<VEC, U, false, true, true>(p, st) : launch_gae2<VEC, U, false, true, false>(p, st);
-    // !gae & !ptl ignores the normaliser (replay_data.py:417-423)
-    return launch_gae2<VEC, U, false, false, false>(p, st);
+    // !gae & !ptl: the returns ignore the normaliser (replay_data.py:417-423) — the kernel's return
+    // formula does not touch V in that branch — but the fused advantage still subtracts the
+    // DENORMALISED value (ppo.py:384-399), so DENORM is honoured
+    return d ? launch_gae2<VEC, U, false, false, true>(p, st) : launch_gae2<VEC, U, false, false, false>(p, st);
 }
 
 bool aligned16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; }

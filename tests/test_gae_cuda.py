@@ -77,7 +77,7 @@ def test_gae_bit_exact_vs_oracle_random(orl_lib, cuda, T, N, A, flags):
     else:
         assert np.array_equal(got, want_ret)
     # fused advantage: returns[:-1] - denorm(value_preds[:-1])  (ppo.py:384-399)
-    vn_for_adv = vn_state if (dn and (use_gae or ptl)) else None
+    vn_for_adv = vn_state if dn else None   # ppo.py:384-399 denormalises whenever a normaliser exists
     raw, _ = ogae.advantages(want_ret, want_vp if use_gae else vp, active, vn_state=vn_for_adv)
     assert np.array_equal(adv.reshape(sh), raw)
     a64 = raw.astype(np.float64)
