@@ -207,6 +207,9 @@ int orl_critic_values(const float* critic_params, int obs_dim, int activation_id
 #define ORL_PPO_VALUENORM 16          /* cfg.use_valuenorm (normaliser present) */
 #define ORL_PPO_ADV_NORMALIZE 32      /* cfg.use_adv_normalize (ppo.py:402-403) */
 #define ORL_PPO_MAX_GRAD_NORM 64      /* cfg.use_max_grad_norm */
+#define ORL_PPO_A2C 256               /* A2CAlgorithm.prepare_loss (openrl/algorithms/a2c.py:39-140): policy loss
+                                         -adv * log-prob instead of the clipped surrogate; ratio reported as 0 */
+#define ORL_PPO_DUAL_CLIP 512         /* cfg.dual_clip_ppo: ratio = min(ratio, dual_clip_coeff) (ppo.py:304-305) */
 #define ORL_PPO_TF32 128              /* fast mode: the 64x64 GEMMs of the trunk on tcgen05 tensor cores
                                          (TF32 operands, FP32 accumulate in TMEM); obs widths <= 8.
                                          Without it everything is fp32 FFMA (1e-4 loss parity mode). */
@@ -251,7 +254,7 @@ typedef struct OrlPpoArgs {
     float* train_info;           /* (6) += {value_loss, critic_grad_norm, policy_loss, dist_entropy,
                                              actor_grad_norm, ratio}  (ppo.py:430-451) */
     int32_t head_kind;           /* ORL_HEAD_*: with GAUSSIAN actions / old_log_probs are (T*B, n) */
-    int32_t reserved1;
+    float dual_clip_coeff;       /* cfg.dual_clip_coeff (used with ORL_PPO_DUAL_CLIP) */
 } OrlPpoArgs;
 /* floats per partial row for given shapes (>= folded gradient size + 8 loss slots, multiple of 4) */
 int orl_ppo_stride(int obs_dim, int critic_obs_dim, int n_actions);   /* valid for both head kinds */

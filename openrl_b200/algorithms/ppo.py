@@ -49,7 +49,9 @@ class PPOAlgorithm:
                          and self.head_kind == lib.HEAD_CATEGORICAL)
         if self.use_tf32:
             self.flags |= lib.PPO_TF32
-        for name in ("use_joint_action_loss", "dual_clip_ppo", "use_policy_vhead", "use_share_model", "use_popart",
+        if getattr(cfg, "dual_clip_ppo", False):
+            self.flags |= lib.PPO_DUAL_CLIP
+        for name in ("use_joint_action_loss", "use_policy_vhead", "use_share_model", "use_popart",
                      "use_amp", "use_deepspeed", "use_naive_recurrent_policy", "use_recurrent_policy"):
             if getattr(cfg, name, False):
                 raise NotImplementedError(f"cfg.{name} is not built into the CUDA update yet (SURVEY.md §8f)")
@@ -73,6 +75,7 @@ class PPOAlgorithm:
         a.obs_dim, a.critic_obs_dim, a.n_actions, a.activation_id = self.d, self.dc, self.n, pol.activation_id
         a.flags, a.grid_per_net = self.flags, self.grid_per_net
         a.head_kind = self.head_kind
+        a.dual_clip_coeff = float(getattr(self.cfg, "dual_clip_coeff", 3.0))
         total = buf.episode_length * buf.n_rollout_threads * buf.num_agents
         a.batch_rows, a.row_begin, a.total_rows = int(batch_rows), int(row_begin), int(total)
         a.indices = lib.ptr(indices)

@@ -235,7 +235,6 @@ __device__ __forceinline__ void ppo_net_pass(const OrlPpoArgs& a, float* smem, i
                         const long long gi = row_idx[row];
                         const float* logstd = params + net_offsets(d, n, 1).ls;
                         const float adv = apply_adv_norm(advn, row_c[row]);
-                        const float lo = 1.0f - a.clip_param, hi = 1.0f + a.clip_param;
                         const float wrow = pol_masks ? active * inv_act : inv_rows;
                         const float went_row = pol_masks ? active * inv_act : inv_rows / (float)n;
 #pragma unroll
@@ -244,14 +243,11 @@ __device__ __forceinline__ void ppo_net_pass(const OrlPpoArgs& a, float* smem, i
                                 const float mean = out[j], ls = logstd[j], std = expf(ls), var = std * std;
                                 const float act = a.actions[gi * n + j], diff = act - mean;
                                 const float lp = -(diff * diff) / (2.0f * var) - ls - 0.9189385332046727f;
-                                const float ratio = expf(lp - a.old_log_probs[gi * n + j]);
-                                const float surr1 = ratio * adv, surr2 = fminf(fmaxf(ratio, lo), hi) * adv;
-                                const bool inside = ratio >= lo && ratio <= hi;
-                                const float sel = surr1 < surr2 ? 1.f : (surr1 > surr2 ? 0.f : (inside ? 1.f : 0.5f));
-                                loss0 += -fminf(surr1, surr2) * wrow;
+                                const PgTerm pg = pg_term(lp, a.old_log_probs[gi * n + j], adv, a.clip_param, a.flags, a.dual_clip_coeff);
+                                loss0 += pg.loss * wrow;
                                 loss1 += (1.4189385332046727f + ls) * went_row;   // 0.5 + 0.5 log(2 pi) + log(std)
-                                loss2 += ratio / (float)n;
-                                const float dlp = -sel * adv * ratio * wrow;
+                                loss2 += pg.ratio / (float)n;
+                                const float dlp = pg.dlogp * wrow;
                                 dl[j] = dlp * diff / var;                                               // dL/dmean
                                 dls_acc[j] += dlp * (diff * diff / var - 1.0f) - a.entropy_coef * went_row;   // dL/dlogstd
                             }
@@ -270,21 +266,16 @@ __device__ __forceinline__ void ppo_net_pass(const OrlPpoArgs& a, float* smem, i
                         float lp = nl[0];
 #pragma unroll
                         for (int j = 1; j < MAX_OUT; ++j) if (j == act) lp = nl[j];
-                        const float ratio = expf(lp - row_b[row]);
                         const float adv = apply_adv_norm(advn, row_c[row]);
-                        const float lo = 1.0f - a.clip_param, hi = 1.0f + a.clip_param;
-                        const float surr1 = ratio * adv;
-                        const float surr2 = fminf(fmaxf(ratio, lo), hi) * adv;
-                        const bool inside = ratio >= lo && ratio <= hi;
-                        const float sel = surr1 < surr2 ? 1.f : (surr1 > surr2 ? 0.f : (inside ? 1.f : 0.5f));
+                        const PgTerm pg = pg_term(lp, row_b[row], adv, a.clip_param, a.flags, a.dual_clip_coeff);
                         const float wrow = pol_masks ? active * inv_act : inv_rows;
                         float ent = 0.f;
 #pragma unroll
                         for (int j = 0; j < MAX_OUT; ++j) if (j < n) ent -= pr[j] * nl[j];
-                        loss0 += -fminf(surr1, surr2) * wrow;
+                        loss0 += pg.loss * wrow;
                         loss1 += ent * wrow;
-                        loss2 += ratio;
-                        const float dlp = -sel * adv * ratio * wrow;
+                        loss2 += pg.ratio;
+                        const float dlp = pg.dlogp * wrow;
                         const float went = a.entropy_coef * wrow;
 #pragma unroll
                         for (int j = 0; j < MAX_OUT; ++j) {

@@ -302,20 +302,16 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, uint8_t* smem, 
                 float lp = nl[0];
 #pragma unroll
                 for (int j = 1; j < MAX_OUT; ++j) if (j == act) lp = nl[j];
-                const float ratio = expf(lp - row_b);
                 float adv = row_c;
                 if (an.two) adv = (adv - an.m0) / an.s0;
                 adv = (adv - an.m1) / an.s1;
-                const float lo = 1.0f - a.clip_param, hi = 1.0f + a.clip_param;
-                const float surr1 = ratio * adv, surr2 = fminf(fmaxf(ratio, lo), hi) * adv;
-                const bool inside = ratio >= lo && ratio <= hi;
-                const float sel = surr1 < surr2 ? 1.f : (surr1 > surr2 ? 0.f : (inside ? 1.f : 0.5f));
+                const PgTerm pg = pg_term(lp, row_b, adv, a.clip_param, a.flags, a.dual_clip_coeff);
                 const float wrow = pol_masks ? active * inv_act : inv_rows;
                 float ent = 0.f;
 #pragma unroll
                 for (int j = 0; j < MAX_OUT; ++j) if (j < n) ent -= pr[j] * nl[j];
-                if (half == 0) { loss0 += -fminf(surr1, surr2) * wrow; loss1 += ent * wrow; loss2 += ratio; }
-                const float dlp = -sel * adv * ratio * wrow, went = a.entropy_coef * wrow;
+                if (half == 0) { loss0 += pg.loss * wrow; loss1 += ent * wrow; loss2 += pg.ratio; }
+                const float dlp = pg.dlogp * wrow, went = a.entropy_coef * wrow;
 #pragma unroll
                 for (int j = 0; j < MAX_OUT; ++j)
                     if (j < n && !((masked >> j) & 1u)) dl[j] = dlp * ((j == act ? 1.f : 0.f) - pr[j]) + went * pr[j] * (nl[j] + ent);

@@ -127,7 +127,7 @@ class OrlPpoArgs(ctypes.Structure):
         ("adam_beta1", _F), ("adam_beta2", _F), ("adam_eps", _F), ("weight_decay", _F), ("reserved0", _F),
         ("vn_beta", _D),
         ("partials", _P), ("folded", _P), ("grads", _P), ("train_info", _P),
-        ("head_kind", _c.c_int32), ("reserved1", _c.c_int32),
+        ("head_kind", _c.c_int32), ("dual_clip_coeff", _F),
     ]
 
 
@@ -150,3 +150,4 @@ HEAD_CATEGORICAL, HEAD_GAUSSIAN = 0, 1
 GAE_USE_GAE, GAE_PROPER_TIME_LIMITS, GAE_DENORM = 1, 2, 4
 PPO_HUBER, PPO_CLIP_VALUE, PPO_VALUE_ACTIVE_MASKS, PPO_POLICY_ACTIVE_MASKS = 1, 2, 4, 8
 PPO_VALUENORM, PPO_ADV_NORMALIZE, PPO_MAX_GRAD_NORM, PPO_TF32 = 16, 32, 64, 128
+PPO_A2C, PPO_DUAL_CLIP = 256, 512

@@ -93,11 +93,17 @@ def ppo_update(cfg, pol, cri, opt_p, opt_c, vn, batch):
     else:
         logp, ent = nets.policy_eval(pol, cfg, batch["policy_obs"], batch["actions"], batch.get("action_masks"),
                                      active, batch.get("rnn_states"), batch.get("masks"))
-    ratio = torch.exp(logp - batch["old_logp"])
     adv = batch["adv"]
-    surr1 = ratio * adv
-    surr2 = torch.clamp(ratio, 1.0 - cfg.clip_param, 1.0 + cfg.clip_param) * adv
-    surr = torch.min(surr1, surr2)
+    if getattr(cfg, "a2c", False):          # A2CAlgorithm.prepare_loss (a2c.py:88): -adv * logp, ratio reported 0
+        ratio = torch.zeros(1)
+        surr = adv.detach() * logp
+    else:
+        ratio = torch.exp(logp - batch["old_logp"])
+        if getattr(cfg, "dual_clip_ppo", False):   # ppo.py:304-305
+            ratio = torch.min(ratio, torch.tensor(cfg.dual_clip_coeff))
+        surr1 = ratio * adv
+        surr2 = torch.clamp(ratio, 1.0 - cfg.clip_param, 1.0 + cfg.clip_param) * adv
+        surr = torch.min(surr1, surr2)
     if cfg.use_policy_active_masks:
         policy_loss = (-torch.sum(surr, dim=-1, keepdim=True) * active).sum() / active.sum()
     else:

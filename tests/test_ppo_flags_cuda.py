@@ -22,10 +22,14 @@ CASES = [
     ["--max_grad_norm", "0.5"],
     ["--use_proper_time_limits", "true"],
     ["--use_gae", "false"],
+    ["--dual_clip_ppo", "true", "--dual_clip_coeff", "1.05"],
+    ["A2C"],
 ]
 
 
 def _build(flags, env_id="GridWorldEnv", N=24, T=20, seed=3):
+    a2c = "A2C" in flags
+    flags = [f for f in flags if f != "A2C"]
     import torch
 
     from openrl_b200.algorithms.ppo import PPOAlgorithm
@@ -39,8 +43,11 @@ def _build(flags, env_id="GridWorldEnv", N=24, T=20, seed=3):
     env = make(env_id, env_num=N)
     net = PPONet(env, cfg=cfg, device="cuda:0")
     cfg.n_rollout_threads = N
-    trainer = PPOAlgorithm(cfg, net.module, agent_num=1, device=net.device)
+    from openrl_b200.algorithms import A2CAlgorithm
+
+    trainer = (A2CAlgorithm if a2c else PPOAlgorithm)(cfg, net.module, agent_num=1, device=net.device)
     buf = NormalReplayBuffer(cfg, 1, env.observation_space, env.action_space, device=net.device)
+    cfg.a2c = a2c
     return cfg, net, trainer, buf
 
 
@@ -56,7 +63,7 @@ def test_update_flag_matrix_vs_oracle(cuda, flags):
     g = torch.Generator().manual_seed(11)
     b.policy_obs.copy_(torch.randint(0, 10, b.policy_obs.shape, generator=g).float())
     b.actions.copy_(torch.randint(0, 5, b.actions.shape, generator=g).float())
-    b.action_log_probs.copy_(-1.6 + 0.1 * torch.randn(b.action_log_probs.shape, generator=g))
+    b.action_log_probs.copy_(-1.6 + 0.15 * torch.randn(b.action_log_probs.shape, generator=g))
     b.rewards.copy_(torch.randn(b.rewards.shape, generator=g))
     b.value_preds.copy_(0.5 * torch.randn(b.value_preds.shape, generator=g))
     b.masks.copy_((torch.rand(b.masks.shape, generator=g) > 0.1).float())
@@ -71,6 +78,7 @@ def test_update_flag_matrix_vs_oracle(cuda, flags):
 
     # ---- oracle on the same data ----
     ocfg = loop.make_cfg(**{k: getattr(cfg, k) for k in loop.DEFAULTS if hasattr(cfg, k)})
+    ocfg.a2c = cfg.a2c
     h = lambda x: x.cpu().numpy()
     ret_o, vp_o = ogae.compute_returns(h(b.rewards), h(b.value_preds), h(b.masks), h(b.bad_masks), h(b.value_preds)[-1],
                                        cfg.gamma, cfg.gae_lambda, cfg.use_gae, cfg.use_proper_time_limits,
