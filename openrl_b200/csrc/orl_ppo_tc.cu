@@ -2,10 +2,10 @@
 // TMEM) — the "fast mode" sibling of ppo_fwdbwd_kernel (orl_ppo.cu), producing the same folded
 // partial gradients and loss sums.  Selected with ORL_PPO_TF32; obs widths <= 8 (CartPole, GridWorld).
 //
-// CTA = 256 threads = 128 tile rows x 2 column halves: warps w and w+4 own the same 32 rows (the TMEM
-// lane quadrant w%4) and columns [0,32) / [32,64), so every row-wise operation (fc1 with K = d <= 8,
+// CTA = 512 threads = 128 tile rows x 4 column quarters: warps w, w+4, w+8, w+12 own the same 32 rows
+// (the TMEM lane quadrant w%4) and 16 columns each, so every row-wise operation (fc1 with K = d <= 8,
 // LayerNorm forward/backward, head, loss) is thread-local apart from a handful of two-float
-// exchanges through shared memory, and the three 64-wide GEMMs of the row tile go to the tensor
+// exchanges through shared memory (named barriers per row group), and the three 64-wide GEMMs of the row tile go to the tensor
 // core, issued by one elected thread:
 //     GEMM1  Z3 [128x64]  = n1 [128x64]  . W3f^T            (M=128, N=64, K=64)    fwd fc3
 //     GEMM2  dN1[128x64]  = dZ3[128x64]  . W3f              (M=128, N=64, K=64)    bwd-data fc3
@@ -29,7 +29,9 @@ namespace {
 using namespace orl;
 using namespace orl::tc;
 
-constexpr int T_M = 128, T_NT = 256;   // two threads per row: thread = (row, column half)
+constexpr int T_M = 128, T_NT = 512;   // four threads per row: thread = (row, column quarter)
+constexpr int T_Q = T_NT / T_M;        // threads per row
+constexpr int T_CH = 8 / T_Q;          // 8-column chunks per thread
 constexpr int NB3 = 80;                       // rows of B3: 64 (n1^T) + 8 (X^T) + 8 (ones / zero)
 constexpr uint32_t LBO_A = 128 * 16 + 16;     // panel stride of 128-row tiles (padded)
 constexpr uint32_t LBO_B3 = NB3 * 16 + 16;
@@ -48,14 +50,17 @@ struct AdvNormTc { float m0, s0, m1, s1; bool two; };
 // NOUT: head width known at compile time (1 critic, 2, 5) or 8 = generic (runtime n <= 8)
 #define FOR_OUT(j) _Pragma("unroll") for (int j = 0; j < NOUT; ++j) if (NOUT != 8 || j < n)
 
-// pair exchange: both column halves of a row publish `cnt` partial sums and read the other's
+// row-group barrier: the T_Q warps that share rows [32g, 32g+32) (g = warp % 4)
+#define ROWGROUP_SYNC() asm volatile("bar.sync %0, %1;" ::"r"(1 + (warp & 3)), "r"(32 * T_Q) : "memory")
+// exchange: the T_Q column slices of a row publish two partial sums and read the others'
 #define PAIR_SUM2(v0, v1)                                                          \
     do {                                                                           \
         xch[(half * T_M + row) * 8 + 0] = (v0); xch[(half * T_M + row) * 8 + 1] = (v1); \
-        __syncthreads();                                                           \
-        const float o0_ = xch[((half ^ 1) * T_M + row) * 8 + 0], o1_ = xch[((half ^ 1) * T_M + row) * 8 + 1]; \
-        (v0) += o0_; (v1) += o1_;                                                  \
-        __syncthreads();                                                           \
+        ROWGROUP_SYNC();                                                           \
+        float t0_ = 0.f, t1_ = 0.f;                                                \
+        _Pragma("unroll") for (int q_ = 0; q_ < T_Q; ++q_) { t0_ += xch[(q_ * T_M + row) * 8 + 0]; t1_ += xch[(q_ * T_M + row) * 8 + 1]; } \
+        (v0) = t0_; (v1) = t1_;                                                    \
+        ROWGROUP_SYNC();                                                           \
     } while (0)
 
 template <bool POLICY, int NOUT>
@@ -65,7 +70,7 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, uint8_t* smem, 
     const float* params = POLICY ? a.policy_params : a.critic_params;
     const float* obs = POLICY ? a.policy_obs : a.critic_obs;
     const int tid = threadIdx.x, warp = tid >> 5;
-    const int row = tid & 127, half = tid >> 7, c0 = 4 * half;   // this thread: tile row, column chunks [c0, c0+4)
+    const int row = tid & 127, half = tid >> 7, c0 = T_CH * half;   // this thread: tile row, column slice `half`, chunks [c0, c0+T_CH)
     const NetOffsets po = net_offsets(d, n);
 
     // ---- shared memory carve-up (all tensor-core tiles 128-byte aligned) ----
@@ -82,8 +87,8 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, uint8_t* smem, 
     float* bhf = whf + MAX_OUT * H;
     float* swh = bhf + MAX_OUT;                  // [8] row sums of whf
     float* DLs = swh + MAX_OUT;                  // [128][8]
-    float* xch = DLs + T_M * 8;                  // [2][128][8] pair exchange
-    float* red = xch + 2 * T_M * 8;              // [32]
+    float* xch = DLs + T_M * 8;                  // [T_Q][128][8] row exchange
+    float* red = xch + T_Q * T_M * 8;            // [64]
     uint64_t* bars = reinterpret_cast<uint64_t*>(red + 32);  // 3 mbarriers
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 3);
 
@@ -153,29 +158,62 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, uint8_t* smem, 
         vn_mean = s.mean; vn_std = s.std;
     }
 
-    float gh_acc[2] = {0.f, 0.f};             // GH outputs o = tid + 256*q  (j = o/64, k = o%64), o < n*64
-    float dbh_acc = 0.f;                        // thread t < n: sum_m dL[m][t]
+    float gh_acc[1] = {0.f};                  // GH output o = tid  (j = o/64, k = o%64), o < n*64 <= 512
+    float dbh_acc = 0.f;                        // threads with k == 0: sum_m dL[m][j]
     float loss0 = 0.f, loss1 = 0.f, loss2 = 0.f;
     uint32_t it = 0;
+    // cycle attribution of the tile pipeline (thread 0 only; written to the spare loss slots 3..7 of the
+    // partial row and read by tools/tc_phase_profile.py): [0] gather+fc1+LN1 until GEMM1 is issued,
+    // [1] wait GEMM1, [2] LN3+head+loss+dZ3 until GEMM2 is issued, [3] wait GEMM2, [4] LN1-bwd, GEMM3 issue, GH
+    uint32_t prof[5] = {0u, 0u, 0u, 0u, 0u};
+    uint32_t tprev = (uint32_t)clock();
+#define PROF_MARK(i) do { if (tid == 0) { const uint32_t now_ = (uint32_t)clock(); prof[i] += now_ - tprev; tprev = now_; } } while (0)
 
     const long long n_tiles = (a.batch_rows + T_M - 1) / T_M;
+    bool nx_valid; long long nx_gi; float nx_x[8], nx_a = 0.f, nx_b = 0.f, nx_c = 0.f, nx_act = 0.f;
+    {   // row data of the first tile
+        const long long r0 = (long long)cta * T_M + row;
+        nx_valid = (cta < n_tiles) && r0 < a.batch_rows;
+        nx_gi = nx_valid ? (a.indices ? a.indices[r0] : a.row_begin + r0) : -1;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) nx_x[k] = (nx_valid && k < d) ? obs[nx_gi * d + k] : 0.f;
+        if (nx_valid) {
+            if (POLICY) { nx_a = a.actions[nx_gi]; nx_b = a.old_log_probs[nx_gi]; nx_c = a.advantages[nx_gi]; }
+            else { nx_a = a.value_preds[nx_gi]; nx_b = a.returns[nx_gi]; }
+            nx_act = a.active_masks[nx_gi];
+        }
+    }
     for (long long tile = cta; tile < n_tiles; tile += G, ++it) {
         const uint32_t par = it & 1u;
-        const long long r = tile * T_M + row;
-        const bool valid = r < a.batch_rows;
-        const long long gi = valid ? (a.indices ? a.indices[r] : a.row_begin + r) : -1;
+        const bool valid = nx_valid;
+        const long long gi = nx_gi;
+        float x[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] = nx_x[k];
+        float row_a = nx_a, row_b = nx_b, row_c = nx_c, active = nx_act;
+        {   // prefetch the NEXT tile's row data (index -> observation / scalars: two dependent global
+            // round trips) so that it overlaps this tile's work
+            const long long rn = (tile + G) * T_M + row;
+            nx_valid = (tile + G < n_tiles) && rn < a.batch_rows;
+            nx_gi = nx_valid ? (a.indices ? a.indices[rn] : a.row_begin + rn) : -1;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) nx_x[k] = (nx_valid && k < d) ? obs[nx_gi * d + k] : 0.f;
+            nx_a = nx_b = nx_c = nx_act = 0.f;
+            if (nx_valid) {
+                if (POLICY) { nx_a = a.actions[nx_gi]; nx_b = a.old_log_probs[nx_gi]; nx_c = a.advantages[nx_gi]; }
+                else { nx_a = a.value_preds[nx_gi]; nx_b = a.returns[nx_gi]; }
+                nx_act = a.active_masks[nx_gi];
+            }
+        }
 
         // All row-wise phases walk the 64 columns in 8 chunks of 8 with ROLLED loops (the row lives
         // in shared memory / TMEM between passes): the tile body must stay inside the instruction
-        // cache — with one warp per scheduler an I-cache miss cannot be hidden.
+        // cache — with few warps per scheduler an I-cache miss cannot be hidden.
         // ---- fc1 + activation (pass 1: raw activations to A12, moments) ----
-        float x[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) x[k] = (valid && k < d) ? obs[gi * d + k] : 0.f;
         unsigned posmask = 0u;   // sign bits of this thread's 32 pre-activations
         float s = 0.f, sq = 0.f;
 #pragma unroll 1
-        for (int c = c0; c < c0 + 4; ++c) {
+        for (int c = c0; c < c0 + T_CH; ++c) {
             float hv[8];
             {
                 const float4 b0 = *reinterpret_cast<const float4*>(b1s + 8 * c), b1v = *reinterpret_cast<const float4*>(b1s + 8 * c + 4);
@@ -198,7 +236,8 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, uint8_t* smem, 
             *reinterpret_cast<float4*>(A12 + poff(LBO_A, row, 8 * c)) = make_float4(hv[0], hv[1], hv[2], hv[3]);
             *reinterpret_cast<float4*>(A12 + poff(LBO_A, row, 8 * c + 4)) = make_float4(hv[4], hv[5], hv[6], hv[7]);
         }
-        PAIR_SUM2(s, sq);   // also orders this tile after every thread's GH reads of the previous tile
+        __syncthreads();    // orders this tile after every thread's GH reads (N3s, DLs) of the previous tile
+        PAIR_SUM2(s, sq);
         const float mu1 = s * (1.f / H);
         const float rstd1 = 1.0f / sqrtf(fmaxf(sq * (1.f / H) - mu1 * mu1, 0.f) + LN_EPS);
 
@@ -206,7 +245,7 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, uint8_t* smem, 
         if (it > 0) mbar_wait(&bars[2], (it - 1) & 1u);
         // pass 2: normalise -> n1 row (GEMM1 A operand) and n1^T (GEMM3 B operand), TF32-rounded
 #pragma unroll 1
-        for (int c = c0; c < c0 + 4; ++c) {
+        for (int c = c0; c < c0 + T_CH; ++c) {
             const float4 r0 = *reinterpret_cast<const float4*>(A12 + poff(LBO_A, row, 8 * c));
             const float4 r1 = *reinterpret_cast<const float4*>(A12 + poff(LBO_A, row, 8 * c + 4));
             float4 v0, v1;
@@ -232,20 +271,15 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, uint8_t* smem, 
             mma_commit(&bars[0]);
         }
 
-        // row scalars while the tensor core works
-        float row_a = 0.f, row_b = 0.f, row_c = 0.f, active = 0.f;
-        if (valid) {
-            if (POLICY) { row_a = a.actions[gi]; row_b = a.old_log_probs[gi]; row_c = a.advantages[gi]; }
-            else { row_a = a.value_preds[gi]; row_b = a.returns[gi]; }
-            active = a.active_masks[gi];
-        }
+        PROF_MARK(0);
         mbar_wait(&bars[0], par);
         tcgen05_fence_after();
+        PROF_MARK(1);
 
         // ---- Z3 (TMEM) + b3f -> moments (pass 1, raw to N3s) -> n3 (pass 2, in place) + head dots ----
         float s3 = 0.f, q3 = 0.f;
 #pragma unroll 1
-        for (int c = c0; c < c0 + 4; ++c) {
+        for (int c = c0; c < c0 + T_CH; ++c) {
             float z[8];
             tmem_ld_row8(tmem_row + 8 * c, z);
 #pragma unroll
@@ -260,7 +294,7 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, uint8_t* smem, 
 #pragma unroll
         for (int j = 0; j < MAX_OUT; ++j) out[j] = 0.f;
 #pragma unroll 1
-        for (int c = c0; c < c0 + 4; ++c) {
+        for (int c = c0; c < c0 + T_CH; ++c) {
             float4 r0 = *reinterpret_cast<const float4*>(N3s + poff(LBO_A, row, 8 * c));
             float4 r1 = *reinterpret_cast<const float4*>(N3s + poff(LBO_A, row, 8 * c + 4));
             r0.x = (r0.x - mu3) * rstd3; r0.y = (r0.y - mu3) * rstd3; r0.z = (r0.z - mu3) * rstd3; r0.w = (r0.w - mu3) * rstd3;
@@ -273,11 +307,16 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, uint8_t* smem, 
                 out[j] = fmaf(r1.x, w1v.x, fmaf(r1.y, w1v.y, fmaf(r1.z, w1v.z, fmaf(r1.w, w1v.w, out[j]))));
             }
         }
-        {   // pair exchange of the partial head dots
+        {   // exchange of the partial head dots
             FOR_OUT(j) xch[(half * T_M + row) * 8 + j] = out[j];
-            __syncthreads();
-            FOR_OUT(j) out[j] += xch[((half ^ 1) * T_M + row) * 8 + j];
-            __syncthreads();
+            ROWGROUP_SYNC();
+            FOR_OUT(j) {
+                float t_ = 0.f;
+#pragma unroll
+                for (int q_ = 0; q_ < T_Q; ++q_) t_ += xch[(q_ * T_M + row) * 8 + j];
+                out[j] = t_;
+            }
+            ROWGROUP_SYNC();
         }
         // dot[j] = sum_k Whf[j][k] n3[k] (needed by the LayerNorm-3 backward); logits add the folded bias
         float dot[MAX_OUT];
@@ -343,7 +382,7 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, uint8_t* smem, 
         FOR_OUT(j) { m1 = fmaf(dl[j], swh[j], m1); m2 = fmaf(dl[j], dot[j], m2); }
         m1 *= (1.f / H); m2 *= (1.f / H);
 #pragma unroll 1
-        for (int c = c0; c < c0 + 4; ++c) {
+        for (int c = c0; c < c0 + T_CH; ++c) {
             const float4 n0 = *reinterpret_cast<const float4*>(N3s + poff(LBO_A, row, 8 * c));
             const float4 n1v = *reinterpret_cast<const float4*>(N3s + poff(LBO_A, row, 8 * c + 4));
             float g8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -374,12 +413,14 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, uint8_t* smem, 
             for (int kk = 0; kk < 8; ++kk) mma_tf32(tmem, kdesc(A12, LBO_A, kk * 8), kdesc(B2, LBO_W, kk * 8), idesc64, kk > 0);
             mma_commit(&bars[1]);
         }
+        PROF_MARK(2);
         mbar_wait(&bars[1], par);
         tcgen05_fence_after();
+        PROF_MARK(3);
         // ---- dN1 (TMEM) -> LayerNorm-1 backward -> activation backward -> dZ1^T (two passes over TMEM) ----
         float t1 = 0.f, t2 = 0.f;
 #pragma unroll 1
-        for (int c = c0; c < c0 + 4; ++c) {
+        for (int c = c0; c < c0 + T_CH; ++c) {
             float g8[8];
             tmem_ld_row8(tmem_row + 8 * c, g8);
             const uint8_t* bt = B3 + poff(LBO_B3, 8 * c, row);
@@ -390,7 +431,7 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, uint8_t* smem, 
         t1 *= (1.f / H); t2 *= (1.f / H);
         const float std1 = 1.0f / rstd1;
 #pragma unroll 1
-        for (int c = c0; c < c0 + 4; ++c) {
+        for (int c = c0; c < c0 + T_CH; ++c) {
             float g8[8];
             tmem_ld_row8(tmem_row + 8 * c, g8);
             const uint8_t* bt = B3 + poff(LBO_B3, 8 * c, row);
@@ -413,23 +454,22 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, uint8_t* smem, 
             mma_commit(&bars[2]);
         }
         // ---- GH += dL^T n3 (FFMA reduction over the tile rows, n3 read back from N3s) ----
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            const int o = tid + T_NT * q;
+        {
+            const int o = tid;
             if (o < n * H) {
                 const int j = o >> 6, k = o & 63;
-                float acc = gh_acc[q];
+                float acc = gh_acc[0], accb = dbh_acc;
                 const uint8_t* np = N3s + poff(LBO_A, 0, k);
 #pragma unroll 8
-                for (int m = 0; m < T_M; ++m) acc = fmaf(DLs[m * 8 + j], *reinterpret_cast<const float*>(np + m * 16), acc);
-                gh_acc[q] = acc;
+                for (int m = 0; m < T_M; ++m) {
+                    const float dlv = DLs[m * 8 + j];
+                    acc = fmaf(dlv, *reinterpret_cast<const float*>(np + m * 16), acc);
+                    if (k == 0) accb += dlv;     // dbh[j] = sum_m dL[m][j], carried by the k == 0 thread of row j
+                }
+                gh_acc[0] = acc; dbh_acc = accb;
             }
         }
-        if (tid < n) {
-            float acc = dbh_acc;
-            for (int m = 0; m < T_M; ++m) acc += DLs[m * 8 + tid];
-            dbh_acc = acc;
-        }
+        PROF_MARK(4);
     }
 
     // ---- flush: G (TMEM) -> partial folded gradients ----
@@ -438,11 +478,17 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, uint8_t* smem, 
     if (it > 0) {
         mbar_wait(&bars[2], (it - 1) & 1u);
         tcgen05_fence_after();
-        float v32[32];
-        tmem_ld_row32(tmem_row + 64 + 32 * half, v32);   // G columns [32*half, 32*half+32) of this row
-        if (row < 64) {
+        {   // G columns [16*half, 16*half+16) of this row
+            uint32_t r16[16];
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                         : "=r"(r16[0]), "=r"(r16[1]), "=r"(r16[2]), "=r"(r16[3]), "=r"(r16[4]), "=r"(r16[5]), "=r"(r16[6]), "=r"(r16[7]),
+                           "=r"(r16[8]), "=r"(r16[9]), "=r"(r16[10]), "=r"(r16[11]), "=r"(r16[12]), "=r"(r16[13]), "=r"(r16[14]), "=r"(r16[15])
+                         : "r"(tmem_row + 64 + 16 * half));
+            tmem_ld_wait();
+            if (row < 64) {
 #pragma unroll
-            for (int c = 0; c < 32; ++c) part[fo.g3 + row * H + 32 * half + c] = v32[c];
+                for (int c = 0; c < 16; ++c) part[fo.g3 + row * H + 16 * half + c] = __uint_as_float(r16[c]);
+            }
         }
         if (half == 0) {
             uint32_t r16[16];
@@ -464,18 +510,22 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, uint8_t* smem, 
         for (int i = tid; i < fo.gh; i += T_NT) part[i] = 0.f;   // G1, db1, G3, db3 of an idle CTA
     }
 #pragma unroll
-    for (int q = 0; q < 2; ++q) { const int o = tid + T_NT * q; if (o < n * H) part[fo.gh + o] = gh_acc[q]; }
-    if (tid < n) { part[fo.dbh + tid] = dbh_acc; part[fo.dls + tid] = 0.f; }
+    { const int o = tid; if (o < n * H) part[fo.gh + o] = gh_acc[0]; }
+    if (tid < n * H && (tid & 63) == 0) { part[fo.dbh + (tid >> 6)] = dbh_acc; part[fo.dls + (tid >> 6)] = 0.f; }
     {
         float v[3] = {loss0, loss1, loss2};
         const int lane = tid & 31;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) { const float sv = warp_sum(v[k]); if (lane == 0) red[k * 8 + warp] = sv; }
+        for (int k = 0; k < 3; ++k) { const float sv = warp_sum(v[k]); if (lane == 0) red[k * 16 + warp] = sv; }
         __syncthreads();
         if (tid < N_LOSS_TC) {
             float sv = 0.f;
-            if (tid < 3) for (int wv = 0; wv < T_NT / 32; ++wv) sv += red[tid * 8 + wv];
+            if (tid < 3) for (int wv = 0; wv < T_NT / 32; ++wv) sv += red[tid * 16 + wv];
             part[stride - N_LOSS_TC + tid] = sv;
+        }
+        if (tid == 0) {
+#pragma unroll
+            for (int i = 0; i < 5; ++i) part[stride - N_LOSS_TC + 3 + i] = (float)prof[i];
         }
     }
     tcgen05_fence_before();
@@ -504,7 +554,7 @@ int launch_ppo_fwdbwd_tc(const OrlPpoArgs& a, cudaStream_t st) {
         return ORL_ERR_UNSUPPORTED;
     }
     const size_t smem = 16 * LBO_A + 32 * LBO_A + 32 * LBO_B3 + 2 * 16 * LBO_W + 16 * LBO_A +
-                        sizeof(float) * (8 * H + H + H + MAX_OUT * H + 2 * MAX_OUT + T_M * 8 + 2 * T_M * 8 + 32) + 3 * 8 + 16 + 128;
+                        sizeof(float) * (8 * H + H + H + MAX_OUT * H + 2 * MAX_OUT + T_M * 8 + T_Q * T_M * 8 + 64) + 3 * 8 + 16 + 128;
     static bool attr_set = false;
     if (!attr_set) {
         int e = check_cuda(cudaFuncSetAttribute(ppo_fwdbwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
