@@ -70,7 +70,9 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, uint8_t* smem, 
     const float* params = POLICY ? a.policy_params : a.critic_params;
     const float* obs = POLICY ? a.policy_obs : a.critic_obs;
     const int tid = threadIdx.x, warp = tid >> 5;
-    const int row = tid & 127, half = tid >> 7, c0 = T_CH * half;   // this thread: tile row, column slice `half`, chunks [c0, c0+T_CH)
+    const int row = tid & 127, half = tid >> 7;   // this thread: tile row, column slice `half`
+    constexpr int CW = 8 * T_CH;                  // columns per thread
+    const int cb = CW * half;                     // first column of the slice
     const NetOffsets po = net_offsets(d, n);
 
     // ---- shared memory carve-up (all tensor-core tiles 128-byte aligned) ----
@@ -206,35 +208,34 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, uint8_t* smem, 
             }
         }
 
-        // All row-wise phases walk the 64 columns in 8 chunks of 8 with ROLLED loops (the row lives
-        // in shared memory / TMEM between passes): the tile body must stay inside the instruction
-        // cache — with few warps per scheduler an I-cache miss cannot be hidden.
-        // ---- fc1 + activation (pass 1: raw activations to A12, moments) ----
-        unsigned posmask = 0u;   // sign bits of this thread's 32 pre-activations
-        float s = 0.f, sq = 0.f;
-#pragma unroll 1
-        for (int c = c0; c < c0 + T_CH; ++c) {
-            float hv[8];
-            {
-                const float4 b0 = *reinterpret_cast<const float4*>(b1s + 8 * c), b1v = *reinterpret_cast<const float4*>(b1s + 8 * c + 4);
-                hv[0] = b0.x; hv[1] = b0.y; hv[2] = b0.z; hv[3] = b0.w; hv[4] = b1v.x; hv[5] = b1v.y; hv[6] = b1v.z; hv[7] = b1v.w;
-            }
+        // Row-wise phases: this thread owns CW = 16 columns [cb, cb+16) of its row and keeps them in
+        // registers across the passes (n1 until the LayerNorm-1 backward, n3 until dZ3); the row's other
+        // slices live in the 3 sibling threads, reached through the two-float exchanges.
+        // ---- fc1 + activation + LayerNorm-1 ----
+        float n1[CW];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                if (k < d) {
-                    const float4 w0 = *reinterpret_cast<const float4*>(w1t + k * H + 8 * c), w1v = *reinterpret_cast<const float4*>(w1t + k * H + 8 * c + 4);
-                    hv[0] = fmaf(x[k], w0.x, hv[0]); hv[1] = fmaf(x[k], w0.y, hv[1]); hv[2] = fmaf(x[k], w0.z, hv[2]); hv[3] = fmaf(x[k], w0.w, hv[3]);
-                    hv[4] = fmaf(x[k], w1v.x, hv[4]); hv[5] = fmaf(x[k], w1v.y, hv[5]); hv[6] = fmaf(x[k], w1v.z, hv[6]); hv[7] = fmaf(x[k], w1v.w, hv[7]);
+        for (int q4 = 0; q4 < CW; q4 += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(b1s + cb + q4);
+            n1[q4] = b.x; n1[q4 + 1] = b.y; n1[q4 + 2] = b.z; n1[q4 + 3] = b.w;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (k < d) {
+#pragma unroll
+                for (int q4 = 0; q4 < CW; q4 += 4) {
+                    const float4 wv = *reinterpret_cast<const float4*>(w1t + k * H + cb + q4);
+                    n1[q4] = fmaf(x[k], wv.x, n1[q4]); n1[q4 + 1] = fmaf(x[k], wv.y, n1[q4 + 1]);
+                    n1[q4 + 2] = fmaf(x[k], wv.z, n1[q4 + 2]); n1[q4 + 3] = fmaf(x[k], wv.w, n1[q4 + 3]);
                 }
             }
+        }
+        unsigned posmask = 0u;   // sign bits of this thread's pre-activations
+        float s = 0.f, sq = 0.f;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                if (hv[i] > 0.f) posmask |= 1u << (8 * (c - c0) + i);
-                hv[i] = act_fwd(hv[i], a.activation_id);
-                s += hv[i]; sq = fmaf(hv[i], hv[i], sq);
-            }
-            *reinterpret_cast<float4*>(A12 + poff(LBO_A, row, 8 * c)) = make_float4(hv[0], hv[1], hv[2], hv[3]);
-            *reinterpret_cast<float4*>(A12 + poff(LBO_A, row, 8 * c + 4)) = make_float4(hv[4], hv[5], hv[6], hv[7]);
+        for (int i = 0; i < CW; ++i) {
+            if (n1[i] > 0.f) posmask |= 1u << i;
+            n1[i] = act_fwd(n1[i], a.activation_id);
+            s += n1[i]; sq = fmaf(n1[i], n1[i], sq);
         }
         __syncthreads();    // orders this tile after every thread's GH reads (N3s, DLs) of the previous tile
         PAIR_SUM2(s, sq);
@@ -243,21 +244,15 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, uint8_t* smem, 
 
         // previous tile's GEMM3 must have finished reading A3 / B3
         if (it > 0) mbar_wait(&bars[2], (it - 1) & 1u);
-        // pass 2: normalise -> n1 row (GEMM1 A operand) and n1^T (GEMM3 B operand), TF32-rounded
-#pragma unroll 1
-        for (int c = c0; c < c0 + T_CH; ++c) {
-            const float4 r0 = *reinterpret_cast<const float4*>(A12 + poff(LBO_A, row, 8 * c));
-            const float4 r1 = *reinterpret_cast<const float4*>(A12 + poff(LBO_A, row, 8 * c + 4));
-            float4 v0, v1;
-            v0.x = to_tf32((r0.x - mu1) * rstd1); v0.y = to_tf32((r0.y - mu1) * rstd1); v0.z = to_tf32((r0.z - mu1) * rstd1); v0.w = to_tf32((r0.w - mu1) * rstd1);
-            v1.x = to_tf32((r1.x - mu1) * rstd1); v1.y = to_tf32((r1.y - mu1) * rstd1); v1.z = to_tf32((r1.z - mu1) * rstd1); v1.w = to_tf32((r1.w - mu1) * rstd1);
-            *reinterpret_cast<float4*>(A12 + poff(LBO_A, row, 8 * c)) = v0;
-            *reinterpret_cast<float4*>(A12 + poff(LBO_A, row, 8 * c + 4)) = v1;
-            uint8_t* bt = B3 + poff(LBO_B3, 8 * c, row);
-            *reinterpret_cast<float*>(bt) = v0.x; *reinterpret_cast<float*>(bt + 16) = v0.y;
-            *reinterpret_cast<float*>(bt + 32) = v0.z; *reinterpret_cast<float*>(bt + 48) = v0.w;
-            *reinterpret_cast<float*>(bt + 64) = v1.x; *reinterpret_cast<float*>(bt + 80) = v1.y;
-            *reinterpret_cast<float*>(bt + 96) = v1.z; *reinterpret_cast<float*>(bt + 112) = v1.w;
+        // n1 row slice (GEMM1 A operand) and n1^T (GEMM3 B operand), TF32-rounded
+#pragma unroll
+        for (int q4 = 0; q4 < CW; q4 += 4) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) n1[q4 + i] = to_tf32((n1[q4 + i] - mu1) * rstd1);
+            *reinterpret_cast<float4*>(A12 + poff(LBO_A, row, cb + q4)) = make_float4(n1[q4], n1[q4 + 1], n1[q4 + 2], n1[q4 + 3]);
+            uint8_t* bt = B3 + poff(LBO_B3, cb + q4, row);
+            *reinterpret_cast<float*>(bt) = n1[q4]; *reinterpret_cast<float*>(bt + 16) = n1[q4 + 1];
+            *reinterpret_cast<float*>(bt + 32) = n1[q4 + 2]; *reinterpret_cast<float*>(bt + 48) = n1[q4 + 3];
         }
 #pragma unroll
         for (int k = 0; k < 8; ++k) if (half == 0 && k < d) pst(B3, LBO_B3, 64 + k, row, to_tf32(x[k]));
@@ -276,35 +271,26 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, uint8_t* smem, 
         tcgen05_fence_after();
         PROF_MARK(1);
 
-        // ---- Z3 (TMEM) + b3f -> moments (pass 1, raw to N3s) -> n3 (pass 2, in place) + head dots ----
+        // ---- Z3 (TMEM) + b3f -> LayerNorm-3 -> n3 (registers; a copy goes to N3s for the GH reduction) ----
+        float n3[CW];
+        tmem_ld_row16(tmem_row + cb, n3);
         float s3 = 0.f, q3 = 0.f;
-#pragma unroll 1
-        for (int c = c0; c < c0 + T_CH; ++c) {
-            float z[8];
-            tmem_ld_row8(tmem_row + 8 * c, z);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { z[i] += b3f[8 * c + i]; s3 += z[i]; q3 = fmaf(z[i], z[i], q3); }
-            *reinterpret_cast<float4*>(N3s + poff(LBO_A, row, 8 * c)) = make_float4(z[0], z[1], z[2], z[3]);
-            *reinterpret_cast<float4*>(N3s + poff(LBO_A, row, 8 * c + 4)) = make_float4(z[4], z[5], z[6], z[7]);
-        }
+        for (int i = 0; i < CW; ++i) { n3[i] += b3f[cb + i]; s3 += n3[i]; q3 = fmaf(n3[i], n3[i], q3); }
         PAIR_SUM2(s3, q3);
         const float mu3 = s3 * (1.f / H);
         const float rstd3 = 1.0f / sqrtf(fmaxf(q3 * (1.f / H) - mu3 * mu3, 0.f) + LN_EPS);
         float out[MAX_OUT];
 #pragma unroll
         for (int j = 0; j < MAX_OUT; ++j) out[j] = 0.f;
-#pragma unroll 1
-        for (int c = c0; c < c0 + T_CH; ++c) {
-            float4 r0 = *reinterpret_cast<const float4*>(N3s + poff(LBO_A, row, 8 * c));
-            float4 r1 = *reinterpret_cast<const float4*>(N3s + poff(LBO_A, row, 8 * c + 4));
-            r0.x = (r0.x - mu3) * rstd3; r0.y = (r0.y - mu3) * rstd3; r0.z = (r0.z - mu3) * rstd3; r0.w = (r0.w - mu3) * rstd3;
-            r1.x = (r1.x - mu3) * rstd3; r1.y = (r1.y - mu3) * rstd3; r1.z = (r1.z - mu3) * rstd3; r1.w = (r1.w - mu3) * rstd3;
-            *reinterpret_cast<float4*>(N3s + poff(LBO_A, row, 8 * c)) = r0;
-            *reinterpret_cast<float4*>(N3s + poff(LBO_A, row, 8 * c + 4)) = r1;
+#pragma unroll
+        for (int q4 = 0; q4 < CW; q4 += 4) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) n3[q4 + i] = (n3[q4 + i] - mu3) * rstd3;
+            *reinterpret_cast<float4*>(N3s + poff(LBO_A, row, cb + q4)) = make_float4(n3[q4], n3[q4 + 1], n3[q4 + 2], n3[q4 + 3]);
             FOR_OUT(j) {
-                const float4 w0 = *reinterpret_cast<const float4*>(whf + j * H + 8 * c), w1v = *reinterpret_cast<const float4*>(whf + j * H + 8 * c + 4);
-                out[j] = fmaf(r0.x, w0.x, fmaf(r0.y, w0.y, fmaf(r0.z, w0.z, fmaf(r0.w, w0.w, out[j]))));
-                out[j] = fmaf(r1.x, w1v.x, fmaf(r1.y, w1v.y, fmaf(r1.z, w1v.z, fmaf(r1.w, w1v.w, out[j]))));
+                const float4 wv = *reinterpret_cast<const float4*>(whf + j * H + cb + q4);
+                out[j] = fmaf(n3[q4], wv.x, fmaf(n3[q4 + 1], wv.y, fmaf(n3[q4 + 2], wv.z, fmaf(n3[q4 + 3], wv.w, out[j]))));
             }
         }
         {   // exchange of the partial head dots
@@ -381,24 +367,19 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, uint8_t* smem, 
         float m1 = 0.f, m2 = 0.f;
         FOR_OUT(j) { m1 = fmaf(dl[j], swh[j], m1); m2 = fmaf(dl[j], dot[j], m2); }
         m1 *= (1.f / H); m2 *= (1.f / H);
-#pragma unroll 1
-        for (int c = c0; c < c0 + T_CH; ++c) {
-            const float4 n0 = *reinterpret_cast<const float4*>(N3s + poff(LBO_A, row, 8 * c));
-            const float4 n1v = *reinterpret_cast<const float4*>(N3s + poff(LBO_A, row, 8 * c + 4));
-            float g8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int q4 = 0; q4 < CW; q4 += 4) {
+            float g4[4] = {0.f, 0.f, 0.f, 0.f};
             FOR_OUT(j) {
-                const float4 w0 = *reinterpret_cast<const float4*>(whf + j * H + 8 * c), w1v = *reinterpret_cast<const float4*>(whf + j * H + 8 * c + 4);
-                g8[0] = fmaf(dl[j], w0.x, g8[0]); g8[1] = fmaf(dl[j], w0.y, g8[1]); g8[2] = fmaf(dl[j], w0.z, g8[2]); g8[3] = fmaf(dl[j], w0.w, g8[3]);
-                g8[4] = fmaf(dl[j], w1v.x, g8[4]); g8[5] = fmaf(dl[j], w1v.y, g8[5]); g8[6] = fmaf(dl[j], w1v.z, g8[6]); g8[7] = fmaf(dl[j], w1v.w, g8[7]);
+                const float4 wv = *reinterpret_cast<const float4*>(whf + j * H + cb + q4);
+                g4[0] = fmaf(dl[j], wv.x, g4[0]); g4[1] = fmaf(dl[j], wv.y, g4[1]); g4[2] = fmaf(dl[j], wv.z, g4[2]); g4[3] = fmaf(dl[j], wv.w, g4[3]);
             }
-            const float nn[8] = {n0.x, n0.y, n0.z, n0.w, n1v.x, n1v.y, n1v.z, n1v.w};
 #pragma unroll
-            for (int i = 0; i < 8; ++i) g8[i] = to_tf32(rstd3 * (g8[i] - m1 - nn[i] * m2));
-            *reinterpret_cast<float4*>(A12 + poff(LBO_A, row, 8 * c)) = make_float4(g8[0], g8[1], g8[2], g8[3]);       // dZ3 row
-            *reinterpret_cast<float4*>(A12 + poff(LBO_A, row, 8 * c + 4)) = make_float4(g8[4], g8[5], g8[6], g8[7]);
-            uint8_t* at = A3 + poff(LBO_A, 8 * c, row);                                                                // dZ3^T
+            for (int i = 0; i < 4; ++i) g4[i] = to_tf32(rstd3 * (g4[i] - m1 - n3[q4 + i] * m2));
+            *reinterpret_cast<float4*>(A12 + poff(LBO_A, row, cb + q4)) = make_float4(g4[0], g4[1], g4[2], g4[3]);   // dZ3 row
+            uint8_t* at = A3 + poff(LBO_A, cb + q4, row);                                                              // dZ3^T
 #pragma unroll
-            for (int i = 0; i < 8; ++i) *reinterpret_cast<float*>(at + 16 * i) = g8[i];
+            for (int i = 0; i < 4; ++i) *reinterpret_cast<float*>(at + 16 * i) = g4[i];
         }
         if (half == 0) {
             *reinterpret_cast<float4*>(DLs + row * 8) = make_float4(dl[0], dl[1], dl[2], dl[3]);
@@ -417,31 +398,22 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, uint8_t* smem, 
         mbar_wait(&bars[1], par);
         tcgen05_fence_after();
         PROF_MARK(3);
-        // ---- dN1 (TMEM) -> LayerNorm-1 backward -> activation backward -> dZ1^T (two passes over TMEM) ----
-        float t1 = 0.f, t2 = 0.f;
-#pragma unroll 1
-        for (int c = c0; c < c0 + T_CH; ++c) {
-            float g8[8];
-            tmem_ld_row8(tmem_row + 8 * c, g8);
-            const uint8_t* bt = B3 + poff(LBO_B3, 8 * c, row);
+        // ---- dN1 (TMEM) -> LayerNorm-1 backward -> activation backward -> dZ1^T ----
+        {
+            float g[CW];
+            tmem_ld_row16(tmem_row + cb, g);
+            float t1 = 0.f, t2 = 0.f;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { t1 += g8[i]; t2 = fmaf(g8[i], *reinterpret_cast<const float*>(bt + 16 * i), t2); }
-        }
-        PAIR_SUM2(t1, t2);
-        t1 *= (1.f / H); t2 *= (1.f / H);
-        const float std1 = 1.0f / rstd1;
-#pragma unroll 1
-        for (int c = c0; c < c0 + T_CH; ++c) {
-            float g8[8];
-            tmem_ld_row8(tmem_row + 8 * c, g8);
-            const uint8_t* bt = B3 + poff(LBO_B3, 8 * c, row);
-            uint8_t* at = A3 + poff(LBO_A, 64 + 8 * c, row);
+            for (int i = 0; i < CW; ++i) { t1 += g[i]; t2 = fmaf(g[i], n1[i], t2); }
+            PAIR_SUM2(t1, t2);
+            t1 *= (1.f / H); t2 *= (1.f / H);
+            const float std1 = 1.0f / rstd1;
+            uint8_t* at = A3 + poff(LBO_A, 64 + cb, row);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float n1k = *reinterpret_cast<const float*>(bt + 16 * i);   // own column of n1^T
-                const float da = rstd1 * (g8[i] - t1 - n1k * t2);
-                const float aval = fmaf(n1k, std1, mu1);                          // activation output
-                *reinterpret_cast<float*>(at + 16 * i) = to_tf32(da * act_bwd(aval, (posmask >> (8 * (c - c0) + i)) & 1u, a.activation_id));
+            for (int i = 0; i < CW; ++i) {
+                const float da = rstd1 * (g[i] - t1 - n1[i] * t2);
+                const float aval = fmaf(n1[i], std1, mu1);                          // activation output
+                *reinterpret_cast<float*>(at + 16 * i) = to_tf32(da * act_bwd(aval, (posmask >> i) & 1u, a.activation_id));
             }
         }
         fence_proxy_async();
