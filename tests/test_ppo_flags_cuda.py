@@ -164,3 +164,55 @@ def test_save_load_roundtrip_and_lr_decay(cuda, tmp_path):
         assert torch.equal(v, ref[k]), k
     a2, _ = agent2.act(obs, deterministic=True)
     assert np.array_equal(a1, a2)
+
+
+@pytest.mark.parametrize("n_actions", [2, 3, 5, 8])
+def test_tf32_kernel_head_width_templates(cuda, n_actions):
+    """The tcgen05 kernel is instantiated for head widths 2, 5 and a generic (runtime n <= 8) variant:
+    each must agree with the fp32 kernel on the same synthetic minibatch (incl. a partial last tile)."""
+    import torch
+
+    from openrl_b200 import lib, spaces
+    from openrl_b200.algorithms.ppo import PPOAlgorithm
+    from openrl_b200.buffers import NormalReplayBuffer
+    from openrl_b200.configs.config import create_config_parser
+    from openrl_b200.modules.common import PPONet
+
+    class Env:
+        agent_num, parallel_env_num = 1, 37
+        observation_space, action_space = spaces.Box(-5, 5, (6,), np.float32), spaces.Discrete(n_actions)
+
+        def reset(self, seed=None):
+            return np.zeros((37, 1, 6), np.float32)
+
+    T, N = 23, 37
+    res = []
+    for tf32 in (False, True):
+        cfg = create_config_parser().parse_args(["--seed", "4", "--episode_length", str(T), "--parity_mode", "true"])
+        cfg.quiet = True
+        net = PPONet(Env(), cfg=cfg, device="cuda:0")
+        cfg.n_rollout_threads = N
+        trainer = PPOAlgorithm(cfg, net.module, agent_num=1, device=net.device)
+        if tf32:
+            trainer.flags |= lib.PPO_TF32
+        buf = NormalReplayBuffer(cfg, 1, Env.observation_space, Env.action_space, device=net.device)
+        b = buf.data
+        g = torch.Generator().manual_seed(5)
+        b.policy_obs.copy_(torch.randn(b.policy_obs.shape, generator=g))
+        b.actions.copy_(torch.randint(0, n_actions, b.actions.shape, generator=g).float())
+        b.action_log_probs.copy_(-np.log(n_actions) + 0.1 * torch.randn(b.action_log_probs.shape, generator=g))
+        b.rewards.copy_(torch.randn(b.rewards.shape, generator=g))
+        b.value_preds.copy_(0.3 * torch.randn(b.value_preds.shape, generator=g))
+        b.masks.copy_((torch.rand(b.masks.shape, generator=g) > 0.1).float())
+        b.active_masks.copy_((torch.rand(b.active_masks.shape, generator=g) > 0.2).float())
+        vn = net.module.get_critic_value_normalizer()
+        b.compute_returns(b.value_preds[-1].clone(), vn)
+        trainer.lrs.copy_(torch.tensor([cfg.lr, cfg.critic_lr]))
+        trainer.train_info.zero_()
+        trainer.ppo_update(b, T * N, None, 0, mb_stats=b.gae_stats[5:8])
+        torch.cuda.synchronize()
+        res.append((trainer.train_info.cpu().numpy().copy(), trainer.grads.cpu().numpy().copy()))
+    np.testing.assert_allclose(res[1][0], res[0][0], rtol=3e-3, atol=2e-5)
+    for net_i in range(2):
+        g32, gtc = res[0][1][net_i], res[1][1][net_i]
+        assert np.linalg.norm(gtc - g32) <= 1e-2 * np.linalg.norm(g32), (n_actions, net_i)
