@@ -46,3 +46,38 @@ def test_oracle_reproduces_reference_trace(tag, env_id):
         for k, v in _params(tr).items():
             np.testing.assert_allclose(v, d[f"it{it}/params/{k}"], rtol=1e-4, atol=1e-6, err_msg=k)
         np.testing.assert_allclose(tr.vn.state(), d[f"it{it}/vn_after_update"], rtol=1e-6)
+
+
+@pytest.mark.parametrize("tag", ["mpe_mlp", "mpe_gru"])
+def test_multi_agent_oracle_reproduces_reference_trace(tag):
+    """MAPPO on simple_spread (3 agents, shared nets; feed-forward and GRU + chunked BPTT with
+    data_chunk_length 2) vs the unmodified reference."""
+    from oracle import loop_ma
+
+    d = np.load(os.path.join(GOLDEN, f"trace_{tag}.npz"), allow_pickle=True)
+    cfg = loop.cfg_from_flags(str(d["meta/flags"]))
+    tr = loop_ma.MATrainer(cfg, "simple_spread", int(d["meta/env_num"]))
+    for mk, prm in (("policy", tr.pol), ("critic", tr.cri)):
+        for k, v in prm.items():
+            np.testing.assert_allclose(v.detach().numpy(), d[f"init/{mk}.{k}"], rtol=0, atol=1e-6, err_msg=k)
+            v.data.copy_(torch.from_numpy(d[f"init/{mk}.{k}"]))
+    for it in range(int(d["meta/iters"])):
+        tr.rollout()
+        b = tr.buf
+        assert np.array_equal(b.actions, d[f"it{it}/actions"])
+        assert np.array_equal(b.policy_obs, d[f"it{it}/policy_obs"])
+        assert np.array_equal(b.rewards, d[f"it{it}/rewards"])
+        assert np.array_equal(b.masks, d[f"it{it}/masks"])
+        if cfg.use_recurrent_policy:
+            np.testing.assert_allclose(b.rnn_states, d[f"it{it}/rnn_states"], rtol=0, atol=1e-5)
+            np.testing.assert_allclose(b.rnn_states_critic, d[f"it{it}/rnn_states_critic"], rtol=0, atol=1e-5)
+        tr.compute_returns()
+        np.testing.assert_allclose(b.value_preds, d[f"it{it}/value_preds"], rtol=0, atol=1e-5)
+        updates, perms = tr.train()
+        assert np.array_equal(perms, d[f"it{it}/perms"])
+        np.testing.assert_allclose(tr.last_adv, d[f"it{it}/advantages"], rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(updates, d[f"it{it}/updates"], rtol=2e-4, atol=2e-6)
+        tr.after_update()
+        for mk, prm in (("policy", tr.pol), ("critic", tr.cri)):
+            for k, v in prm.items():
+                np.testing.assert_allclose(v.detach().numpy(), d[f"it{it}/params/{mk}.{k}"], rtol=2e-4, atol=2e-6, err_msg=k)
