@@ -269,6 +269,61 @@ int orl_ppo_apply(const OrlPpoArgs* args, void* stream);
 int orl_minibatch_stats(const int64_t* indices, int64_t batch_rows, const float* returns,
                         const float* active_masks, double* mb_stats_out, void* stream);
 
+
+/* ---- recurrent (GRU) policy / value networks --------------------------------------------
+ * Replace, for cfg.use_recurrent_policy, RNNLayer (openrl/modules/networks/utils/rnn.py:5-99) inside
+ * PolicyNetwork / ValueNetwork, the recurrent half of OnPolicyDriver.act / add2buffer
+ * (onpolicy_driver.py:80-152,236-279), ReplayData.recurrent_generator (replay_data.py:1062-1258:
+ * chunks of L = data_chunk_length over the agent-major / time-minor flattening f = (n*A + a)*T + t,
+ * initial hidden state rnn_states[f = c*L], chunks ignore trajectory boundaries) and the BPTT part of
+ * PPOAlgorithm.ppo_update.  First, correctness-first implementation: one thread per row (rollout,
+ * critic) or per chunk (update) running the sequential core of csrc/orl_rnn_core.h (verified on the
+ * CPU against the oracle); parameter gradients are reductions of a per-row tape, dW = sum P^T Q.
+ * Parameter layout of a recurrent net (reference state_dict order):
+ *   W1[64][d] b1 g1 be1 | W3[64][64] b3 g3 be3 | Wih[192][64] Whh[192][64] bih bhh | g_rnn be_rnn | Wh[n][64] bh[n]
+ */
+typedef struct OrlRnnArgs {
+    int32_t env_kind, n_envs, n_agents, episode_length;   /* N, A, T; rows B = N*A */
+    int32_t t_begin, t_end;
+    int32_t obs_dim, critic_obs_dim, n_actions, activation_id;
+    int32_t deterministic, chunk_length;                  /* L = cfg.data_chunk_length (<= 4) */
+    int32_t flags;                                        /* ORL_PPO_* */
+    int32_t env_table_len;
+    int64_t n_chunks;                                     /* chunks in this minibatch */
+    const int64_t* chunk_ids;                             /* (n_chunks) chunk indices c (torch.randperm slice) */
+    float* policy_params; float* critic_params;
+    float* policy_obs; float* critic_obs;                 /* (T+1, B, d) / (T+1, B, dc) */
+    float* rnn_states; float* rnn_states_critic;          /* (T+1, B, 64) */
+    float* actions; float* action_log_probs; float* rewards;
+    float* masks; float* active_masks;
+    float* value_preds; const float* returns; const float* advantages;
+    const float* exp_noise;                               /* (T, B, n) or NULL */
+    uint64_t rng_seed; uint64_t rng_step_base; uint64_t* rng_counter;
+    double* env_f64; uint64_t* env_u64; int32_t* env_i32; const int32_t* env_table;
+    float* ep_return; int32_t* ep_length; double* episode_stats;
+    const double* gae_stats; const double* mb_stats; float* vn_state;
+    float* tape;                                          /* workspace: (n_chunks*L, orl_rnn_tape_width()) floats, one net at a time */
+    float* grads;                                         /* (2, grads_stride) true gradients, policy then critic */
+    int32_t grads_stride; int32_t reserved1;
+    float* loss_acc;                                      /* (8) zeroed by orl_rnn_fwdbwd: policy_loss, entropy, ratio, value_loss sums */
+    float* policy_adam_m; float* policy_adam_v; float* critic_adam_m; float* critic_adam_v;
+    int32_t* adam_steps; const float* lrs;
+    float clip_param, entropy_coef, value_loss_coef, huber_delta, max_grad_norm;
+    float adam_beta1, adam_beta2, adam_eps, weight_decay, dual_clip_coeff;
+    double vn_beta;
+    float* train_info;
+} OrlRnnArgs;
+int orl_rnn_param_count(int obs_dim, int n_out);
+int orl_rnn_tape_width(void);
+/* policy GRU rollout for steps [t_begin, t_end) fused with the device env (simple_spread, CartPole, GridWorld) */
+int orl_rnn_rollout(const OrlRnnArgs* args, void* stream);
+/* recurrent critic over slots 0..T: value_preds[t] and rnn_states_critic[t+1] */
+int orl_rnn_critic(const OrlRnnArgs* args, void* stream);
+/* chunked BPTT forward + loss + backward of both nets over the minibatch chunks -> grads, loss_acc */
+int orl_rnn_fwdbwd(const OrlRnnArgs* args, void* stream);
+/* per-net global-norm clip + Adam on `grads`; ValueNorm commit; train_info accumulation */
+int orl_rnn_apply(const OrlRnnArgs* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

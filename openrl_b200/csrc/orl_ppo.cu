@@ -13,7 +13,7 @@
 // Arithmetic per row (d=4, n=2, both nets): ~53 kFLOP; bytes per row: ~60 B  => fp32-pipe bound.
 #include <algorithm>
 
-#include "orl_mlp.cuh"
+#include "orl_loss.cuh"
 
 namespace {
 using namespace orl;
@@ -98,48 +98,6 @@ __device__ __forceinline__ void wgrad_flush(float* __restrict__ scratch, const W
     }
 }
 
-struct AdvNorm { float m0, s0, m1, s1; bool two_stage; };
-__device__ __forceinline__ AdvNorm make_adv_norm(const double* __restrict__ gs, bool use_adv_normalize) {
-    // ppo.py:402-409
-    AdvNorm r;
-    const double n_all = gs[ORL_GS_COUNT], n_act = gs[ORL_GS_ACT_COUNT];
-    const double mean_all = gs[ORL_GS_ADV_SUM] / n_all;
-    const double var_all = fmax(gs[ORL_GS_ADV_SQSUM] / n_all - mean_all * mean_all, 0.0);
-    double mean_act = gs[ORL_GS_ADV_ACT_SUM] / n_act;
-    const double var_act = fmax(gs[ORL_GS_ADV_ACT_SQSUM] / n_act - mean_act * mean_act, 0.0);
-    double std_act = sqrt(var_act);
-    r.two_stage = use_adv_normalize;
-    r.m0 = 0.f; r.s0 = 1.f;
-    if (use_adv_normalize) {
-        const double s0 = (double)((float)sqrt(var_all)) + 1e-5;
-        r.m0 = (float)mean_all;
-        r.s0 = (float)s0;
-        mean_act = (mean_act - mean_all) / s0;
-        std_act = std_act / s0;
-    }
-    r.m1 = (float)mean_act;
-    r.s1 = (float)((double)((float)std_act) + 1e-5);
-    return r;
-}
-__device__ __forceinline__ float apply_adv_norm(const AdvNorm& r, float a) {
-    if (r.two_stage) a = (a - r.m0) / r.s0;
-    return (a - r.m1) / r.s1;
-}
-
-// ValueNorm.update (valuenorm.py:59-76) applied to the old state with this minibatch's moments.
-__device__ __forceinline__ void vn_updated(const float* __restrict__ vn_state, const double* __restrict__ mb_stats,
-                                           double batch_rows, double beta_d, float (&out)[3]) {
-    const float bm = (float)(mb_stats[0] / batch_rows);
-    const float bsq = (float)(mb_stats[1] / batch_rows);
-    const float beta = (float)beta_d;
-    const float omw = (float)(1.0 - beta_d);
-    out[0] = __fadd_rn(__fmul_rn(vn_state[0], beta), __fmul_rn(bm, omw));
-    out[1] = __fadd_rn(__fmul_rn(vn_state[1], beta), __fmul_rn(bsq, omw));
-    out[2] = __fadd_rn(__fmul_rn(vn_state[2], beta), __fmul_rn(1.0f, omw));
-}
-
-__device__ __forceinline__ float huber(float e, float d) { return fabsf(e) <= d ? 0.5f * e * e : d * (fabsf(e) - 0.5f * d); }
-__device__ __forceinline__ float huber_grad(float e, float d) { return fabsf(e) <= d ? e : (e > 0.f ? d : -d); }
 
 template <bool POLICY>
 __device__ __forceinline__ void ppo_net_pass(const OrlPpoArgs& a, float* smem, int cta, int G) {

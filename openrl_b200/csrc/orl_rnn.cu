@@ -1,0 +1,462 @@
+// Recurrent (GRU) policy / value networks: rollout, critic pass, chunked-BPTT update, optimizer.
+//
+// Replaces, for cfg.use_recurrent_policy:
+//   RNNLayer.forward                      openrl/modules/networks/utils/rnn.py:39-99
+//   OnPolicyDriver.act / add2buffer       openrl/drivers/onpolicy_driver.py:80-152,236-279 (rnn-state carry,
+//                                         zeroing on dones_env)
+//   ReplayData.recurrent_generator        openrl/buffers/replay_data.py:1062-1258 (chunks of L over f=(n*A+a)*T+t)
+//   PPOAlgorithm.ppo_update (BPTT part)   openrl/algorithms/ppo.py:46-458
+//
+// Correctness-first design (DESIGN.md "recurrent path"): every kernel is a thin wrapper that runs the
+// sequential core of orl_rnn_core.h — the same source the CPU test checks against the torch oracle — with one
+// thread per env (rollout), per row (critic) or per chunk (update).  Parameter gradients are reductions of the
+// per-row tape, dW = sum_rows P^T Q, done by a small staged-GEMM kernel with float atomics into the true-layout
+// gradient buffer.  This path is latency/occupancy bound by construction; it exists so that recurrent configs
+// run on the device with reference numerics, not to set a speed record (the feed-forward path is the fast one).
+#include <algorithm>
+
+#include "orl_envstep.cuh"
+#include "orl_loss.cuh"
+#include "orl_rnn_core.h"
+
+namespace {
+using namespace orl;
+namespace rc = orl_rnn;
+
+static_assert(rc::MAXN == MAX_OUT, "head width limits must agree");
+constexpr int LMAX = 4;      // data_chunk_length limit (StepSave is 2.6 KB per step of per-thread local memory)
+constexpr int RNN_NT = 64;   // threads per CTA of the sequential kernels
+
+__device__ __forceinline__ int pick_action(const OrlRnnArgs& a, const float (&pr)[MAX_OUT], int n, size_t grow, int row,
+                                           int t, uint64_t rng_base) {
+    if (a.deterministic) {
+        int act = 0;
+#pragma unroll
+        for (int j = 1; j < MAX_OUT; ++j) if (j < n && pr[j] > pr[act]) act = j;
+        return act;
+    }
+    float q[MAX_OUT];
+    if (a.exp_noise) {
+#pragma unroll
+        for (int j = 0; j < MAX_OUT; ++j) q[j] = (j < n) ? a.exp_noise[grow * n + j] : 1.f;
+    } else {
+        const uint64_t step = rng_base + (uint64_t)t;
+        const uint2 key = make_uint2((uint32_t)a.rng_seed, (uint32_t)(a.rng_seed >> 32));
+        const uint4 r0 = philox4x32_10(make_uint4((uint32_t)step, (uint32_t)(step >> 32), (uint32_t)row, 0u), key);
+        const uint4 r1 = philox4x32_10(make_uint4((uint32_t)step, (uint32_t)(step >> 32), (uint32_t)row, 1u), key);
+        const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+        for (int j = 0; j < MAX_OUT; ++j) q[j] = -logf(u32_to_unit_open(rr[j]));
+    }
+    return sample_categorical(pr, n, q);
+}
+
+// ---- rollout: one thread per env; policy GRU step for each agent row, then env.step ----
+template <int ENV>
+__global__ void __launch_bounds__(RNN_NT) rnn_rollout_kernel(const OrlRnnArgs a) {
+    constexpr int A = ENV == ORL_ENV_MPE_SPREAD ? 3 : 1;
+    constexpr int D = ENV == ORL_ENV_MPE_SPREAD ? 18 : 4;
+    const int N = a.n_envs, B = N * A, n = a.n_actions;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= N) return;
+    const rc::Offsets o = rc::rnn_offsets(D, n);
+    const float* P = a.policy_params;
+    EnvPtrs E{a.env_f64, a.env_u64, a.env_i32, a.env_table, a.env_table_len, a.rng_seed, a.ep_return, a.ep_length, a.episode_stats};
+    const uint64_t rng_base = a.rng_step_base + (a.rng_counter ? *a.rng_counter : 0ull);
+
+    for (int t = a.t_begin; t < a.t_end; ++t) {
+        int acts[A];
+        for (int ag = 0; ag < A; ++ag) {
+            const int row = e * A + ag;
+            const size_t grow = (size_t)t * B + row;
+            float x[D], h[rc::H], hn[rc::H], logit[MAX_OUT];
+            for (int k = 0; k < D; ++k) x[k] = a.policy_obs[grow * D + k];
+            for (int j = 0; j < rc::H; ++j) h[j] = a.rnn_states[grow * rc::H + j];
+            rc::rnn_step_forward(P, o, a.activation_id, x, h, a.masks[grow], hn, logit, nullptr, nullptr);
+            // tentative next state; zeroed below if the env finishes (onpolicy_driver.py:262-269)
+            for (int j = 0; j < rc::H; ++j) a.rnn_states[((size_t)(t + 1) * B + row) * rc::H + j] = hn[j];
+#pragma unroll
+            for (int j = 0; j < MAX_OUT; ++j) if (j >= n) logit[j] = 0.f;
+            float nl[MAX_OUT], pr[MAX_OUT];
+            log_softmax_n(logit, n, nl, pr);
+            const int act = pick_action(a, pr, n, grow, row, t, rng_base);
+            float lp = nl[0];
+#pragma unroll
+            for (int j = 1; j < MAX_OUT; ++j) if (j == act) lp = nl[j];
+            a.actions[grow] = (float)act;
+            a.action_log_probs[grow] = lp;
+            acts[ag] = act;
+        }
+        bool done; float reward;
+        if constexpr (ENV == ORL_ENV_MPE_SPREAD) {
+            float ob[3][18];
+            const int acts3[3] = {acts[0], acts[1], acts[2]};
+            env_step_mpe(E, e, N, acts3, ob, reward, done);
+            const size_t r1 = (size_t)(t + 1) * B + (size_t)e * 3;
+            for (int ag = 0; ag < 3; ++ag) {
+                for (int k = 0; k < 18; ++k) {
+                    a.policy_obs[(r1 + ag) * 18 + k] = ob[ag][k];
+                    for (int dst = 0; dst < 3; ++dst) a.critic_obs[(r1 + dst) * 54 + ag * 18 + k] = ob[ag][k];
+                }
+            }
+        } else {
+            float ob[4], fin[4];
+            env_step_single(E, ENV, e, N, acts[0], ob, reward, done, fin);
+            const size_t o1 = (size_t)(t + 1) * B + e;
+            for (int k = 0; k < 4; ++k) {
+                a.policy_obs[o1 * 4 + k] = ob[k];
+                if (a.critic_obs != a.policy_obs) a.critic_obs[o1 * 4 + k] = ob[k];
+            }
+        }
+        for (int ag = 0; ag < A; ++ag) {
+            const size_t r1 = (size_t)(t + 1) * B + (size_t)e * A + ag;
+            a.rewards[(size_t)t * B + (size_t)e * A + ag] = reward;
+            a.masks[r1] = done ? 0.f : 1.f;
+            a.active_masks[r1] = 1.f;
+            if (done) for (int j = 0; j < rc::H; ++j) a.rnn_states[r1 * rc::H + j] = 0.f;
+        }
+    }
+}
+
+// ---- recurrent critic over all T+1 slots: one thread per row ----
+__global__ void __launch_bounds__(RNN_NT) rnn_critic_kernel(const OrlRnnArgs a) {
+    const int B = a.n_envs * a.n_agents, T = a.episode_length, dc = a.critic_obs_dim;
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= B) return;
+    const rc::Offsets o = rc::rnn_offsets(dc, 1);
+    const float* P = a.critic_params;
+    float h[rc::H], hn[rc::H], x[rc::MAXD], out[MAX_OUT];
+    for (int j = 0; j < rc::H; ++j) h[j] = a.rnn_states_critic[(size_t)row * rc::H + j];
+    for (int t = 0; t <= T; ++t) {
+        const size_t grow = (size_t)t * B + row;
+        for (int k = 0; k < dc; ++k) x[k] = a.critic_obs[grow * dc + k];
+        rc::rnn_step_forward(P, o, a.activation_id, x, h, a.masks[grow], hn, out, nullptr, nullptr);
+        a.value_preds[grow] = out[0];
+        if (t < T) {
+            const float keep = a.masks[grow + B] == 0.f ? 0.f : 1.f;   // rnn_states_critic[dones_env] = 0
+            for (int j = 0; j < rc::H; ++j) { h[j] = hn[j] * keep; a.rnn_states_critic[(grow + B) * rc::H + j] = h[j]; }
+        }
+    }
+}
+
+// ---- update: one thread per chunk; L forward steps with saves, per-step loss, L backward steps ----
+template <bool POLICY>
+__global__ void __launch_bounds__(RNN_NT) rnn_chunk_kernel(const OrlRnnArgs a) {
+    const int B = a.n_envs * a.n_agents, T = a.episode_length, L = a.chunk_length;
+    const int d = POLICY ? a.obs_dim : a.critic_obs_dim, n = POLICY ? a.n_actions : 1;
+    const float* P = POLICY ? a.policy_params : a.critic_params;
+    const float* obs = POLICY ? a.policy_obs : a.critic_obs;
+    const float* states = POLICY ? a.rnn_states : a.rnn_states_critic;
+    const rc::Offsets o = rc::rnn_offsets(d, n);
+    const long long cpos = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    float loss0 = 0.f, loss1 = 0.f, loss2 = 0.f;
+
+    if (cpos < a.n_chunks) {
+        const double rows_d = (double)a.n_chunks * L;
+        const float inv_rows = (float)(1.0 / rows_d);
+        const float inv_act = (float)(1.0 / a.mb_stats[2]);
+        const bool pol_masks = a.flags & ORL_PPO_POLICY_ACTIVE_MASKS, val_masks = a.flags & ORL_PPO_VALUE_ACTIVE_MASKS;
+        AdvNorm advn;
+        float vn_mean = 0.f, vn_std = 1.f;
+        if (POLICY) advn = make_adv_norm(a.gae_stats, a.flags & ORL_PPO_ADV_NORMALIZE);
+        else if (a.flags & ORL_PPO_VALUENORM) {
+            float st[3];
+            vn_updated(a.vn_state, a.mb_stats, rows_d, a.vn_beta, st);
+            const VnScalars s = vn_mean_std(st);
+            vn_mean = s.mean; vn_std = s.std;
+        }
+        const long long f0 = a.chunk_ids[cpos] * (long long)L;
+        rc::StepSave sv[LMAX];
+        float msk[LMAX], dl[LMAX][MAX_OUT];
+        float h[rc::H], h2[rc::H], x[rc::MAXD];
+        {
+            const long long row0 = f0 / T, t0 = f0 % T;
+            for (int j = 0; j < rc::H; ++j) h[j] = states[((size_t)t0 * B + row0) * rc::H + j];
+        }
+        for (int l = 0; l < L; ++l) {
+            const long long f = f0 + l, row = f / T, t = f % T;
+            const size_t bi = (size_t)t * B + row;
+            for (int k = 0; k < d; ++k) x[k] = obs[bi * d + k];
+            msk[l] = a.masks[bi];
+            float out[MAX_OUT];
+            float* tape = a.tape + ((size_t)cpos * L + l) * rc::TAPE;
+            rc::rnn_step_forward(P, o, a.activation_id, x, h, msk[l], h2, out, &sv[l], tape);
+            for (int j = 0; j < rc::H; ++j) h[j] = h2[j];
+#pragma unroll
+            for (int j = 0; j < MAX_OUT; ++j) dl[l][j] = 0.f;
+            const float active = a.active_masks[bi];
+            if (POLICY) {
+#pragma unroll
+                for (int j = 0; j < MAX_OUT; ++j) if (j >= n) out[j] = 0.f;
+                float nl[MAX_OUT], pr[MAX_OUT];
+                log_softmax_n(out, n, nl, pr);
+                const int act = (int)a.actions[bi];
+                float lp = nl[0];
+#pragma unroll
+                for (int j = 1; j < MAX_OUT; ++j) if (j == act) lp = nl[j];
+                const float adv = apply_adv_norm(advn, a.advantages[bi]);
+                const PgTerm pg = pg_term(lp, a.action_log_probs[bi], adv, a.clip_param, a.flags, a.dual_clip_coeff);
+                const float wrow = pol_masks ? active * inv_act : inv_rows;
+                float ent = 0.f;
+#pragma unroll
+                for (int j = 0; j < MAX_OUT; ++j) if (j < n) ent -= pr[j] * nl[j];
+                loss0 += pg.loss * wrow; loss1 += ent * wrow; loss2 += pg.ratio;
+                const float dlp = pg.dlogp * wrow, went = a.entropy_coef * wrow;
+#pragma unroll
+                for (int j = 0; j < MAX_OUT; ++j)
+                    if (j < n) dl[l][j] = dlp * ((j == act ? 1.f : 0.f) - pr[j]) + went * pr[j] * (nl[j] + ent);
+            } else {
+                const float ret = a.returns[bi];
+                const float target = (a.flags & ORL_PPO_VALUENORM) ? (ret - vn_mean) / vn_std : ret;
+                const ValueTerm vt = value_term(out[0], a.value_preds[bi], target, a.clip_param, a.huber_delta, a.flags);
+                const float wrow = val_masks ? active * inv_act : inv_rows;
+                loss0 += vt.loss * wrow;
+                dl[l][0] = a.value_loss_coef * wrow * vt.dv;
+            }
+        }
+        float dh[rc::H], dhp[rc::H];
+        for (int j = 0; j < rc::H; ++j) dh[j] = 0.f;
+        for (int l = L - 1; l >= 0; --l) {
+            float* tape = a.tape + ((size_t)cpos * L + l) * rc::TAPE;
+            rc::rnn_step_backward(P, o, a.activation_id, sv[l], msk[l], dl[l], dh, dhp, tape);
+            for (int j = 0; j < rc::H; ++j) dh[j] = dhp[j];
+        }
+    }
+    __shared__ float red[3][RNN_NT / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    loss0 = warp_sum(loss0); loss1 = warp_sum(loss1); loss2 = warp_sum(loss2);
+    if (lane == 0) { red[0][warp] = loss0; red[1][warp] = loss1; red[2][warp] = loss2; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        float s = 0.f;
+        for (int w = 0; w < RNN_NT / 32; ++w) s += red[threadIdx.x][w];
+        if (POLICY) atomicAdd(a.loss_acc + threadIdx.x, s);
+        else if (threadIdx.x == 0) atomicAdd(a.loss_acc + 3, s);
+    }
+}
+
+// ---- tape reductions: out[m*ldo + k] += sum_rows tape[r][p_off+m] * tape[r][q_off+k]  (q_off < 0: Q == 1) ----
+struct TapeJob { int p_off, M, q_off, N, out_off, ldo; };
+constexpr int MAX_JOBS = 17;
+struct TapeJobs { TapeJob j[MAX_JOBS]; int count; };
+constexpr int TR_NT = 256, TR_ROWS = 256, TR_SUB = 16, TR_ACC = (rc::G3 * rc::H) / TR_NT;
+
+__global__ void __launch_bounds__(TR_NT) tape_reduce_kernel(const float* __restrict__ tape, long long rows, TapeJobs jobs,
+                                                            float* __restrict__ grads) {
+    const TapeJob jb = jobs.j[blockIdx.y];
+    const long long r_begin = (long long)blockIdx.x * TR_ROWS;
+    const int rows_here = (int)min((long long)TR_ROWS, rows - r_begin);
+    __shared__ float Ps[TR_SUB][rc::G3];
+    __shared__ float Qs[TR_SUB][rc::H];
+    const int tid = threadIdx.x, MN = jb.M * jb.N;
+    float acc[TR_ACC];
+#pragma unroll
+    for (int i = 0; i < TR_ACC; ++i) acc[i] = 0.f;
+    for (int s0 = 0; s0 < rows_here; s0 += TR_SUB) {
+        const int sub = min(TR_SUB, rows_here - s0);
+        for (int i = tid; i < TR_SUB * jb.M; i += TR_NT) {
+            const int r = i / jb.M, m = i % jb.M;
+            Ps[r][m] = r < sub ? tape[(size_t)(r_begin + s0 + r) * rc::TAPE + jb.p_off + m] : 0.f;
+        }
+        for (int i = tid; i < TR_SUB * jb.N; i += TR_NT) {
+            const int r = i / jb.N, k = i % jb.N;
+            Qs[r][k] = r < sub ? (jb.q_off < 0 ? 1.f : tape[(size_t)(r_begin + s0 + r) * rc::TAPE + jb.q_off + k]) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < TR_ACC; ++i) {
+            const int idx = tid + i * TR_NT;
+            if (idx < MN) {
+                const int m = idx / jb.N, k = idx % jb.N;
+                float s = acc[i];
+#pragma unroll
+                for (int r = 0; r < TR_SUB; ++r) s = fmaf(Ps[r][m], Qs[r][k], s);
+                acc[i] = s;
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < TR_ACC; ++i) {
+        const int idx = tid + i * TR_NT;
+        if (idx < MN) atomicAdd(grads + jb.out_off + (idx / jb.N) * jb.ldo + (idx % jb.N), acc[i]);
+    }
+}
+
+TapeJobs make_jobs(int d, int n) {
+    const rc::Offsets o = rc::rnn_offsets(d, n);
+    TapeJobs t; int c = 0;
+    auto gemm = [&](int p, int M, int q, int N, int out) { t.j[c++] = TapeJob{p, M, q, N, out, N}; };
+    auto col = [&](int p, int M, int out) { t.j[c++] = TapeJob{p, M, -1, 1, out, 1}; };
+    gemm(rc::TP_DZ1, rc::H, rc::TQ_X, d, o.w1);     col(rc::TP_DZ1, rc::H, o.b1);
+    col(rc::TS_DY1N1, rc::H, o.g1);                  col(rc::TS_DY1, rc::H, o.be1);
+    gemm(rc::TP_DZ3, rc::H, rc::TQ_Y1, rc::H, o.w3); col(rc::TP_DZ3, rc::H, o.b3);
+    col(rc::TS_DY3N3, rc::H, o.g3);                  col(rc::TS_DY3, rc::H, o.be3);
+    gemm(rc::TP_DGI, rc::G3, rc::TQ_Y3, rc::H, o.wih); gemm(rc::TP_DGH, rc::G3, rc::TQ_HM, rc::H, o.whh);
+    col(rc::TP_DGI, rc::G3, o.bih);                  col(rc::TP_DGH, rc::G3, o.bhh);
+    col(rc::TS_DONO, rc::H, o.gr);                   col(rc::TS_DO, rc::H, o.ber);
+    gemm(rc::TP_DLOG, n, rc::TQ_O, rc::H, o.wh);     col(rc::TP_DLOG, n, o.bh);
+    t.count = c;
+    return t;
+}
+
+// ---- optimizer: per-net global-norm clip + Adam on the true-layout gradients (one CTA per net) ----
+__global__ void __launch_bounds__(1024) rnn_apply_kernel(const OrlRnnArgs a) {
+    const int net = blockIdx.x;
+    const int total = net == 0 ? rc::rnn_offsets(a.obs_dim, a.n_actions).total : rc::rnn_offsets(a.critic_obs_dim, 1).total;
+    float* params = net == 0 ? a.policy_params : a.critic_params;
+    float* am = net == 0 ? a.policy_adam_m : a.critic_adam_m;
+    float* av = net == 0 ? a.policy_adam_v : a.critic_adam_v;
+    const float* grads = a.grads + (size_t)net * a.grads_stride;
+    __shared__ float red[32];
+    __shared__ float s_norm;
+    const int tid = threadIdx.x;
+    float sq = 0.f;
+    for (int i = tid; i < total; i += blockDim.x) { const float g = grads[i]; sq = fmaf(g, g, sq); }
+    {
+        const float s = warp_sum(sq);
+        if ((tid & 31) == 0) red[tid >> 5] = s;
+        __syncthreads();
+        if (tid < 32) {
+            float v = (tid < (int)(blockDim.x >> 5)) ? red[tid] : 0.f;
+            v = warp_sum(v);
+            if (tid == 0) s_norm = sqrtf(v);
+        }
+        __syncthreads();
+    }
+    const float norm = s_norm;
+    float clip = 1.f;
+    if (a.flags & ORL_PPO_MAX_GRAD_NORM) clip = fminf(a.max_grad_norm / (norm + 1e-6f), 1.0f);
+    const int step = a.adam_steps[net] + 1;
+    const double bc1 = 1.0 - pow((double)a.adam_beta1, (double)step);
+    const double bc2 = 1.0 - pow((double)a.adam_beta2, (double)step);
+    const float step_size = (float)((double)a.lrs[net] / bc1);
+    const float bc2_sqrt = (float)sqrt(bc2);
+    for (int i = tid; i < total; i += blockDim.x) {
+        float g = grads[i] * clip;
+        const float pv = params[i];
+        if (a.weight_decay != 0.f) g = fmaf(a.weight_decay, pv, g);
+        const float m = am[i] + (g - am[i]) * (1.f - a.adam_beta1);
+        const float v = fmaf(av[i], a.adam_beta2, (g * g) * (1.f - a.adam_beta2));
+        am[i] = m; av[i] = v;
+        params[i] = pv - step_size * (m / (sqrtf(v) / bc2_sqrt + a.adam_eps));
+    }
+    if (tid == 0) {
+        a.adam_steps[net] = step;
+        if (net == 0) {
+            a.train_info[2] += a.loss_acc[0];
+            a.train_info[3] += a.loss_acc[1];
+            a.train_info[4] += norm;
+            a.train_info[5] += a.loss_acc[2] / (float)((double)a.n_chunks * a.chunk_length);
+        } else {
+            a.train_info[0] += a.loss_acc[3];
+            a.train_info[1] += norm;
+            if (a.flags & ORL_PPO_VALUENORM) {
+                float st[3];
+                vn_updated(a.vn_state, a.mb_stats, (double)a.n_chunks * a.chunk_length, a.vn_beta, st);
+                a.vn_state[0] = st[0]; a.vn_state[1] = st[1]; a.vn_state[2] = st[2];
+            }
+        }
+    }
+}
+
+int check_common(const OrlRnnArgs& a) {
+    ORL_CHECK_ARG(a.n_envs > 0 && a.n_agents > 0 && a.episode_length > 0, "n_envs / n_agents / episode_length");
+    ORL_CHECK_ARG(a.obs_dim > 0 && a.obs_dim <= rc::MAXD && a.critic_obs_dim > 0 && a.critic_obs_dim <= rc::MAXD, "obs dims (<= 64)");
+    ORL_CHECK_ARG(a.n_actions > 0 && a.n_actions <= MAX_OUT, "n_actions (<= 8)");
+    ORL_CHECK_ARG(a.activation_id >= 0 && a.activation_id <= 3, "activation_id");
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int orl_rnn_param_count(int obs_dim, int n_out) { return rc::rnn_offsets(obs_dim, n_out).total; }
+int orl_rnn_tape_width(void) { return rc::TAPE; }
+
+int orl_rnn_rollout(const OrlRnnArgs* ap, void* stream) {
+    ORL_CHECK_ARG(ap, "args");
+    const OrlRnnArgs& a = *ap;
+    if (int e = check_common(a)) return e;
+    ORL_CHECK_ARG(a.policy_params && a.policy_obs && a.critic_obs && a.rnn_states && a.actions && a.action_log_probs &&
+                      a.rewards && a.masks && a.active_masks, "null rollout buffer");
+    ORL_CHECK_ARG(a.t_begin >= 0 && a.t_end <= a.episode_length && a.t_begin <= a.t_end, "t range");
+    ORL_CHECK_ARG(a.env_kind == ORL_ENV_MPE_SPREAD || a.env_kind == ORL_ENV_CARTPOLE || a.env_kind == ORL_ENV_GRIDWORLD,
+                  "recurrent rollout needs a device env");
+    ORL_CHECK_ARG(a.ep_return && a.ep_length && a.episode_stats, "episode statistics buffers");
+    if (a.env_kind == ORL_ENV_MPE_SPREAD) {
+        ORL_CHECK_ARG(a.n_agents == 3 && a.obs_dim == 18 && a.critic_obs_dim == 54 && a.env_f64 && a.env_u64 && a.env_i32,
+                      "simple_spread shapes / state");
+    } else {
+        ORL_CHECK_ARG(a.n_agents == 1 && a.obs_dim == 4, "single-agent env shapes");
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = (a.n_envs + RNN_NT - 1) / RNN_NT;
+    if (a.t_end > a.t_begin) {
+        switch (a.env_kind) {
+            case ORL_ENV_MPE_SPREAD: rnn_rollout_kernel<ORL_ENV_MPE_SPREAD><<<grid, RNN_NT, 0, st>>>(a); break;
+            case ORL_ENV_CARTPOLE: rnn_rollout_kernel<ORL_ENV_CARTPOLE><<<grid, RNN_NT, 0, st>>>(a); break;
+            default: rnn_rollout_kernel<ORL_ENV_GRIDWORLD><<<grid, RNN_NT, 0, st>>>(a); break;
+        }
+    }
+    return orl::check_cuda(cudaGetLastError(), "rnn_rollout_kernel launch");
+}
+
+int orl_rnn_critic(const OrlRnnArgs* ap, void* stream) {
+    ORL_CHECK_ARG(ap, "args");
+    const OrlRnnArgs& a = *ap;
+    if (int e = check_common(a)) return e;
+    ORL_CHECK_ARG(a.critic_params && a.critic_obs && a.rnn_states_critic && a.masks && a.value_preds, "null critic buffer");
+    const int B = a.n_envs * a.n_agents;
+    rnn_critic_kernel<<<(B + RNN_NT - 1) / RNN_NT, RNN_NT, 0, (cudaStream_t)stream>>>(a);
+    return orl::check_cuda(cudaGetLastError(), "rnn_critic_kernel launch");
+}
+
+int orl_rnn_fwdbwd(const OrlRnnArgs* ap, void* stream) {
+    ORL_CHECK_ARG(ap, "args");
+    const OrlRnnArgs& a = *ap;
+    if (int e = check_common(a)) return e;
+    ORL_CHECK_ARG(a.chunk_length >= 1 && a.chunk_length <= LMAX, "chunk_length (data_chunk_length) must be in [1, 4]");
+    ORL_CHECK_ARG(a.n_chunks > 0 && a.chunk_ids, "chunks");
+    ORL_CHECK_ARG(a.policy_params && a.critic_params && a.policy_obs && a.critic_obs && a.rnn_states && a.rnn_states_critic &&
+                      a.actions && a.action_log_probs && a.masks && a.active_masks && a.value_preds && a.returns && a.advantages,
+                  "null update buffer");
+    ORL_CHECK_ARG(a.gae_stats && a.mb_stats && a.tape && a.grads && a.loss_acc, "stats / workspace");
+    ORL_CHECK_ARG(a.grads_stride >= rc::rnn_offsets(a.obs_dim, a.n_actions).total &&
+                      a.grads_stride >= rc::rnn_offsets(a.critic_obs_dim, 1).total, "grads_stride");
+    if (a.flags & ORL_PPO_VALUENORM) { ORL_CHECK_ARG(a.vn_state, "vn_state"); }
+    cudaStream_t st = (cudaStream_t)stream;
+    int e = orl::check_cuda(cudaMemsetAsync(a.grads, 0, 2 * (size_t)a.grads_stride * sizeof(float), st), "memset grads");
+    if (e) return e;
+    e = orl::check_cuda(cudaMemsetAsync(a.loss_acc, 0, 8 * sizeof(float), st), "memset loss_acc");
+    if (e) return e;
+    const long long rows = a.n_chunks * a.chunk_length;
+    const int cgrid = (int)((a.n_chunks + RNN_NT - 1) / RNN_NT);
+    const int rgrid = (int)((rows + TR_ROWS - 1) / TR_ROWS);
+    {
+        rnn_chunk_kernel<true><<<cgrid, RNN_NT, 0, st>>>(a);
+        const TapeJobs jobs = make_jobs(a.obs_dim, a.n_actions);
+        tape_reduce_kernel<<<dim3(rgrid, jobs.count), TR_NT, 0, st>>>(a.tape, rows, jobs, a.grads);
+    }
+    {
+        rnn_chunk_kernel<false><<<cgrid, RNN_NT, 0, st>>>(a);
+        const TapeJobs jobs = make_jobs(a.critic_obs_dim, 1);
+        tape_reduce_kernel<<<dim3(rgrid, jobs.count), TR_NT, 0, st>>>(a.tape, rows, jobs, a.grads + a.grads_stride);
+    }
+    return orl::check_cuda(cudaGetLastError(), "rnn update launches");
+}
+
+int orl_rnn_apply(const OrlRnnArgs* ap, void* stream) {
+    ORL_CHECK_ARG(ap, "args");
+    const OrlRnnArgs& a = *ap;
+    if (int e = check_common(a)) return e;
+    ORL_CHECK_ARG(a.policy_params && a.critic_params && a.grads && a.loss_acc && a.policy_adam_m && a.policy_adam_v &&
+                      a.critic_adam_m && a.critic_adam_v && a.adam_steps && a.lrs && a.train_info && a.mb_stats, "null optimizer buffer");
+    ORL_CHECK_ARG(a.n_chunks > 0 && a.chunk_length >= 1, "chunks");
+    if (a.flags & ORL_PPO_VALUENORM) { ORL_CHECK_ARG(a.vn_state, "vn_state"); }
+    rnn_apply_kernel<<<2, 1024, 0, (cudaStream_t)stream>>>(a);
+    return orl::check_cuda(cudaGetLastError(), "rnn_apply_kernel launch");
+}
+
+}  // extern "C"

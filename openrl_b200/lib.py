@@ -145,6 +145,44 @@ _SIGNATURES.update({
     "orl_minibatch_stats": [_P, _c.c_int64, _P, _P, _P, _P],
 })
 
+
+class OrlRnnArgs(ctypes.Structure):
+    """Mirror of OrlRnnArgs (include/openrl_b200.h): recurrent (GRU) rollout / critic / update / optimizer."""
+    _fields_ = [
+        ("env_kind", _c.c_int32), ("n_envs", _c.c_int32), ("n_agents", _c.c_int32), ("episode_length", _c.c_int32),
+        ("t_begin", _c.c_int32), ("t_end", _c.c_int32),
+        ("obs_dim", _c.c_int32), ("critic_obs_dim", _c.c_int32), ("n_actions", _c.c_int32), ("activation_id", _c.c_int32),
+        ("deterministic", _c.c_int32), ("chunk_length", _c.c_int32),
+        ("flags", _c.c_int32), ("env_table_len", _c.c_int32),
+        ("n_chunks", _c.c_int64), ("chunk_ids", _P),
+        ("policy_params", _P), ("critic_params", _P), ("policy_obs", _P), ("critic_obs", _P),
+        ("rnn_states", _P), ("rnn_states_critic", _P),
+        ("actions", _P), ("action_log_probs", _P), ("rewards", _P), ("masks", _P), ("active_masks", _P),
+        ("value_preds", _P), ("returns", _P), ("advantages", _P), ("exp_noise", _P),
+        ("rng_seed", _c.c_uint64), ("rng_step_base", _c.c_uint64), ("rng_counter", _P),
+        ("env_f64", _P), ("env_u64", _P), ("env_i32", _P), ("env_table", _P),
+        ("ep_return", _P), ("ep_length", _P), ("episode_stats", _P),
+        ("gae_stats", _P), ("mb_stats", _P), ("vn_state", _P),
+        ("tape", _P), ("grads", _P), ("grads_stride", _c.c_int32), ("reserved1", _c.c_int32),
+        ("loss_acc", _P),
+        ("policy_adam_m", _P), ("policy_adam_v", _P), ("critic_adam_m", _P), ("critic_adam_v", _P),
+        ("adam_steps", _P), ("lrs", _P),
+        ("clip_param", _F), ("entropy_coef", _F), ("value_loss_coef", _F), ("huber_delta", _F), ("max_grad_norm", _F),
+        ("adam_beta1", _F), ("adam_beta2", _F), ("adam_eps", _F), ("weight_decay", _F), ("dual_clip_coeff", _F),
+        ("vn_beta", _D),
+        ("train_info", _P),
+    ]
+
+
+_SIGNATURES.update({
+    "orl_rnn_param_count": [_I, _I],
+    "orl_rnn_tape_width": [],
+    "orl_rnn_rollout": [_c.POINTER(OrlRnnArgs), _P],
+    "orl_rnn_critic": [_c.POINTER(OrlRnnArgs), _P],
+    "orl_rnn_fwdbwd": [_c.POINTER(OrlRnnArgs), _P],
+    "orl_rnn_apply": [_c.POINTER(OrlRnnArgs), _P],
+})
+
 ENV_NONE, ENV_CARTPOLE, ENV_GRIDWORLD, ENV_MPE_SPREAD = 0, 1, 2, 3
 HEAD_CATEGORICAL, HEAD_GAUSSIAN = 0, 1
 GAE_USE_GAE, GAE_PROPER_TIME_LIMITS, GAE_DENORM = 1, 2, 4

@@ -25,7 +25,8 @@ def _c_layout(struct, fields, tmp_path):
 def test_struct_layouts_match_header(tmp_path):
     from openrl_b200 import lib
 
-    for name, cls in (("OrlRolloutArgs", lib.OrlRolloutArgs), ("OrlPpoArgs", lib.OrlPpoArgs)):
+    for name, cls in (("OrlRolloutArgs", lib.OrlRolloutArgs), ("OrlPpoArgs", lib.OrlPpoArgs),
+                      ("OrlRnnArgs", lib.OrlRnnArgs)):
         fields = [f[0] for f in cls._fields_]
         c = _c_layout(name, fields, tmp_path)
         assert c["sizeof"] == ctypes.sizeof(cls), name
