@@ -52,9 +52,23 @@ class PPOAlgorithm:
         if getattr(cfg, "dual_clip_ppo", False):
             self.flags |= lib.PPO_DUAL_CLIP
         for name in ("use_joint_action_loss", "use_policy_vhead", "use_share_model", "use_popart",
-                     "use_amp", "use_deepspeed", "use_naive_recurrent_policy", "use_recurrent_policy"):
+                     "use_amp", "use_deepspeed", "use_naive_recurrent_policy"):
             if getattr(cfg, name, False):
                 raise NotImplementedError(f"cfg.{name} is not built into the CUDA update yet (SURVEY.md §8f)")
+        self.recurrent = bool(cfg.use_recurrent_policy)
+        if self.recurrent:
+            if self.world_size > 1:
+                raise NotImplementedError("the recurrent update is single-GPU for now (DESIGN.md, recurrent path)")
+            if self.head_kind != lib.HEAD_CATEGORICAL:
+                raise NotImplementedError("recurrent policies are built for Discrete action spaces")
+            if not 1 <= cfg.data_chunk_length <= 4:
+                raise NotImplementedError("data_chunk_length must be in [1, 4] for the recurrent kernels")
+            self.use_tf32 = False
+            self.flags &= ~lib.PPO_TF32
+            self.rnn_stride = (max(self._lib.orl_rnn_param_count(self.d, self.n), self._lib.orl_rnn_param_count(self.dc, 1)) + 3) & ~3
+            self.rnn_grads = torch.zeros(2, self.rnn_stride, dtype=torch.float32, device=dev)
+            self.loss_acc = torch.zeros(8, dtype=torch.float32, device=dev)
+            self.tape = None
         self.gpu_launches = 0
         self.h2d_bytes = 0
         self.d2h_bytes = 0
@@ -117,6 +131,79 @@ class PPOAlgorithm:
         lib.check(L.orl_ppo_apply(a, s), "orl_ppo_apply")
         self.gpu_launches += 3
 
+    def _rnn_args(self, buf, chunk_ids, mb_stats):
+        m = self.algo_module
+        pol, cri = m.models["policy"], m.models["critic"]
+        op, oc = m.optimizers["policy"], m.optimizers["critic"]
+        cfg = self.cfg
+        a = lib.OrlRnnArgs()
+        a.n_envs, a.n_agents, a.episode_length = buf.n_rollout_threads, buf.num_agents, buf.episode_length
+        a.obs_dim, a.critic_obs_dim, a.n_actions, a.activation_id = self.d, self.dc, self.n, pol.activation_id
+        a.chunk_length, a.flags = cfg.data_chunk_length, self.flags
+        a.n_chunks, a.chunk_ids = int(chunk_ids.numel()), lib.ptr(chunk_ids)
+        a.policy_params, a.critic_params = lib.ptr(pol.flat_params), lib.ptr(cri.flat_params)
+        a.policy_obs, a.critic_obs = lib.ptr(buf.policy_obs), lib.ptr(buf.critic_obs)
+        a.rnn_states, a.rnn_states_critic = lib.ptr(buf.rnn_states), lib.ptr(buf.rnn_states_critic)
+        a.actions, a.action_log_probs = lib.ptr(buf.actions), lib.ptr(buf.action_log_probs)
+        a.masks, a.active_masks = lib.ptr(buf.masks), lib.ptr(buf.active_masks)
+        a.value_preds, a.returns, a.advantages = lib.ptr(buf.value_preds), lib.ptr(buf.returns), lib.ptr(buf.advantages)
+        a.gae_stats, a.mb_stats = lib.ptr(buf.gae_stats), lib.ptr(mb_stats)
+        vn = cri.value_normalizer
+        a.vn_state = None if vn is None else lib.ptr(vn.state)
+        a.tape, a.grads, a.grads_stride, a.loss_acc = lib.ptr(self.tape), lib.ptr(self.rnn_grads), self.rnn_stride, lib.ptr(self.loss_acc)
+        a.policy_adam_m, a.policy_adam_v = lib.ptr(op.exp_avg), lib.ptr(op.exp_avg_sq)
+        a.critic_adam_m, a.critic_adam_v = lib.ptr(oc.exp_avg), lib.ptr(oc.exp_avg_sq)
+        a.adam_steps, a.lrs = lib.ptr(m.adam_steps), lib.ptr(self.lrs)
+        a.clip_param, a.entropy_coef, a.value_loss_coef = cfg.clip_param, cfg.entropy_coef, cfg.value_loss_coef
+        a.huber_delta, a.max_grad_norm = cfg.huber_delta, cfg.max_grad_norm
+        g = op.param_groups[0]
+        a.adam_beta1, a.adam_beta2, a.adam_eps, a.weight_decay = g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"]
+        a.dual_clip_coeff = float(getattr(cfg, "dual_clip_coeff", 3.0))
+        a.vn_beta = 0.99999 if vn is None else vn.beta
+        a.train_info = lib.ptr(self.train_info)
+        return a
+
+    def _train_recurrent(self, buf):
+        """train_ppo with ReplayData.recurrent_generator (replay_data.py:1062-1258): per epoch one permutation of
+        the data chunks (L consecutive steps of the agent-major / time-minor flattening f = (n*A + a)*T + t);
+        a minibatch is a slice of chunk ids, gathered inside the kernels."""
+        cfg = self.cfg
+        T, B = buf.episode_length, buf.n_rollout_threads * buf.num_agents
+        total, L = T * B, cfg.data_chunk_length
+        if total < L:
+            raise AssertionError(f"PPO requires the number of processes ({buf.n_rollout_threads}) * episode length ({T}) "
+                                 f"* agents to be greater than or equal to the data chunk length ({L}).")
+        data_chunks = total // L
+        mbc = data_chunks // self.num_mini_batch
+        rows = mbc * L
+        width = self._lib.orl_rnn_tape_width()
+        if self.tape is None or self.tape.shape[0] < rows:
+            self.tape = torch.empty(rows, width, dtype=torch.float32, device=self.device)
+        whole = self.num_mini_batch == 1 and rows == total
+        s, Lb = lib.current_stream(), self._lib
+        lane = torch.arange(L, device=self.device)
+        for _ in range(self.ppo_epoch):
+            if cfg.parity_mode:
+                perm = torch.randperm(data_chunks).to(self.device, non_blocking=True)   # global CPU generator
+                self.h2d_bytes += data_chunks * 8
+            else:
+                perm = torch.randperm(data_chunks, device=self.device)
+            for i in range(self.num_mini_batch):
+                ids = perm[i * mbc:(i + 1) * mbc].contiguous()
+                if whole:
+                    mb_stats = buf.gae_stats[5:8]
+                else:
+                    f = (ids[:, None] * L + lane[None, :]).reshape(-1)
+                    bi = ((f % T) * B + f // T).contiguous()        # buffer row of (t, row) is t*B + row
+                    lib.check(Lb.orl_minibatch_stats(lib.ptr(bi), int(rows), lib.ptr(buf.returns), lib.ptr(buf.active_masks),
+                                                     lib.ptr(self.mb_stats), s), "orl_minibatch_stats")
+                    mb_stats = self.mb_stats
+                    self.gpu_launches += 1
+                a = self._rnn_args(buf, ids, mb_stats)
+                lib.check(Lb.orl_rnn_fwdbwd(a, s), "orl_rnn_fwdbwd")
+                lib.check(Lb.orl_rnn_apply(a, s), "orl_rnn_apply")
+                self.gpu_launches += 5
+
     def train(self, buffer, turn_on=True):
         """train_ppo (ppo.py:383-458).  `buffer` is the device ReplayData whose returns/advantages
         were produced by `compute_returns` (orl_gae).  Returns the averaged metrics (one D2H read)."""
@@ -141,6 +228,8 @@ class PPOAlgorithm:
             self.h2d_bytes += 8
         self.train_info.zero_()
         parallel.allreduce_sum_(buf.gae_stats)  # global advantage / return moments (ppo.py:402-409 semantics)
+        if self.recurrent:
+            return self._train_recurrent(buf)
         total = buf.episode_length * buf.n_rollout_threads * buf.num_agents
         mb = total // self.num_mini_batch
         whole = self.num_mini_batch == 1

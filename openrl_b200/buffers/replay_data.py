@@ -51,6 +51,13 @@ class ReplayData:
         self.rewards = f(T, N, A, 1)
         self.advantages = f(T, N, A, 1)  # raw returns - V, written by the GAE kernel (ppo.py:384-399)
         self.gae_stats = torch.zeros(8, dtype=torch.float64, device=self.device)
+        # hidden states, one per (slot, row): replay_data.py:96-111.  (T+1, N, A, recurrent_N, H)
+        self.recurrent = bool(cfg.use_recurrent_policy)
+        if self.recurrent:
+            self.rnn_states = f(T + 1, N, A, cfg.recurrent_N, cfg.hidden_size)
+            self.rnn_states_critic = f(T + 1, N, A, cfg.recurrent_N, cfg.hidden_size)
+        else:
+            self.rnn_states = self.rnn_states_critic = None
         self.step = 0
         self._lib = lib.load()
 
@@ -69,6 +76,9 @@ class ReplayData:
         self.active_masks[0].copy_(self.active_masks[-1])
         if not self.action_masks_trivial:
             self.action_masks[0].copy_(self.action_masks[-1])
+        if self.recurrent:
+            self.rnn_states[0].copy_(self.rnn_states[-1])
+            self.rnn_states_critic[0].copy_(self.rnn_states_critic[-1])
 
     def compute_returns(self, next_value, value_normalizer=None):
         """replay_data.py:320-423 on the device (orl_gae), fused with the advantage build.

@@ -55,7 +55,8 @@ __device__ __forceinline__ int pick_action(const OrlRnnArgs& a, const float (&pr
 template <int ENV>
 __global__ void __launch_bounds__(RNN_NT) rnn_rollout_kernel(const OrlRnnArgs a) {
     constexpr int A = ENV == ORL_ENV_MPE_SPREAD ? 3 : 1;
-    constexpr int D = ENV == ORL_ENV_MPE_SPREAD ? 18 : 4;
+    constexpr int DX = ENV == ORL_ENV_MPE_SPREAD ? 18 : (ENV == ORL_ENV_NONE ? rc::MAXD : 4);
+    const int D = ENV == ORL_ENV_NONE ? a.obs_dim : DX;
     const int N = a.n_envs, B = N * A, n = a.n_actions;
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= N) return;
@@ -69,7 +70,7 @@ __global__ void __launch_bounds__(RNN_NT) rnn_rollout_kernel(const OrlRnnArgs a)
         for (int ag = 0; ag < A; ++ag) {
             const int row = e * A + ag;
             const size_t grow = (size_t)t * B + row;
-            float x[D], h[rc::H], hn[rc::H], logit[MAX_OUT];
+            float x[DX], h[rc::H], hn[rc::H], logit[MAX_OUT];
             for (int k = 0; k < D; ++k) x[k] = a.policy_obs[grow * D + k];
             for (int j = 0; j < rc::H; ++j) h[j] = a.rnn_states[grow * rc::H + j];
             rc::rnn_step_forward(P, o, a.activation_id, x, h, a.masks[grow], hn, logit, nullptr, nullptr);
@@ -87,7 +88,8 @@ __global__ void __launch_bounds__(RNN_NT) rnn_rollout_kernel(const OrlRnnArgs a)
             a.action_log_probs[grow] = lp;
             acts[ag] = act;
         }
-        bool done; float reward;
+        if constexpr (ENV == ORL_ENV_NONE) continue;   // act only (PPOModule.act): the caller owns env.step and the masks
+        bool done = false; float reward = 0.f;
         if constexpr (ENV == ORL_ENV_MPE_SPREAD) {
             float ob[3][18];
             const int acts3[3] = {acts[0], acts[1], acts[2]};
@@ -99,7 +101,7 @@ __global__ void __launch_bounds__(RNN_NT) rnn_rollout_kernel(const OrlRnnArgs a)
                     for (int dst = 0; dst < 3; ++dst) a.critic_obs[(r1 + dst) * 54 + ag * 18 + k] = ob[ag][k];
                 }
             }
-        } else {
+        } else if constexpr (ENV != ORL_ENV_NONE) {
             float ob[4], fin[4];
             env_step_single(E, ENV, e, N, acts[0], ob, reward, done, fin);
             const size_t o1 = (size_t)(t + 1) * B + e;
@@ -117,6 +119,8 @@ __global__ void __launch_bounds__(RNN_NT) rnn_rollout_kernel(const OrlRnnArgs a)
         }
     }
 }
+
+__global__ void rnn_bump_counter_kernel(uint64_t* c, uint64_t by) { *c += by; }
 
 // ---- recurrent critic over all T+1 slots: one thread per row ----
 __global__ void __launch_bounds__(RNN_NT) rnn_critic_kernel(const OrlRnnArgs a) {
@@ -176,7 +180,7 @@ __global__ void __launch_bounds__(RNN_NT) rnn_chunk_kernel(const OrlRnnArgs a) {
         for (int l = 0; l < L; ++l) {
             const long long f = f0 + l, row = f / T, t = f % T;
             const size_t bi = (size_t)t * B + row;
-            for (int k = 0; k < d; ++k) x[k] = obs[bi * d + k];
+            for (int k = 0; k < rc::MAXD; ++k) x[k] = k < d ? obs[bi * d + k] : 0.f;
             msk[l] = a.masks[bi];
             float out[MAX_OUT];
             float* tape = a.tape + ((size_t)cpos * L + l) * rc::TAPE;
@@ -379,11 +383,19 @@ int orl_rnn_rollout(const OrlRnnArgs* ap, void* stream) {
     ORL_CHECK_ARG(ap, "args");
     const OrlRnnArgs& a = *ap;
     if (int e = check_common(a)) return e;
-    ORL_CHECK_ARG(a.policy_params && a.policy_obs && a.critic_obs && a.rnn_states && a.actions && a.action_log_probs &&
-                      a.rewards && a.masks && a.active_masks, "null rollout buffer");
+    ORL_CHECK_ARG(a.policy_params && a.policy_obs && a.rnn_states && a.actions && a.action_log_probs && a.masks, "null rollout buffer");
     ORL_CHECK_ARG(a.t_begin >= 0 && a.t_end <= a.episode_length && a.t_begin <= a.t_end, "t range");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = (a.n_envs + RNN_NT - 1) / RNN_NT;
+    if (a.env_kind == ORL_ENV_NONE) {   // policy step(s) only: rows = n_envs, slot t -> actions[t], rnn_states[t+1]
+        ORL_CHECK_ARG(a.n_agents == 1, "ENV_NONE rows are passed as n_envs with n_agents == 1");
+        if (a.t_end > a.t_begin) rnn_rollout_kernel<ORL_ENV_NONE><<<grid, RNN_NT, 0, st>>>(a);
+        if (a.rng_counter) rnn_bump_counter_kernel<<<1, 1, 0, st>>>(a.rng_counter, (uint64_t)(a.t_end - a.t_begin));
+        return orl::check_cuda(cudaGetLastError(), "rnn_rollout_kernel(act) launch");
+    }
+    ORL_CHECK_ARG(a.critic_obs && a.rewards && a.active_masks, "null rollout buffer");
     ORL_CHECK_ARG(a.env_kind == ORL_ENV_MPE_SPREAD || a.env_kind == ORL_ENV_CARTPOLE || a.env_kind == ORL_ENV_GRIDWORLD,
-                  "recurrent rollout needs a device env");
+                  "unknown env kind");
     ORL_CHECK_ARG(a.ep_return && a.ep_length && a.episode_stats, "episode statistics buffers");
     if (a.env_kind == ORL_ENV_MPE_SPREAD) {
         ORL_CHECK_ARG(a.n_agents == 3 && a.obs_dim == 18 && a.critic_obs_dim == 54 && a.env_f64 && a.env_u64 && a.env_i32,
@@ -391,8 +403,6 @@ int orl_rnn_rollout(const OrlRnnArgs* ap, void* stream) {
     } else {
         ORL_CHECK_ARG(a.n_agents == 1 && a.obs_dim == 4, "single-agent env shapes");
     }
-    cudaStream_t st = (cudaStream_t)stream;
-    const int grid = (a.n_envs + RNN_NT - 1) / RNN_NT;
     if (a.t_end > a.t_begin) {
         switch (a.env_kind) {
             case ORL_ENV_MPE_SPREAD: rnn_rollout_kernel<ORL_ENV_MPE_SPREAD><<<grid, RNN_NT, 0, st>>>(a); break;
@@ -400,6 +410,7 @@ int orl_rnn_rollout(const OrlRnnArgs* ap, void* stream) {
             default: rnn_rollout_kernel<ORL_ENV_GRIDWORLD><<<grid, RNN_NT, 0, st>>>(a); break;
         }
     }
+    if (a.rng_counter) rnn_bump_counter_kernel<<<1, 1, 0, st>>>(a.rng_counter, (uint64_t)(a.t_end - a.t_begin));
     return orl::check_cuda(cudaGetLastError(), "rnn_rollout_kernel launch");
 }
 

@@ -15,8 +15,13 @@
 
 #ifdef __CUDACC__
 #define ORL_HD __host__ __device__ __forceinline__
+// The two step functions are real calls on the device (own stack frames): with everything inlined into the
+// per-chunk kernel nvcc 12.9 merged the stack slots of the caller's observation row and the callee's GRU
+// output (observed in SASS and as a corrupted tape, see profiles/r1_gru_debug.md), i.e. wrong gradients.
+#define ORL_HD_STEP __host__ __device__ __noinline__
 #else
 #define ORL_HD static inline
+#define ORL_HD_STEP static inline
 #endif
 
 namespace orl_rnn {
@@ -80,9 +85,10 @@ struct StepSave {
 
 // One forward step of a recurrent net.  x[d], h_in[64], mask -> h_out[64], head out[n].
 // `sv` may be NULL (rollout).  Also returns y1 / o through the tape pointer when given.
-ORL_HD void rnn_step_forward(const float* P, const Offsets& o, int act_id, const float* x, const float* h_in, float mask,
+ORL_HD_STEP void rnn_step_forward(const float* P, const Offsets& o, int act_id, const float* x, const float* h_in, float mask,
                              float* h_out, float* out, StepSave* sv, float* tape) {
     float a1[H], n1[H], y1[H], z3[H], n3[H], y3[H];
+    if (tape) for (int k = 0; k < MAXD; ++k) tape[TQ_X + k] = k < o.d ? x[k] : 0.f;
     for (int j = 0; j < H; ++j) {
         float s = P[o.b1 + j];
         for (int k = 0; k < o.d; ++k) s = fmaf(P[o.w1 + j * o.d + k], x[k], s);
@@ -134,7 +140,6 @@ ORL_HD void rnn_step_forward(const float* P, const Offsets& o, int act_id, const
         sv->rstd1 = rstd1; sv->rstd3 = rstd3; sv->rstdr = rstdr;
     }
     if (tape) {
-        for (int k = 0; k < MAXD; ++k) tape[TQ_X + k] = k < o.d ? x[k] : 0.f;
         for (int j = 0; j < H; ++j) { tape[TQ_Y1 + j] = y1[j]; tape[TQ_Y3 + j] = y3[j]; tape[TQ_HM + j] = hm[j]; tape[TQ_O + j] = ov[j]; }
     }
 }
@@ -142,7 +147,7 @@ ORL_HD void rnn_step_forward(const float* P, const Offsets& o, int act_id, const
 // Backward of one row-step.  dlogit[n]: dL/d head output; dh_from_next[64]: dL/d h_out arriving from the
 // following step of the chunk (zero for the last step).  Writes the P / S parts of the tape and returns
 // dL/d h_in (already multiplied by the mask) in dh_prev.
-ORL_HD void rnn_step_backward(const float* P, const Offsets& o, int act_id, const StepSave& sv, float mask, const float* dlogit,
+ORL_HD_STEP void rnn_step_backward(const float* P, const Offsets& o, int act_id, const StepSave& sv, float mask, const float* dlogit,
                               const float* dh_from_next, float* dh_prev, float* tape) {
     float dov[H], dno[H], dh[H];
     for (int k = 0; k < H; ++k) {

@@ -43,6 +43,9 @@ class OnPolicyDriver:
         self.h2d_bytes = 0
         self.d2h_bytes = 0
         self.phase_events = None  # set to a list by bench.py to collect (name, start, end) CUDA events
+        self.recurrent = bool(cfg.use_recurrent_policy)
+        if self.recurrent and self.envs.kind == lib.ENV_NONE:
+            raise NotImplementedError("recurrent policies need a device env (CartPole-v1, GridWorldEnv, simple_spread)")
 
     # -- reference surface -------------------------------------------------------------------
     def run(self):
@@ -135,6 +138,38 @@ class OnPolicyDriver:
         a.ep_return, a.ep_length, a.episode_stats = lib.ptr(env.ep_return), lib.ptr(env.ep_length), lib.ptr(env.episode_stats)
         return a
 
+    def _rnn_args(self, t_begin, t_end, noise):
+        """OrlRnnArgs for the recurrent rollout / critic launches (update fields are filled by PPOAlgorithm)."""
+        d, env = self.buffer.data, self.envs
+        pol, cri = self.trainer.algo_module.models["policy"], self.trainer.algo_module.models["critic"]
+        a = lib.OrlRnnArgs()
+        a.env_kind, a.n_envs, a.n_agents = env.kind, env.parallel_env_num, env.agent_num
+        a.episode_length, a.t_begin, a.t_end = self.episode_length, t_begin, t_end
+        a.obs_dim, a.critic_obs_dim, a.n_actions = d.obs_dim, d.critic_obs_dim, d.n_actions
+        a.activation_id, a.deterministic = pol.activation_id, 0
+        a.env_table_len = env.env_table_len
+        a.policy_params, a.critic_params = lib.ptr(pol.flat_params), lib.ptr(cri.flat_params)
+        a.policy_obs, a.critic_obs = lib.ptr(d.policy_obs), lib.ptr(d.critic_obs)
+        a.rnn_states, a.rnn_states_critic = lib.ptr(d.rnn_states), lib.ptr(d.rnn_states_critic)
+        a.actions, a.action_log_probs, a.rewards = lib.ptr(d.actions), lib.ptr(d.action_log_probs), lib.ptr(d.rewards)
+        a.masks, a.active_masks, a.value_preds = lib.ptr(d.masks), lib.ptr(d.active_masks), lib.ptr(d.value_preds)
+        a.exp_noise = lib.ptr(noise)
+        a.rng_seed, a.rng_step_base, a.rng_counter = int(self.cfg.seed) + 0x9E3779B9 * (self.rank + 1), 0, lib.ptr(self.rng_counter)
+        a.env_f64, a.env_u64, a.env_i32 = lib.ptr(env.env_f64), lib.ptr(env.env_u64), lib.ptr(env.env_i32)
+        a.env_table = lib.ptr(env.env_table)
+        a.ep_return, a.ep_length, a.episode_stats = lib.ptr(env.ep_return), lib.ptr(env.ep_length), lib.ptr(env.episode_stats)
+        return a
+
+    def _launch_steps(self, t_begin, t_end, noise):
+        """Policy + env for steps [t_begin, t_end): feed-forward (orl_rollout) or recurrent (orl_rnn_rollout)."""
+        s = lib.current_stream()
+        if self.recurrent:
+            lib.check(self._lib.orl_rnn_rollout(self._rnn_args(t_begin, t_end, noise), s), "orl_rnn_rollout")
+            self.gpu_launches += 2
+        else:
+            lib.check(self._lib.orl_rollout(self._rollout_args(t_begin, t_end, noise), s), "orl_rollout")
+            self.gpu_launches += 2
+
     def _draw_noise(self):
         """(T, B, n) Exp(1) noise from the global CPU generator, one draw per step like the
         reference's `torch.multinomial` inside Categorical.sample()."""
@@ -153,9 +188,7 @@ class OnPolicyDriver:
     def _rollout_launch(self):
         noise = self._draw_noise() if self.cfg.parity_mode else None
         with self._phase("rollout"):
-            lib.check(self._lib.orl_rollout(self._rollout_args(0, self.episode_length, noise), lib.current_stream()),
-                      "orl_rollout")
-        self.gpu_launches += 2
+            self._launch_steps(0, self.episode_length, noise)
         self.agent.num_time_steps += self.envs.parallel_env_num * self.episode_length
 
     def actor_rollout(self):
@@ -175,8 +208,7 @@ class OnPolicyDriver:
             noise = self._draw_noise() if self.cfg.parity_mode else None
             d = self.buffer.data
             for step in range(T):
-                lib.check(self._lib.orl_rollout(self._rollout_args(step, step + 1, noise), s), "orl_rollout")
-                self.gpu_launches += 2
+                self._launch_steps(step, step + 1, noise)
                 self.agent.num_time_steps += N
                 # materialise the reference's per-step locals for the callbacks
                 actions = d.actions[step].cpu().numpy()  # noqa: F841
@@ -248,6 +280,15 @@ class OnPolicyDriver:
         d = self.buffer.data
         cri = self.trainer.algo_module.models["critic"]
         rows = (self.episode_length + 1) * d.n_rollout_threads * d.num_agents
+        if self.recurrent:
+            # the recurrent critic replays slots 0..T in order (its hidden state is part of the path)
+            with self._phase("critic"):
+                lib.check(self._lib.orl_rnn_critic(self._rnn_args(0, self.episode_length, None), lib.current_stream()),
+                          "orl_rnn_critic")
+            with self._phase("gae"):
+                self.buffer.compute_returns(None, self.trainer.algo_module.get_critic_value_normalizer())
+            self.gpu_launches += 2
+            return
         with self._phase("critic"):
             lib.check(self._lib.orl_critic_values(lib.ptr(cri.flat_params), cri.obs_dim, cri.activation_id,
                                                   lib.ptr(d.critic_obs), lib.ptr(d.value_preds), rows,

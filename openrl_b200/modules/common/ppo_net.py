@@ -32,6 +32,16 @@ class PPONet:
         self.rnn_states_actor, self.masks = None, None
 
     def act(self, observation, action_masks=None, deterministic=False, episode_starts=None):
+        if self.cfg.use_recurrent_policy:
+            if episode_starts is not None and self.rnn_states_actor is not None:
+                # reset_rnn_states (ppo_net.py:33-47): zero the hidden state of every agent of a restarted env
+                keep = 1.0 - np.repeat(np.asarray(episode_starts, dtype=np.float32), self.env.agent_num)
+                keep = torch.as_tensor(keep, dtype=torch.float32).to(self.device)[:, None, None]
+                self.rnn_states_actor = torch.as_tensor(self.rnn_states_actor, dtype=torch.float32).to(self.device) * keep
+            actions, _, self.rnn_states_actor = self.module.act(
+                obs=observation, rnn_states_actor=self.rnn_states_actor, masks=self.masks, action_masks=action_masks,
+                deterministic=deterministic)
+            return actions, self.rnn_states_actor
         actions, _ = self.module.act(obs=observation, rnn_states_actor=self.rnn_states_actor, masks=self.masks,
                                      action_masks=action_masks, deterministic=deterministic)
         return actions, self.rnn_states_actor

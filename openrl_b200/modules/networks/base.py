@@ -50,6 +50,24 @@ class MLPBase(nn.Module):
         return self.hidden_size
 
 
+class RNNLayer(nn.Module):
+    """rnn.py:5-28: one-layer nn.GRU (orthogonal weights, zero biases) followed by LayerNorm.  Only the
+    parameter tree / initialisation lives here; the forward and the chunked BPTT are orl_rnn.cu."""
+
+    def __init__(self, inputs_dim, outputs_dim, recurrent_N, use_orthogonal, rnn_type="gru"):
+        super().__init__()
+        if rnn_type != "gru" or recurrent_N != 1:
+            raise NotImplementedError("the recurrent kernels are built for rnn_type == 'gru' and recurrent_N == 1 "
+                                      "(the reference defaults)")
+        self.rnn = nn.GRU(inputs_dim, outputs_dim, num_layers=recurrent_N)
+        for name, param in self.rnn.named_parameters():
+            if "bias" in name:
+                nn.init.constant_(param, 0)
+            elif "weight" in name:
+                (nn.init.orthogonal_ if use_orthogonal else nn.init.xavier_uniform_)(param)
+        self.norm = nn.LayerNorm(outputs_dim)
+
+
 class Categorical(nn.Module):
     def __init__(self, num_inputs, num_outputs, use_orthogonal=True, gain=0.01):
         super().__init__()

@@ -3,7 +3,7 @@ with the `value_normalizer` attribute the algorithm looks up (ppo_module.py:212-
 import torch
 import torch.nn as nn
 
-from .base import FlatParams, MLPBase, ValueNorm, _init
+from .base import FlatParams, MLPBase, RNNLayer, ValueNorm, _init
 
 
 def _critic_shape(space):
@@ -13,8 +13,10 @@ def _critic_shape(space):
 class ValueNetwork(nn.Module):
     def __init__(self, cfg, input_space, action_space=None, use_half=False, device=torch.device("cpu"), extra_args=None):
         super().__init__()
-        if cfg.use_recurrent_policy or cfg.use_naive_recurrent_policy:
-            raise NotImplementedError("recurrent critics are the next row of the build plan (DESIGN.md)")
+        if cfg.use_naive_recurrent_policy:
+            raise NotImplementedError("use_naive_recurrent_policy (whole-trajectory BPTT) is not built; "
+                                      "use_recurrent_policy (chunked) is")
+        self.recurrent = bool(cfg.use_recurrent_policy)
         if cfg.use_popart:
             raise NotImplementedError("PopArt is a 'next' row (SURVEY.md §8f)")
         shape = _critic_shape(input_space)
@@ -23,6 +25,8 @@ class ValueNetwork(nn.Module):
         self.obs_dim = shape[0]
         self.activation_id = cfg.activation_id
         self.base = MLPBase(cfg, shape)
+        if self.recurrent:
+            self.rnn = RNNLayer(self.base.output_size, self.base.output_size, cfg.recurrent_N, cfg.use_orthogonal, cfg.rnn_type)
         self.v_out = _init(nn.Linear(self.base.output_size, 1), 1.0, cfg.use_orthogonal)
         self.device = torch.device(device)
         self._flat = FlatParams(self, self.device)

@@ -84,6 +84,8 @@ class PPOModule:
         pol = self.models["policy"]
         obs = torch.as_tensor(obs, dtype=torch.float32).to(self.device).contiguous().view(-1, pol.obs_dim)
         rows = obs.shape[0]
+        if getattr(pol, "recurrent", False):
+            return self._act_recurrent(pol, obs, rnn_states_actor, masks, deterministic, exp_noise, rng_seed, rng_step)
         act_w = pol.n_actions if pol.head_kind == lib.HEAD_GAUSSIAN else 1
         actions = torch.empty(rows, act_w, dtype=torch.float32, device=self.device)
         logp = torch.empty(rows, act_w, dtype=torch.float32, device=self.device)
@@ -101,6 +103,32 @@ class PPOModule:
         a.head_kind = pol.head_kind
         lib.check(self._lib.orl_rollout(a, lib.current_stream()), "orl_rollout(act)")
         return actions, logp
+
+    def _act_recurrent(self, pol, obs, rnn_states_actor, masks, deterministic, exp_noise, rng_seed, rng_step):
+        """One GRU policy step on a (rows, d) batch: returns (actions, log-probs, new rnn states (rows, 1, H))
+        (policy_network.py:130-162 with RNNLayer; orl_rnn_rollout with ENV_NONE)."""
+        rows, H = obs.shape[0], pol.hidden_size
+        states = torch.zeros(2, rows, H, dtype=torch.float32, device=self.device)
+        if rnn_states_actor is not None:
+            states[0].copy_(torch.as_tensor(rnn_states_actor, dtype=torch.float32).to(self.device).reshape(rows, H))
+        mk = torch.ones(rows, dtype=torch.float32, device=self.device)
+        if masks is not None:
+            mk.copy_(torch.as_tensor(masks, dtype=torch.float32).to(self.device).reshape(rows))
+        actions = torch.empty(rows, 1, dtype=torch.float32, device=self.device)
+        logp = torch.empty(rows, 1, dtype=torch.float32, device=self.device)
+        noise = None if exp_noise is None else torch.as_tensor(exp_noise, dtype=torch.float32).to(self.device).contiguous()
+        a = lib.OrlRnnArgs()
+        a.env_kind, a.n_envs, a.n_agents, a.episode_length = lib.ENV_NONE, rows, 1, 1
+        a.t_begin, a.t_end = 0, 1
+        a.obs_dim, a.critic_obs_dim, a.n_actions = pol.obs_dim, pol.obs_dim, pol.n_actions
+        a.activation_id, a.deterministic = pol.activation_id, int(bool(deterministic))
+        a.policy_params, a.policy_obs = lib.ptr(pol.flat_params), lib.ptr(obs)
+        a.rnn_states, a.masks = lib.ptr(states), lib.ptr(mk)
+        a.actions, a.action_log_probs = lib.ptr(actions), lib.ptr(logp)
+        a.exp_noise = lib.ptr(noise)
+        a.rng_seed, a.rng_step_base = int(rng_seed), int(rng_step)
+        lib.check(self._lib.orl_rnn_rollout(a, lib.current_stream()), "orl_rnn_rollout(act)")
+        return actions, logp, states[1].view(rows, 1, H)
 
     @staticmethod
     def init_rnn_states(rollout_num, agent_num, rnn_layers, hidden_size):

@@ -79,6 +79,8 @@ class PPOAgent:
 
     def act(self, observation, info=None, deterministic=True, episode_starts=None):
         """ppo_agent.py:134-158: observation (N, A, d) -> actions (N, A, 1) numpy."""
+        if isinstance(observation, dict):   # Dict spaces: the actor reads the "policy" entry (policy_network.py:137-139)
+            observation = observation["policy"]
         obs = np.asarray(observation, dtype=np.float32)
         N, A = obs.shape[0], obs.shape[1]
         actions, _ = self.net.act(obs.reshape(N * A, -1), deterministic=deterministic, episode_starts=episode_starts)
