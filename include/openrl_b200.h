@@ -302,7 +302,7 @@ typedef struct OrlRnnArgs {
     double* env_f64; uint64_t* env_u64; int32_t* env_i32; const int32_t* env_table;
     float* ep_return; int32_t* ep_length; double* episode_stats;
     const double* gae_stats; const double* mb_stats; float* vn_state;
-    float* tape;                                          /* workspace: (n_chunks*L, orl_rnn_tape_width()) floats, one net at a time */
+    float* tape;                                          /* workspace: orl_rnn_workspace_floats(n_chunks*L, grads_stride) floats (tape rows, then reduction partials) */
     float* grads;                                         /* (2, grads_stride) true gradients, policy then critic */
     int32_t grads_stride; int32_t reserved1;
     float* loss_acc;                                      /* (8) zeroed by orl_rnn_fwdbwd: policy_loss, entropy, ratio, value_loss sums */
@@ -315,6 +315,8 @@ typedef struct OrlRnnArgs {
 } OrlRnnArgs;
 int orl_rnn_param_count(int obs_dim, int n_out);
 int orl_rnn_tape_width(void);
+/* floats of OrlRnnArgs.tape for a minibatch of `rows` = n_chunks * chunk_length row-steps */
+long long orl_rnn_workspace_floats(long long rows, int grads_stride);
 /* policy GRU rollout for steps [t_begin, t_end) fused with the device env (simple_spread, CartPole, GridWorld) */
 int orl_rnn_rollout(const OrlRnnArgs* args, void* stream);
 /* recurrent critic over slots 0..T: value_preds[t] and rnn_states_critic[t+1] */

@@ -176,9 +176,9 @@ class PPOAlgorithm:
         data_chunks = total // L
         mbc = data_chunks // self.num_mini_batch
         rows = mbc * L
-        width = self._lib.orl_rnn_tape_width()
-        if self.tape is None or self.tape.shape[0] < rows:
-            self.tape = torch.empty(rows, width, dtype=torch.float32, device=self.device)
+        need = int(self._lib.orl_rnn_workspace_floats(rows, self.rnn_stride))   # tape rows + reduction partials
+        if self.tape is None or self.tape.numel() < need:
+            self.tape = torch.empty(need, dtype=torch.float32, device=self.device)
         whole = self.num_mini_batch == 1 and rows == total
         s, Lb = lib.current_stream(), self._lib
         lane = torch.arange(L, device=self.device)
@@ -202,7 +202,7 @@ class PPOAlgorithm:
                 a = self._rnn_args(buf, ids, mb_stats)
                 lib.check(Lb.orl_rnn_fwdbwd(a, s), "orl_rnn_fwdbwd")
                 lib.check(Lb.orl_rnn_apply(a, s), "orl_rnn_apply")
-                self.gpu_launches += 5
+                self.gpu_launches += 9   # 2 x (chunk, tape gemm, tape colsum, partial sum) + apply
 
     def train(self, buffer, turn_on=True):
         """train_ppo (ppo.py:383-458).  `buffer` is the device ReplayData whose returns/advantages

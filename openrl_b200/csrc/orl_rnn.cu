@@ -7,24 +7,28 @@
 //   ReplayData.recurrent_generator        openrl/buffers/replay_data.py:1062-1258 (chunks of L over f=(n*A+a)*T+t)
 //   PPOAlgorithm.ppo_update (BPTT part)   openrl/algorithms/ppo.py:46-458
 //
-// Correctness-first design (DESIGN.md "recurrent path"): every kernel is a thin wrapper that runs the
-// sequential core of orl_rnn_core.h — the same source the CPU test checks against the torch oracle — with one
-// thread per env (rollout), per row (critic) or per chunk (update).  Parameter gradients are reductions of the
-// per-row tape, dW = sum_rows P^T Q, done by a small staged-GEMM kernel with float atomics into the true-layout
-// gradient buffer.  This path is latency/occupancy bound by construction; it exists so that recurrent configs
-// run on the device with reference numerics, not to set a speed record (the feed-forward path is the fast one).
+// Design (DESIGN.md "recurrent path"): ONE WARP per env (rollout), per row (critic) or per chunk (update) running
+// the warp-cooperative step of orl_rnn_warp.cuh — 64-vectors as two registers per lane, the net's weights staged
+// once per persistent CTA in 136 KB of shared memory, mat-vecs by shuffle broadcast (shared-memory-bandwidth
+// bound: one LDS per FMA).  The update writes a per-row-step tape (forward activations, local gradients);
+// parameter gradients are reductions of the tape, dW = sum_rows P^T Q, by a staged-GEMM kernel with float atomics
+// into the true-layout gradient buffer.  The sequential restatement of the same step (orl_rnn_core.h, pinned to
+// the torch oracle on the CPU) serves PPOModule.act and is the element-wise checker of the warp path
+// (tests/debug_gru.py).
 #include <algorithm>
 
 #include "orl_envstep.cuh"
 #include "orl_loss.cuh"
 #include "orl_rnn_core.h"
+#include "orl_rnn_warp.cuh"
 
 namespace {
 using namespace orl;
 namespace rc = orl_rnn;
+namespace rw = orl_rnnw;
 
 static_assert(rc::MAXN == MAX_OUT, "head width limits must agree");
-constexpr int LMAX = 4;      // data_chunk_length limit (StepSave is 2.6 KB per step of per-thread local memory)
+constexpr int LMAX = 4;      // data_chunk_length limit accepted by the host API (the tape is sized n_chunks * L rows)
 constexpr int RNN_NT = 64;   // threads per CTA of the sequential kernels
 
 __device__ __forceinline__ int pick_action(const OrlRnnArgs& a, const float (&pr)[MAX_OUT], int n, size_t grow, int row,
@@ -51,147 +55,185 @@ __device__ __forceinline__ int pick_action(const OrlRnnArgs& a, const float (&pr
     return sample_categorical(pr, n, q);
 }
 
-// ---- rollout: one thread per env; policy GRU step for each agent row, then env.step ----
-template <int ENV>
-__global__ void __launch_bounds__(RNN_NT) rnn_rollout_kernel(const OrlRnnArgs a) {
-    constexpr int A = ENV == ORL_ENV_MPE_SPREAD ? 3 : 1;
-    constexpr int DX = ENV == ORL_ENV_MPE_SPREAD ? 18 : (ENV == ORL_ENV_NONE ? rc::MAXD : 4);
-    const int D = ENV == ORL_ENV_NONE ? a.obs_dim : DX;
-    const int N = a.n_envs, B = N * A, n = a.n_actions;
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= N) return;
-    const rc::Offsets o = rc::rnn_offsets(D, n);
-    const float* P = a.policy_params;
-    EnvPtrs E{a.env_f64, a.env_u64, a.env_i32, a.env_table, a.env_table_len, a.rng_seed, a.ep_return, a.ep_length, a.episode_stats};
+// ---- act only (PPOModule.act / PPONet.act): one thread per row runs the sequential core; the caller owns env.step ----
+__global__ void __launch_bounds__(RNN_NT) rnn_act_kernel(const OrlRnnArgs a) {
+    const int B = a.n_envs, n = a.n_actions, d = a.obs_dim;
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= B) return;
+    const rc::Offsets o = rc::rnn_offsets(d, n);
     const uint64_t rng_base = a.rng_step_base + (a.rng_counter ? *a.rng_counter : 0ull);
-
     for (int t = a.t_begin; t < a.t_end; ++t) {
-        int acts[A];
-        for (int ag = 0; ag < A; ++ag) {
-            const int row = e * A + ag;
-            const size_t grow = (size_t)t * B + row;
-            float x[DX], h[rc::H], hn[rc::H], logit[MAX_OUT];
-            for (int k = 0; k < D; ++k) x[k] = a.policy_obs[grow * D + k];
-            for (int j = 0; j < rc::H; ++j) h[j] = a.rnn_states[grow * rc::H + j];
-            rc::rnn_step_forward(P, o, a.activation_id, x, h, a.masks[grow], hn, logit, nullptr, nullptr);
-            // tentative next state; zeroed below if the env finishes (onpolicy_driver.py:262-269)
-            for (int j = 0; j < rc::H; ++j) a.rnn_states[((size_t)(t + 1) * B + row) * rc::H + j] = hn[j];
+        const size_t grow = (size_t)t * B + row;
+        float x[rc::MAXD], h[rc::H], hn[rc::H], logit[MAX_OUT];
+        for (int k = 0; k < rc::MAXD; ++k) x[k] = k < d ? a.policy_obs[grow * d + k] : 0.f;
+        for (int j = 0; j < rc::H; ++j) h[j] = a.rnn_states[grow * rc::H + j];
+        rc::rnn_step_forward(a.policy_params, o, a.activation_id, x, h, a.masks[grow], hn, logit, nullptr, nullptr);
+        for (int j = 0; j < rc::H; ++j) a.rnn_states[((size_t)(t + 1) * B + row) * rc::H + j] = hn[j];
 #pragma unroll
-            for (int j = 0; j < MAX_OUT; ++j) if (j >= n) logit[j] = 0.f;
-            float nl[MAX_OUT], pr[MAX_OUT];
-            log_softmax_n(logit, n, nl, pr);
-            const int act = pick_action(a, pr, n, grow, row, t, rng_base);
-            float lp = nl[0];
+        for (int j = 0; j < MAX_OUT; ++j) if (j >= n) logit[j] = 0.f;
+        float nl[MAX_OUT], pr[MAX_OUT];
+        log_softmax_n(logit, n, nl, pr);
+        const int act = pick_action(a, pr, n, grow, row, t, rng_base);
+        float lp = nl[0];
 #pragma unroll
-            for (int j = 1; j < MAX_OUT; ++j) if (j == act) lp = nl[j];
-            a.actions[grow] = (float)act;
-            a.action_log_probs[grow] = lp;
-            acts[ag] = act;
-        }
-        if constexpr (ENV == ORL_ENV_NONE) continue;   // act only (PPOModule.act): the caller owns env.step and the masks
-        bool done = false; float reward = 0.f;
-        if constexpr (ENV == ORL_ENV_MPE_SPREAD) {
-            float ob[3][18];
-            const int acts3[3] = {acts[0], acts[1], acts[2]};
-            env_step_mpe(E, e, N, acts3, ob, reward, done);
-            const size_t r1 = (size_t)(t + 1) * B + (size_t)e * 3;
-            for (int ag = 0; ag < 3; ++ag) {
-                for (int k = 0; k < 18; ++k) {
-                    a.policy_obs[(r1 + ag) * 18 + k] = ob[ag][k];
-                    for (int dst = 0; dst < 3; ++dst) a.critic_obs[(r1 + dst) * 54 + ag * 18 + k] = ob[ag][k];
-                }
-            }
-        } else if constexpr (ENV != ORL_ENV_NONE) {
-            float ob[4], fin[4];
-            env_step_single(E, ENV, e, N, acts[0], ob, reward, done, fin);
-            const size_t o1 = (size_t)(t + 1) * B + e;
-            for (int k = 0; k < 4; ++k) {
-                a.policy_obs[o1 * 4 + k] = ob[k];
-                if (a.critic_obs != a.policy_obs) a.critic_obs[o1 * 4 + k] = ob[k];
-            }
-        }
-        for (int ag = 0; ag < A; ++ag) {
-            const size_t r1 = (size_t)(t + 1) * B + (size_t)e * A + ag;
-            a.rewards[(size_t)t * B + (size_t)e * A + ag] = reward;
-            a.masks[r1] = done ? 0.f : 1.f;
-            a.active_masks[r1] = 1.f;
-            if (done) for (int j = 0; j < rc::H; ++j) a.rnn_states[r1 * rc::H + j] = 0.f;
-        }
+        for (int j = 1; j < MAX_OUT; ++j) if (j == act) lp = nl[j];
+        a.actions[grow] = (float)act;
+        a.action_log_probs[grow] = lp;
     }
 }
 
 __global__ void rnn_bump_counter_kernel(uint64_t* c, uint64_t by) { *c += by; }
 
-// ---- recurrent critic over all T+1 slots: one thread per row ----
-__global__ void __launch_bounds__(RNN_NT) rnn_critic_kernel(const OrlRnnArgs a) {
-    const int B = a.n_envs * a.n_agents, T = a.episode_length, dc = a.critic_obs_dim;
-    const int row = blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= B) return;
-    const rc::Offsets o = rc::rnn_offsets(dc, 1);
-    const float* P = a.critic_params;
-    float h[rc::H], hn[rc::H], x[rc::MAXD], out[MAX_OUT];
-    for (int j = 0; j < rc::H; ++j) h[j] = a.rnn_states_critic[(size_t)row * rc::H + j];
-    for (int t = 0; t <= T; ++t) {
-        const size_t grow = (size_t)t * B + row;
-        for (int k = 0; k < dc; ++k) x[k] = a.critic_obs[grow * dc + k];
-        rc::rnn_step_forward(P, o, a.activation_id, x, h, a.masks[grow], hn, out, nullptr, nullptr);
-        a.value_preds[grow] = out[0];
-        if (t < T) {
-            const float keep = a.masks[grow + B] == 0.f ? 0.f : 1.f;   // rnn_states_critic[dones_env] = 0
-            for (int j = 0; j < rc::H; ++j) { h[j] = hn[j] * keep; a.rnn_states_critic[(grow + B) * rc::H + j] = h[j]; }
+constexpr int W_NT = 512, W_WPC = W_NT / 32;   // one persistent CTA per SM, 16 warps, weights of one net in smem
+
+// ---- rollout: one warp per env; policy GRU step of each agent row, env.step on lane 0 ----
+template <int ENV>
+__global__ void __launch_bounds__(W_NT, 1) rnn_rollout_warp_kernel(const OrlRnnArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    constexpr int A = ENV == ORL_ENV_MPE_SPREAD ? 3 : 1;
+    constexpr int D = ENV == ORL_ENV_MPE_SPREAD ? 18 : 4;
+    const int N = a.n_envs, B = N * A, n = a.n_actions;
+    const rc::Offsets o = rc::rnn_offsets(D, n);
+    const rw::SmemNet W = rw::load_net(smem, a.policy_params, o, threadIdx.x, W_NT);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    EnvPtrs E{a.env_f64, a.env_u64, a.env_i32, a.env_table, a.env_table_len, a.rng_seed, a.ep_return, a.ep_length, a.episode_stats};
+    const uint64_t rng_base = a.rng_step_base + (a.rng_counter ? *a.rng_counter : 0ull);
+    for (int e = blockIdx.x * W_WPC + warp; e < N; e += gridDim.x * W_WPC) {
+        for (int t = a.t_begin; t < a.t_end; ++t) {
+            int acts[A];
+            rw::V2 hn[A];
+#pragma unroll
+            for (int ag = 0; ag < A; ++ag) {
+                const int row = e * A + ag;
+                const size_t grow = (size_t)t * B + row;
+                const float* ob = a.policy_obs + grow * D;
+                const rw::V2 x{lane < D ? ob[lane] : 0.f, lane + 32 < D ? ob[lane + 32] : 0.f};
+                const rw::V2 h = rw::ldv(a.rnn_states + grow * rc::H, lane);
+                float logit[MAX_OUT];
+                rw::step_forward(W, D, n, a.activation_id, x, h, a.masks[grow], hn[ag], logit, nullptr, lane);
+                float nl[MAX_OUT], pr[MAX_OUT];
+                log_softmax_n(logit, n, nl, pr);                 // identical on every lane
+                const int act = pick_action(a, pr, n, grow, row, t, rng_base);
+                float lp = nl[0];
+#pragma unroll
+                for (int j = 1; j < MAX_OUT; ++j) if (j == act) lp = nl[j];
+                if (lane == 0) { a.actions[grow] = (float)act; a.action_log_probs[grow] = lp; }
+                acts[ag] = act;
+            }
+            int done_i = 0;
+            if (lane == 0) {
+                bool done = false; float reward = 0.f;
+                if constexpr (ENV == ORL_ENV_MPE_SPREAD) {
+                    float ob[3][18];
+                    const int acts3[3] = {acts[0], acts[A > 1 ? 1 : 0], acts[A > 2 ? 2 : 0]};
+                    env_step_mpe(E, e, N, acts3, ob, reward, done);
+                    const size_t r1 = (size_t)(t + 1) * B + (size_t)e * 3;
+                    for (int ag = 0; ag < 3; ++ag)
+                        for (int k = 0; k < 18; ++k) {
+                            a.policy_obs[(r1 + ag) * 18 + k] = ob[ag][k];
+                            for (int dst = 0; dst < 3; ++dst) a.critic_obs[(r1 + dst) * 54 + ag * 18 + k] = ob[ag][k];
+                        }
+                } else {
+                    float ob[4], fin[4];
+                    env_step_single(E, ENV, e, N, acts[0], ob, reward, done, fin);
+                    const size_t o1 = (size_t)(t + 1) * B + e;
+                    for (int k = 0; k < 4; ++k) {
+                        a.policy_obs[o1 * 4 + k] = ob[k];
+                        if (a.critic_obs != a.policy_obs) a.critic_obs[o1 * 4 + k] = ob[k];
+                    }
+                }
+                for (int ag = 0; ag < A; ++ag) {
+                    const size_t r1 = (size_t)(t + 1) * B + (size_t)e * A + ag;
+                    a.rewards[(size_t)t * B + (size_t)e * A + ag] = reward;
+                    a.masks[r1] = done ? 0.f : 1.f;
+                    a.active_masks[r1] = 1.f;
+                }
+                done_i = done ? 1 : 0;
+            }
+            done_i = __shfl_sync(0xffffffffu, done_i, 0);
+#pragma unroll
+            for (int ag = 0; ag < A; ++ag) {   // rnn_states[dones_env] = 0 (onpolicy_driver.py:262-269)
+                const size_t r1 = (size_t)(t + 1) * B + (size_t)e * A + ag;
+                rw::stv(a.rnn_states + r1 * rc::H, lane, done_i ? rw::V2{0.f, 0.f} : hn[ag]);
+            }
+            __syncwarp();   // lane 0's observation / mask writes are read by the whole warp in the next step
         }
     }
 }
 
-// ---- update: one thread per chunk; L forward steps with saves, per-step loss, L backward steps ----
+// ---- recurrent critic over all T+1 slots: one warp per row ----
+__global__ void __launch_bounds__(W_NT, 1) rnn_critic_warp_kernel(const OrlRnnArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    const int B = a.n_envs * a.n_agents, T = a.episode_length, dc = a.critic_obs_dim;
+    const rc::Offsets o = rc::rnn_offsets(dc, 1);
+    const rw::SmemNet W = rw::load_net(smem, a.critic_params, o, threadIdx.x, W_NT);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int row = blockIdx.x * W_WPC + warp; row < B; row += gridDim.x * W_WPC) {
+        rw::V2 h = rw::ldv(a.rnn_states_critic + (size_t)row * rc::H, lane);
+        for (int t = 0; t <= T; ++t) {
+            const size_t grow = (size_t)t * B + row;
+            const float* ob = a.critic_obs + grow * dc;
+            const rw::V2 x{lane < dc ? ob[lane] : 0.f, lane + 32 < dc ? ob[lane + 32] : 0.f};
+            rw::V2 hn; float out[MAX_OUT];
+            rw::step_forward(W, dc, 1, a.activation_id, x, h, a.masks[grow], hn, out, nullptr, lane);
+            if (lane == 0) a.value_preds[grow] = out[0];
+            if (t < T) {
+                const float keep = a.masks[grow + B] == 0.f ? 0.f : 1.f;   // rnn_states_critic[dones_env] = 0
+                h = rw::V2{hn.a * keep, hn.b * keep};
+                rw::stv(a.rnn_states_critic + (grow + B) * rc::H, lane, h);
+            }
+        }
+    }
+}
+
+// ---- update: one warp per chunk; L forward steps (tape), per-step loss, L backward steps ----
 template <bool POLICY>
-__global__ void __launch_bounds__(RNN_NT) rnn_chunk_kernel(const OrlRnnArgs a) {
+__global__ void __launch_bounds__(W_NT, 1) rnn_chunk_warp_kernel(const OrlRnnArgs a) {
+    extern __shared__ __align__(16) float smem[];
     const int B = a.n_envs * a.n_agents, T = a.episode_length, L = a.chunk_length;
     const int d = POLICY ? a.obs_dim : a.critic_obs_dim, n = POLICY ? a.n_actions : 1;
-    const float* P = POLICY ? a.policy_params : a.critic_params;
     const float* obs = POLICY ? a.policy_obs : a.critic_obs;
     const float* states = POLICY ? a.rnn_states : a.rnn_states_critic;
     const rc::Offsets o = rc::rnn_offsets(d, n);
-    const long long cpos = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    float loss0 = 0.f, loss1 = 0.f, loss2 = 0.f;
+    const rw::SmemNet W = rw::load_net(smem, POLICY ? a.policy_params : a.critic_params, o, threadIdx.x, W_NT);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float loss0 = 0.f, loss1 = 0.f, loss2 = 0.f;   // identical on every lane; lane 0's copy is reduced
 
-    if (cpos < a.n_chunks) {
-        const double rows_d = (double)a.n_chunks * L;
-        const float inv_rows = (float)(1.0 / rows_d);
-        const float inv_act = (float)(1.0 / a.mb_stats[2]);
-        const bool pol_masks = a.flags & ORL_PPO_POLICY_ACTIVE_MASKS, val_masks = a.flags & ORL_PPO_VALUE_ACTIVE_MASKS;
-        AdvNorm advn;
-        float vn_mean = 0.f, vn_std = 1.f;
-        if (POLICY) advn = make_adv_norm(a.gae_stats, a.flags & ORL_PPO_ADV_NORMALIZE);
-        else if (a.flags & ORL_PPO_VALUENORM) {
-            float st[3];
-            vn_updated(a.vn_state, a.mb_stats, rows_d, a.vn_beta, st);
-            const VnScalars s = vn_mean_std(st);
-            vn_mean = s.mean; vn_std = s.std;
-        }
+    const double rows_d = (double)a.n_chunks * L;
+    const float inv_rows = (float)(1.0 / rows_d);
+    const float inv_act = (float)(1.0 / a.mb_stats[2]);
+    const bool pol_masks = a.flags & ORL_PPO_POLICY_ACTIVE_MASKS, val_masks = a.flags & ORL_PPO_VALUE_ACTIVE_MASKS;
+    AdvNorm advn;
+    float vn_mean = 0.f, vn_std = 1.f;
+    if (POLICY) advn = make_adv_norm(a.gae_stats, a.flags & ORL_PPO_ADV_NORMALIZE);
+    else if (a.flags & ORL_PPO_VALUENORM) {
+        float st[3];
+        vn_updated(a.vn_state, a.mb_stats, rows_d, a.vn_beta, st);
+        const VnScalars s = vn_mean_std(st);
+        vn_mean = s.mean; vn_std = s.std;
+    }
+
+    for (long long cpos = (long long)blockIdx.x * W_WPC + warp; cpos < a.n_chunks; cpos += (long long)gridDim.x * W_WPC) {
         const long long f0 = a.chunk_ids[cpos] * (long long)L;
-        rc::StepSave sv[LMAX];
-        float msk[LMAX], dl[LMAX][MAX_OUT];
-        float h[rc::H], h2[rc::H], x[rc::MAXD];
-        {
-            const long long row0 = f0 / T, t0 = f0 % T;
-            for (int j = 0; j < rc::H; ++j) h[j] = states[((size_t)t0 * B + row0) * rc::H + j];
-        }
+        rw::V2 h = rw::ldv(states + ((size_t)(f0 % T) * B + (size_t)(f0 / T)) * rc::H, lane);
         for (int l = 0; l < L; ++l) {
             const long long f = f0 + l, row = f / T, t = f % T;
             const size_t bi = (size_t)t * B + row;
-            for (int k = 0; k < rc::MAXD; ++k) x[k] = k < d ? obs[bi * d + k] : 0.f;
-            msk[l] = a.masks[bi];
+            const float* ob = obs + bi * d;
+            const rw::V2 x{lane < d ? ob[lane] : 0.f, lane + 32 < d ? ob[lane + 32] : 0.f};
+            float* tape = a.tape + ((size_t)cpos * L + l) * rw::TAPE_W;
             float out[MAX_OUT];
-            float* tape = a.tape + ((size_t)cpos * L + l) * rc::TAPE;
-            rc::rnn_step_forward(P, o, a.activation_id, x, h, msk[l], h2, out, &sv[l], tape);
-            for (int j = 0; j < rc::H; ++j) h[j] = h2[j];
+            rw::V2 h2;
+            rw::step_forward(W, d, n, a.activation_id, x, h, a.masks[bi], h2, out, tape, lane);
+            h = h2;
+            float dl[MAX_OUT];
 #pragma unroll
-            for (int j = 0; j < MAX_OUT; ++j) dl[l][j] = 0.f;
+            for (int j = 0; j < MAX_OUT; ++j) dl[j] = 0.f;
             const float active = a.active_masks[bi];
             if (POLICY) {
-#pragma unroll
-                for (int j = 0; j < MAX_OUT; ++j) if (j >= n) out[j] = 0.f;
                 float nl[MAX_OUT], pr[MAX_OUT];
                 log_softmax_n(out, n, nl, pr);
                 const int act = (int)a.actions[bi];
@@ -208,90 +250,127 @@ __global__ void __launch_bounds__(RNN_NT) rnn_chunk_kernel(const OrlRnnArgs a) {
                 const float dlp = pg.dlogp * wrow, went = a.entropy_coef * wrow;
 #pragma unroll
                 for (int j = 0; j < MAX_OUT; ++j)
-                    if (j < n) dl[l][j] = dlp * ((j == act ? 1.f : 0.f) - pr[j]) + went * pr[j] * (nl[j] + ent);
+                    if (j < n) dl[j] = dlp * ((j == act ? 1.f : 0.f) - pr[j]) + went * pr[j] * (nl[j] + ent);
             } else {
                 const float ret = a.returns[bi];
                 const float target = (a.flags & ORL_PPO_VALUENORM) ? (ret - vn_mean) / vn_std : ret;
                 const ValueTerm vt = value_term(out[0], a.value_preds[bi], target, a.clip_param, a.huber_delta, a.flags);
                 const float wrow = val_masks ? active * inv_act : inv_rows;
                 loss0 += vt.loss * wrow;
-                dl[l][0] = a.value_loss_coef * wrow * vt.dv;
+                dl[0] = a.value_loss_coef * wrow * vt.dv;
             }
+            float mine = 0.f;   // lane m < 8 stores dL/dout[m]
+#pragma unroll
+            for (int j = 0; j < MAX_OUT; ++j) if (lane == j) mine = dl[j];
+            if (lane < MAX_OUT) tape[rc::TP_DLOG + lane] = mine;
         }
-        float dh[rc::H], dhp[rc::H];
-        for (int j = 0; j < rc::H; ++j) dh[j] = 0.f;
-        for (int l = L - 1; l >= 0; --l) {
-            float* tape = a.tape + ((size_t)cpos * L + l) * rc::TAPE;
-            rc::rnn_step_backward(P, o, a.activation_id, sv[l], msk[l], dl[l], dh, dhp, tape);
-            for (int j = 0; j < rc::H; ++j) dh[j] = dhp[j];
-        }
+        __syncwarp();   // tape scalars (lane 0) and dL/dout (lanes < 8) are read by every lane below
+        rw::V2 dh{0.f, 0.f};
+        for (int l = L - 1; l >= 0; --l)
+            dh = rw::step_backward(W, n, a.activation_id, a.tape + ((size_t)cpos * L + l) * rw::TAPE_W, dh, lane);
     }
-    __shared__ float red[3][RNN_NT / 32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    loss0 = warp_sum(loss0); loss1 = warp_sum(loss1); loss2 = warp_sum(loss2);
+    __shared__ float red[3][W_WPC];
     if (lane == 0) { red[0][warp] = loss0; red[1][warp] = loss1; red[2][warp] = loss2; }
     __syncthreads();
     if (threadIdx.x < 3) {
         float s = 0.f;
-        for (int w = 0; w < RNN_NT / 32; ++w) s += red[threadIdx.x][w];
+        for (int w = 0; w < W_WPC; ++w) s += red[threadIdx.x][w];
         if (POLICY) atomicAdd(a.loss_acc + threadIdx.x, s);
         else if (threadIdx.x == 0) atomicAdd(a.loss_acc + 3, s);
     }
 }
 
-// ---- tape reductions: out[m*ldo + k] += sum_rows tape[r][p_off+m] * tape[r][q_off+k]  (q_off < 0: Q == 1) ----
-struct TapeJob { int p_off, M, q_off, N, out_off, ldo; };
-constexpr int MAX_JOBS = 17;
-struct TapeJobs { TapeJob j[MAX_JOBS]; int count; };
-constexpr int TR_NT = 256, TR_ROWS = 256, TR_SUB = 16, TR_ACC = (rc::G3 * rc::H) / TR_NT;
+// ---- tape reductions (deterministic, two stages) ----
+// Stage 1: every CTA owns TR_ROWS tape rows and one job and writes its partial result to partials[row_block][...]:
+//   gemm job   part[out_off + m*N + k] = sum_rows tape[r][p_off+m] * tape[r][q_off+k]     (register-tiled, 12x4 per thread)
+//   column job part[out_off + m]       = sum_rows tape[r][p_off+m]
+// Stage 2: grads[i] = sum over row blocks of partials[rb][i], fixed order.
+struct TapeJob { int p_off, M, q_off, N, out_off; };
+constexpr int MAX_GEMM_JOBS = 5, MAX_COL_JOBS = 11;
+struct TapeJobs { TapeJob gemm[MAX_GEMM_JOBS]; TapeJob col[MAX_COL_JOBS]; int n_gemm, n_col; };
+constexpr int TR_NT = 256, TR_ROWS = 1024, TR_SUB = 32, TR_MI = rc::G3 / 16;   // 16 x 16 threads; thread tile (M/16) x 4
 
-__global__ void __launch_bounds__(TR_NT) tape_reduce_kernel(const float* __restrict__ tape, long long rows, TapeJobs jobs,
-                                                            float* __restrict__ grads) {
-    const TapeJob jb = jobs.j[blockIdx.y];
+__global__ void __launch_bounds__(TR_NT) tape_gemm_kernel(const float* __restrict__ tape, long long rows, TapeJobs jobs,
+                                                          float* __restrict__ partials, int stride) {
+    const TapeJob jb = jobs.gemm[blockIdx.y];
     const long long r_begin = (long long)blockIdx.x * TR_ROWS;
     const int rows_here = (int)min((long long)TR_ROWS, rows - r_begin);
-    __shared__ float Ps[TR_SUB][rc::G3];
-    __shared__ float Qs[TR_SUB][rc::H];
-    const int tid = threadIdx.x, MN = jb.M * jb.N;
-    float acc[TR_ACC];
+    __shared__ __align__(16) float Ps[TR_SUB][rc::G3];
+    __shared__ __align__(16) float Qs[TR_SUB][rc::H];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int MI = (jb.M + 15) >> 4;
+    float acc[TR_MI][4];
 #pragma unroll
-    for (int i = 0; i < TR_ACC; ++i) acc[i] = 0.f;
+    for (int i = 0; i < TR_MI; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
     for (int s0 = 0; s0 < rows_here; s0 += TR_SUB) {
         const int sub = min(TR_SUB, rows_here - s0);
-        for (int i = tid; i < TR_SUB * jb.M; i += TR_NT) {
-            const int r = i / jb.M, m = i % jb.M;
-            Ps[r][m] = r < sub ? tape[(size_t)(r_begin + s0 + r) * rc::TAPE + jb.p_off + m] : 0.f;
+        const int Mp = MI * 16;
+        for (int i = tid; i < TR_SUB * Mp; i += TR_NT) {
+            const int r = i / Mp, m = i % Mp;
+            Ps[r][m] = (r < sub && m < jb.M) ? tape[(size_t)(r_begin + s0 + r) * rw::TAPE_W + jb.p_off + m] : 0.f;
         }
-        for (int i = tid; i < TR_SUB * jb.N; i += TR_NT) {
-            const int r = i / jb.N, k = i % jb.N;
-            Qs[r][k] = r < sub ? (jb.q_off < 0 ? 1.f : tape[(size_t)(r_begin + s0 + r) * rc::TAPE + jb.q_off + k]) : 0.f;
+        for (int i = tid; i < TR_SUB * rc::H; i += TR_NT) {
+            const int r = i >> 6, k = i & 63;
+            Qs[r][k] = (r < sub && k < jb.N) ? tape[(size_t)(r_begin + s0 + r) * rw::TAPE_W + jb.q_off + k] : 0.f;
         }
         __syncthreads();
+#pragma unroll 4
+        for (int r = 0; r < TR_SUB; ++r) {
+            const float4 q = *reinterpret_cast<const float4*>(&Qs[r][4 * tx]);
 #pragma unroll
-        for (int i = 0; i < TR_ACC; ++i) {
-            const int idx = tid + i * TR_NT;
-            if (idx < MN) {
-                const int m = idx / jb.N, k = idx % jb.N;
-                float s = acc[i];
-#pragma unroll
-                for (int r = 0; r < TR_SUB; ++r) s = fmaf(Ps[r][m], Qs[r][k], s);
-                acc[i] = s;
+            for (int i = 0; i < TR_MI; ++i) {
+                if (i < MI) {
+                    const float p = Ps[r][ty + 16 * i];
+                    acc[i][0] = fmaf(p, q.x, acc[i][0]); acc[i][1] = fmaf(p, q.y, acc[i][1]);
+                    acc[i][2] = fmaf(p, q.z, acc[i][2]); acc[i][3] = fmaf(p, q.w, acc[i][3]);
+                }
             }
         }
         __syncthreads();
     }
+    float* part = partials + (size_t)blockIdx.x * stride + jb.out_off;
 #pragma unroll
-    for (int i = 0; i < TR_ACC; ++i) {
-        const int idx = tid + i * TR_NT;
-        if (idx < MN) atomicAdd(grads + jb.out_off + (idx / jb.N) * jb.ldo + (idx % jb.N), acc[i]);
+    for (int i = 0; i < TR_MI; ++i) {
+        const int m = ty + 16 * i;
+        if (i < MI && m < jb.M) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { const int k = 4 * tx + c; if (k < jb.N) part[m * jb.N + k] = acc[i][c]; }
+        }
     }
+}
+
+__global__ void __launch_bounds__(rc::G3) tape_colsum_kernel(const float* __restrict__ tape, long long rows, TapeJobs jobs,
+                                                             float* __restrict__ partials, int stride) {
+    const TapeJob jb = jobs.col[blockIdx.y];
+    const long long r_begin = (long long)blockIdx.x * TR_ROWS;
+    const int rows_here = (int)min((long long)TR_ROWS, rows - r_begin);
+    const int m = threadIdx.x;
+    if (m >= jb.M) return;
+    const float* p = tape + (size_t)r_begin * rw::TAPE_W + jb.p_off + m;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int r = 0;
+    for (; r + 4 <= rows_here; r += 4) {
+        s0 += p[(size_t)r * rw::TAPE_W]; s1 += p[(size_t)(r + 1) * rw::TAPE_W];
+        s2 += p[(size_t)(r + 2) * rw::TAPE_W]; s3 += p[(size_t)(r + 3) * rw::TAPE_W];
+    }
+    for (; r < rows_here; ++r) s0 += p[(size_t)r * rw::TAPE_W];
+    partials[(size_t)blockIdx.x * stride + jb.out_off + m] = (s0 + s1) + (s2 + s3);
+}
+
+__global__ void tape_partial_sum_kernel(const float* __restrict__ partials, int row_blocks, int stride, int total,
+                                        float* __restrict__ grads) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    float s = 0.f;
+    for (int rb = 0; rb < row_blocks; ++rb) s += partials[(size_t)rb * stride + i];
+    grads[i] = s;
 }
 
 TapeJobs make_jobs(int d, int n) {
     const rc::Offsets o = rc::rnn_offsets(d, n);
-    TapeJobs t; int c = 0;
-    auto gemm = [&](int p, int M, int q, int N, int out) { t.j[c++] = TapeJob{p, M, q, N, out, N}; };
-    auto col = [&](int p, int M, int out) { t.j[c++] = TapeJob{p, M, -1, 1, out, 1}; };
+    TapeJobs t; int g = 0, c = 0;
+    auto gemm = [&](int p, int M, int q, int N, int out) { t.gemm[g++] = TapeJob{p, M, q, N, out}; };
+    auto col = [&](int p, int M, int out) { t.col[c++] = TapeJob{p, M, -1, 1, out}; };
     gemm(rc::TP_DZ1, rc::H, rc::TQ_X, d, o.w1);     col(rc::TP_DZ1, rc::H, o.b1);
     col(rc::TS_DY1N1, rc::H, o.g1);                  col(rc::TS_DY1, rc::H, o.be1);
     gemm(rc::TP_DZ3, rc::H, rc::TQ_Y1, rc::H, o.w3); col(rc::TP_DZ3, rc::H, o.b3);
@@ -300,9 +379,13 @@ TapeJobs make_jobs(int d, int n) {
     col(rc::TP_DGI, rc::G3, o.bih);                  col(rc::TP_DGH, rc::G3, o.bhh);
     col(rc::TS_DONO, rc::H, o.gr);                   col(rc::TS_DO, rc::H, o.ber);
     gemm(rc::TP_DLOG, n, rc::TQ_O, rc::H, o.wh);     col(rc::TP_DLOG, n, o.bh);
-    t.count = c;
+    t.n_gemm = g; t.n_col = c;
     return t;
 }
+
+// workspace = tape (rows x TAPE_W) followed by the reduction partials (row blocks x grads_stride)
+long long ws_tape_floats(long long rows) { return rows * rw::TAPE_W; }
+int ws_row_blocks(long long rows) { return (int)((rows + TR_ROWS - 1) / TR_ROWS); }
 
 // ---- optimizer: per-net global-norm clip + Adam on the true-layout gradients (one CTA per net) ----
 __global__ void __launch_bounds__(1024) rnn_apply_kernel(const OrlRnnArgs a) {
@@ -364,6 +447,16 @@ __global__ void __launch_bounds__(1024) rnn_apply_kernel(const OrlRnnArgs a) {
     }
 }
 
+constexpr size_t W_SMEM = (size_t)rw::smem_net_floats() * sizeof(float);
+template <typename K>
+int warp_kernel_prepare(K kernel, const char* what) {
+    return orl::check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W_SMEM), what);
+}
+int warp_grid(long long units) {   // persistent CTAs: one per SM, never more than the work needs
+    const long long need = (units + W_WPC - 1) / W_WPC;
+    return (int)std::max(1LL, std::min<long long>(need, orl::sm_count()));
+}
+
 int check_common(const OrlRnnArgs& a) {
     ORL_CHECK_ARG(a.n_envs > 0 && a.n_agents > 0 && a.episode_length > 0, "n_envs / n_agents / episode_length");
     ORL_CHECK_ARG(a.obs_dim > 0 && a.obs_dim <= rc::MAXD && a.critic_obs_dim > 0 && a.critic_obs_dim <= rc::MAXD, "obs dims (<= 64)");
@@ -377,7 +470,10 @@ int check_common(const OrlRnnArgs& a) {
 extern "C" {
 
 int orl_rnn_param_count(int obs_dim, int n_out) { return rc::rnn_offsets(obs_dim, n_out).total; }
-int orl_rnn_tape_width(void) { return rc::TAPE; }
+int orl_rnn_tape_width(void) { return rw::TAPE_W; }
+long long orl_rnn_workspace_floats(long long rows, int grads_stride) {
+    return ws_tape_floats(rows) + (long long)ws_row_blocks(rows) * grads_stride;
+}
 
 int orl_rnn_rollout(const OrlRnnArgs* ap, void* stream) {
     ORL_CHECK_ARG(ap, "args");
@@ -389,9 +485,9 @@ int orl_rnn_rollout(const OrlRnnArgs* ap, void* stream) {
     const int grid = (a.n_envs + RNN_NT - 1) / RNN_NT;
     if (a.env_kind == ORL_ENV_NONE) {   // policy step(s) only: rows = n_envs, slot t -> actions[t], rnn_states[t+1]
         ORL_CHECK_ARG(a.n_agents == 1, "ENV_NONE rows are passed as n_envs with n_agents == 1");
-        if (a.t_end > a.t_begin) rnn_rollout_kernel<ORL_ENV_NONE><<<grid, RNN_NT, 0, st>>>(a);
+        if (a.t_end > a.t_begin) rnn_act_kernel<<<grid, RNN_NT, 0, st>>>(a);
         if (a.rng_counter) rnn_bump_counter_kernel<<<1, 1, 0, st>>>(a.rng_counter, (uint64_t)(a.t_end - a.t_begin));
-        return orl::check_cuda(cudaGetLastError(), "rnn_rollout_kernel(act) launch");
+        return orl::check_cuda(cudaGetLastError(), "rnn_act_kernel launch");
     }
     ORL_CHECK_ARG(a.critic_obs && a.rewards && a.active_masks, "null rollout buffer");
     ORL_CHECK_ARG(a.env_kind == ORL_ENV_MPE_SPREAD || a.env_kind == ORL_ENV_CARTPOLE || a.env_kind == ORL_ENV_GRIDWORLD,
@@ -404,14 +500,22 @@ int orl_rnn_rollout(const OrlRnnArgs* ap, void* stream) {
         ORL_CHECK_ARG(a.n_agents == 1 && a.obs_dim == 4, "single-agent env shapes");
     }
     if (a.t_end > a.t_begin) {
+        const int wg = warp_grid(a.n_envs);
+        int e = 0;
         switch (a.env_kind) {
-            case ORL_ENV_MPE_SPREAD: rnn_rollout_kernel<ORL_ENV_MPE_SPREAD><<<grid, RNN_NT, 0, st>>>(a); break;
-            case ORL_ENV_CARTPOLE: rnn_rollout_kernel<ORL_ENV_CARTPOLE><<<grid, RNN_NT, 0, st>>>(a); break;
-            default: rnn_rollout_kernel<ORL_ENV_GRIDWORLD><<<grid, RNN_NT, 0, st>>>(a); break;
+            case ORL_ENV_MPE_SPREAD:
+                if ((e = warp_kernel_prepare(rnn_rollout_warp_kernel<ORL_ENV_MPE_SPREAD>, "smem attr (rnn rollout)"))) return e;
+                rnn_rollout_warp_kernel<ORL_ENV_MPE_SPREAD><<<wg, W_NT, W_SMEM, st>>>(a); break;
+            case ORL_ENV_CARTPOLE:
+                if ((e = warp_kernel_prepare(rnn_rollout_warp_kernel<ORL_ENV_CARTPOLE>, "smem attr (rnn rollout)"))) return e;
+                rnn_rollout_warp_kernel<ORL_ENV_CARTPOLE><<<wg, W_NT, W_SMEM, st>>>(a); break;
+            default:
+                if ((e = warp_kernel_prepare(rnn_rollout_warp_kernel<ORL_ENV_GRIDWORLD>, "smem attr (rnn rollout)"))) return e;
+                rnn_rollout_warp_kernel<ORL_ENV_GRIDWORLD><<<wg, W_NT, W_SMEM, st>>>(a); break;
         }
     }
     if (a.rng_counter) rnn_bump_counter_kernel<<<1, 1, 0, st>>>(a.rng_counter, (uint64_t)(a.t_end - a.t_begin));
-    return orl::check_cuda(cudaGetLastError(), "rnn_rollout_kernel launch");
+    return orl::check_cuda(cudaGetLastError(), "rnn_rollout_warp_kernel launch");
 }
 
 int orl_rnn_critic(const OrlRnnArgs* ap, void* stream) {
@@ -420,8 +524,9 @@ int orl_rnn_critic(const OrlRnnArgs* ap, void* stream) {
     if (int e = check_common(a)) return e;
     ORL_CHECK_ARG(a.critic_params && a.critic_obs && a.rnn_states_critic && a.masks && a.value_preds, "null critic buffer");
     const int B = a.n_envs * a.n_agents;
-    rnn_critic_kernel<<<(B + RNN_NT - 1) / RNN_NT, RNN_NT, 0, (cudaStream_t)stream>>>(a);
-    return orl::check_cuda(cudaGetLastError(), "rnn_critic_kernel launch");
+    if (int e = warp_kernel_prepare(rnn_critic_warp_kernel, "smem attr (rnn critic)")) return e;
+    rnn_critic_warp_kernel<<<warp_grid(B), W_NT, W_SMEM, (cudaStream_t)stream>>>(a);
+    return orl::check_cuda(cudaGetLastError(), "rnn_critic_warp_kernel launch");
 }
 
 int orl_rnn_fwdbwd(const OrlRnnArgs* ap, void* stream) {
@@ -438,22 +543,24 @@ int orl_rnn_fwdbwd(const OrlRnnArgs* ap, void* stream) {
                       a.grads_stride >= rc::rnn_offsets(a.critic_obs_dim, 1).total, "grads_stride");
     if (a.flags & ORL_PPO_VALUENORM) { ORL_CHECK_ARG(a.vn_state, "vn_state"); }
     cudaStream_t st = (cudaStream_t)stream;
-    int e = orl::check_cuda(cudaMemsetAsync(a.grads, 0, 2 * (size_t)a.grads_stride * sizeof(float), st), "memset grads");
-    if (e) return e;
-    e = orl::check_cuda(cudaMemsetAsync(a.loss_acc, 0, 8 * sizeof(float), st), "memset loss_acc");
+    int e = orl::check_cuda(cudaMemsetAsync(a.loss_acc, 0, 8 * sizeof(float), st), "memset loss_acc");
     if (e) return e;
     const long long rows = a.n_chunks * a.chunk_length;
-    const int cgrid = (int)((a.n_chunks + RNN_NT - 1) / RNN_NT);
-    const int rgrid = (int)((rows + TR_ROWS - 1) / TR_ROWS);
-    {
-        rnn_chunk_kernel<true><<<cgrid, RNN_NT, 0, st>>>(a);
-        const TapeJobs jobs = make_jobs(a.obs_dim, a.n_actions);
-        tape_reduce_kernel<<<dim3(rgrid, jobs.count), TR_NT, 0, st>>>(a.tape, rows, jobs, a.grads);
-    }
-    {
-        rnn_chunk_kernel<false><<<cgrid, RNN_NT, 0, st>>>(a);
-        const TapeJobs jobs = make_jobs(a.critic_obs_dim, 1);
-        tape_reduce_kernel<<<dim3(rgrid, jobs.count), TR_NT, 0, st>>>(a.tape, rows, jobs, a.grads + a.grads_stride);
+    const int cgrid = warp_grid(a.n_chunks);
+    const int rb = ws_row_blocks(rows);
+    float* partials = a.tape + ws_tape_floats(rows);
+    if ((e = warp_kernel_prepare(rnn_chunk_warp_kernel<true>, "smem attr (rnn chunk policy)"))) return e;
+    if ((e = warp_kernel_prepare(rnn_chunk_warp_kernel<false>, "smem attr (rnn chunk critic)"))) return e;
+    for (int net = 0; net < 2; ++net) {
+        const int d = net == 0 ? a.obs_dim : a.critic_obs_dim, n = net == 0 ? a.n_actions : 1;
+        if (net == 0) rnn_chunk_warp_kernel<true><<<cgrid, W_NT, W_SMEM, st>>>(a);
+        else rnn_chunk_warp_kernel<false><<<cgrid, W_NT, W_SMEM, st>>>(a);
+        const TapeJobs jobs = make_jobs(d, n);
+        tape_gemm_kernel<<<dim3(rb, jobs.n_gemm), TR_NT, 0, st>>>(a.tape, rows, jobs, partials, a.grads_stride);
+        tape_colsum_kernel<<<dim3(rb, jobs.n_col), rc::G3, 0, st>>>(a.tape, rows, jobs, partials, a.grads_stride);
+        const int total = rc::rnn_offsets(d, n).total;
+        tape_partial_sum_kernel<<<(total + 255) / 256, 256, 0, st>>>(partials, rb, a.grads_stride, total,
+                                                                     a.grads + (size_t)net * a.grads_stride);
     }
     return orl::check_cuda(cudaGetLastError(), "rnn update launches");
 }

@@ -69,6 +69,7 @@ def load(path=None):
         fn.restype = _I
     lib.orl_last_error.restype = _c.c_char_p
     lib.orl_last_error.argtypes = []
+    lib.orl_rnn_workspace_floats.restype = _c.c_int64
     if lib.orl_abi_version() != 1:
         raise OrlLibraryError("ABI version mismatch")
     if path is None:
@@ -177,6 +178,7 @@ class OrlRnnArgs(ctypes.Structure):
 _SIGNATURES.update({
     "orl_rnn_param_count": [_I, _I],
     "orl_rnn_tape_width": [],
+    "orl_rnn_workspace_floats": [_c.c_int64, _I],
     "orl_rnn_rollout": [_c.POINTER(OrlRnnArgs), _P],
     "orl_rnn_critic": [_c.POINTER(OrlRnnArgs), _P],
     "orl_rnn_fwdbwd": [_c.POINTER(OrlRnnArgs), _P],

@@ -63,7 +63,8 @@ def main():
             print(f"{mk:7s} {k:34s} |ref|max {np.abs(ref).max():.3e}  max err {err:.3e}")
             off += n
     # tape check (critic tape is the last one written): numpy reductions of the tape vs device grads vs oracle
-    tape = tr.tape.cpu().numpy().astype(np.float64)
+    WT = tr._lib.orl_rnn_tape_width()
+    tape = tr.tape[:300 * WT].view(300, WT).cpu().numpy().astype(np.float64)
     TP_DZ1, TP_DZ3, TP_DGI, TP_DGH, TP_DLOG = 0, 64, 128, 320, 512
     TQ_X, TQ_Y1, TQ_Y3, TQ_HM, TQ_O = 520, 584, 648, 712, 776
     dc = 54
@@ -92,8 +93,8 @@ def main():
     torch.set_rng_state(rng)
     perm = torch.randperm(150).numpy()
     T, B, L, nch = 25, 12, 2, 150
-    tape32 = tr.tape.cpu().numpy()
-    dev = tape32.reshape(nch, L, 1224)                      # [cpos][l]
+    tape32 = tr.tape[:300 * WT].view(300, WT).cpu().numpy()
+    dev = tape32[:nch * L].reshape(nch, L, -1)[:, :, :1224]   # [cpos][l], the fields shared with the CPU core
     X = np.zeros((L, nch, dc), np.float32); M = np.zeros((L, nch), np.float32); DL = np.zeros((L, nch, 1), np.float32)
     H0 = np.zeros((nch, 64), np.float32)
     hc = snap["rnn_states_critic"].reshape(26, B, 64); mk = snap["masks"].reshape(26, B); co = snap["critic_obs"].reshape(26, B, dc)

@@ -125,6 +125,29 @@ def test_recurrent_training_runs_and_acts(cuda, env_id, chunk, mini):
     np.testing.assert_array_equal(s_reset.cpu().numpy(), torch.as_tensor(agent.net.rnn_states_actor).cpu().numpy())
 
 
+def test_mpe_gru_runs_at_baseline_scale(cuda):
+    """BASELINE configs[2]: simple_spread MAPPO, 3 agents x 2048 envs, shared GRU actor-critic (examples/mpe/mpe_ppo.yaml)."""
+    from openrl_b200.configs.config import create_config_parser
+    from openrl_b200.envs.common import make
+    from openrl_b200.modules.common import PPONet
+    from openrl_b200.runners.common import PPOAgent
+    from openrl_b200.utils.logger import Logger
+
+    cfg = create_config_parser().parse_args(["--episode_length", "25", "--lr", "7e-4", "--critic_lr", "7e-4", "--ppo_epoch", "2",
+                                             "--use_recurrent_policy", "true", "--use_valuenorm", "true",
+                                             "--use_adv_normalize", "true", "--log_interval", "1"])
+    cfg.quiet = True
+    env = make("simple_spread", env_num=2048)
+    agent = PPOAgent(PPONet(env, cfg=cfg, device="cuda:0"))
+    logger = Logger(quiet=True)
+    agent.train(total_time_steps=25 * 2048 * 2, logger=logger)
+    logs = [h[1] for h in logger.history if "value_loss" in h[1]]
+    assert len(logs) == 2 and all(np.isfinite(list(l.values())).all() for l in logs), logs
+    assert abs(logs[0]["ratio"] - 1.0) < 1e-3 and logs[0]["dist_entropy"] > 1.5
+    roll = [h[1] for h in logger.history if "rollout_episode_reward" in h[1]]
+    assert all(r["rollout_episode_reward"] < 0 for r in roll)
+
+
 def test_recurrent_limits_are_loud(cuda):
     from openrl_b200.configs.config import create_config_parser
     from openrl_b200.envs.common import make
