@@ -86,7 +86,7 @@ __global__ void rnn_bump_counter_kernel(uint64_t* c, uint64_t by) { *c += by; }
 
 constexpr int W_NT = 512, W_WPC = W_NT / 32;   // one persistent CTA per SM, 16 warps, weights of one net in smem
 
-// ---- rollout: one warp per env; policy GRU step of each agent row, env.step on lane 0 ----
+// ---- rollout: one warp per env advances its A agent rows together; env.step on lane 0 ----
 template <int ENV>
 __global__ void __launch_bounds__(W_NT, 1) rnn_rollout_warp_kernel(const OrlRnnArgs a) {
     extern __shared__ __align__(16) float smem[];
@@ -97,23 +97,30 @@ __global__ void __launch_bounds__(W_NT, 1) rnn_rollout_warp_kernel(const OrlRnnA
     const rw::SmemNet W = rw::load_net(smem, a.policy_params, o, threadIdx.x, W_NT);
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* scr = smem + rw::smem_net_floats() + warp * A * rw::SCR;
     EnvPtrs E{a.env_f64, a.env_u64, a.env_i32, a.env_table, a.env_table_len, a.rng_seed, a.ep_return, a.ep_length, a.episode_stats};
     const uint64_t rng_base = a.rng_step_base + (a.rng_counter ? *a.rng_counter : 0ull);
+    float* const no_tape[A] = {};
     for (int e = blockIdx.x * W_WPC + warp; e < N; e += gridDim.x * W_WPC) {
         for (int t = a.t_begin; t < a.t_end; ++t) {
+            rw::V2 x[A], h[A], hn[A];
+            float mk[A], logit[A][MAX_OUT];
             int acts[A];
-            rw::V2 hn[A];
+#pragma unroll
+            for (int ag = 0; ag < A; ++ag) {
+                const size_t grow = (size_t)t * B + e * A + ag;
+                const float* ob = a.policy_obs + grow * D;
+                x[ag] = rw::V2{lane < D ? ob[lane] : 0.f, lane + 32 < D ? ob[lane + 32] : 0.f};
+                h[ag] = rw::ldv(a.rnn_states + grow * rc::H, lane);
+                mk[ag] = a.masks[grow];
+            }
+            rw::step_forward<A>(W, scr, D, n, a.activation_id, x, h, mk, hn, logit, no_tape, lane);
 #pragma unroll
             for (int ag = 0; ag < A; ++ag) {
                 const int row = e * A + ag;
                 const size_t grow = (size_t)t * B + row;
-                const float* ob = a.policy_obs + grow * D;
-                const rw::V2 x{lane < D ? ob[lane] : 0.f, lane + 32 < D ? ob[lane + 32] : 0.f};
-                const rw::V2 h = rw::ldv(a.rnn_states + grow * rc::H, lane);
-                float logit[MAX_OUT];
-                rw::step_forward(W, D, n, a.activation_id, x, h, a.masks[grow], hn[ag], logit, nullptr, lane);
                 float nl[MAX_OUT], pr[MAX_OUT];
-                log_softmax_n(logit, n, nl, pr);                 // identical on every lane
+                log_softmax_n(logit[ag], n, nl, pr);                 // identical on every lane
                 const int act = pick_action(a, pr, n, grow, row, t, rng_base);
                 float lp = nl[0];
 #pragma unroll
@@ -170,25 +177,29 @@ __global__ void __launch_bounds__(W_NT, 1) rnn_critic_warp_kernel(const OrlRnnAr
     const rw::SmemNet W = rw::load_net(smem, a.critic_params, o, threadIdx.x, W_NT);
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* scr = smem + rw::smem_net_floats() + warp * rw::SCR;
+    float* const no_tape[1] = {nullptr};
     for (int row = blockIdx.x * W_WPC + warp; row < B; row += gridDim.x * W_WPC) {
-        rw::V2 h = rw::ldv(a.rnn_states_critic + (size_t)row * rc::H, lane);
+        rw::V2 h[1] = {rw::ldv(a.rnn_states_critic + (size_t)row * rc::H, lane)};
         for (int t = 0; t <= T; ++t) {
             const size_t grow = (size_t)t * B + row;
             const float* ob = a.critic_obs + grow * dc;
-            const rw::V2 x{lane < dc ? ob[lane] : 0.f, lane + 32 < dc ? ob[lane + 32] : 0.f};
-            rw::V2 hn; float out[MAX_OUT];
-            rw::step_forward(W, dc, 1, a.activation_id, x, h, a.masks[grow], hn, out, nullptr, lane);
-            if (lane == 0) a.value_preds[grow] = out[0];
+            const rw::V2 x[1] = {rw::V2{lane < dc ? ob[lane] : 0.f, lane + 32 < dc ? ob[lane + 32] : 0.f}};
+            const float mk[1] = {a.masks[grow]};
+            rw::V2 hn[1]; float out[1][MAX_OUT];
+            rw::step_forward<1>(W, scr, dc, 1, a.activation_id, x, h, mk, hn, out, no_tape, lane);
+            if (lane == 0) a.value_preds[grow] = out[0][0];
             if (t < T) {
                 const float keep = a.masks[grow + B] == 0.f ? 0.f : 1.f;   // rnn_states_critic[dones_env] = 0
-                h = rw::V2{hn.a * keep, hn.b * keep};
-                rw::stv(a.rnn_states_critic + (grow + B) * rc::H, lane, h);
+                h[0] = rw::V2{hn[0].a * keep, hn[0].b * keep};
+                rw::stv(a.rnn_states_critic + (grow + B) * rc::H, lane, h[0]);
             }
         }
     }
 }
 
-// ---- update: one warp per chunk; L forward steps (tape), per-step loss, L backward steps ----
+// ---- update: one warp per C_R chunks; L forward steps (tape), per-step loss, L backward steps ----
+constexpr int C_R = 2;
 template <bool POLICY>
 __global__ void __launch_bounds__(W_NT, 1) rnn_chunk_warp_kernel(const OrlRnnArgs a) {
     extern __shared__ __align__(16) float smem[];
@@ -200,6 +211,7 @@ __global__ void __launch_bounds__(W_NT, 1) rnn_chunk_warp_kernel(const OrlRnnArg
     const rw::SmemNet W = rw::load_net(smem, POLICY ? a.policy_params : a.critic_params, o, threadIdx.x, W_NT);
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* scr = smem + rw::smem_net_floats() + warp * C_R * rw::SCR;
     float loss0 = 0.f, loss1 = 0.f, loss2 = 0.f;   // identical on every lane; lane 0's copy is reduced
 
     const double rows_d = (double)a.n_chunks * L;
@@ -216,58 +228,83 @@ __global__ void __launch_bounds__(W_NT, 1) rnn_chunk_warp_kernel(const OrlRnnArg
         vn_mean = s.mean; vn_std = s.std;
     }
 
-    for (long long cpos = (long long)blockIdx.x * W_WPC + warp; cpos < a.n_chunks; cpos += (long long)gridDim.x * W_WPC) {
-        const long long f0 = a.chunk_ids[cpos] * (long long)L;
-        rw::V2 h = rw::ldv(states + ((size_t)(f0 % T) * B + (size_t)(f0 / T)) * rc::H, lane);
+    const long long n_groups = (a.n_chunks + C_R - 1) / C_R;
+    for (long long grp = (long long)blockIdx.x * W_WPC + warp; grp < n_groups; grp += (long long)gridDim.x * W_WPC) {
+        long long cpos[C_R], f0[C_R];
+        bool valid[C_R];
+        rw::V2 h[C_R];
+#pragma unroll
+        for (int r = 0; r < C_R; ++r) {
+            valid[r] = grp * C_R + r < a.n_chunks;
+            cpos[r] = valid[r] ? grp * C_R + r : grp * C_R;   // a tail slot recomputes chunk 0 of the group (same values, same addresses)
+            f0[r] = a.chunk_ids[cpos[r]] * (long long)L;
+            h[r] = rw::ldv(states + ((size_t)(f0[r] % T) * B + (size_t)(f0[r] / T)) * rc::H, lane);
+        }
         for (int l = 0; l < L; ++l) {
-            const long long f = f0 + l, row = f / T, t = f % T;
-            const size_t bi = (size_t)t * B + row;
-            const float* ob = obs + bi * d;
-            const rw::V2 x{lane < d ? ob[lane] : 0.f, lane + 32 < d ? ob[lane + 32] : 0.f};
-            float* tape = a.tape + ((size_t)cpos * L + l) * rw::TAPE_W;
-            float out[MAX_OUT];
-            rw::V2 h2;
-            rw::step_forward(W, d, n, a.activation_id, x, h, a.masks[bi], h2, out, tape, lane);
-            h = h2;
-            float dl[MAX_OUT];
+            rw::V2 x[C_R], h2[C_R];
+            float mk[C_R], out[C_R][MAX_OUT];
+            float* tape[C_R];
+            size_t bi[C_R];
 #pragma unroll
-            for (int j = 0; j < MAX_OUT; ++j) dl[j] = 0.f;
-            const float active = a.active_masks[bi];
-            if (POLICY) {
-                float nl[MAX_OUT], pr[MAX_OUT];
-                log_softmax_n(out, n, nl, pr);
-                const int act = (int)a.actions[bi];
-                float lp = nl[0];
-#pragma unroll
-                for (int j = 1; j < MAX_OUT; ++j) if (j == act) lp = nl[j];
-                const float adv = apply_adv_norm(advn, a.advantages[bi]);
-                const PgTerm pg = pg_term(lp, a.action_log_probs[bi], adv, a.clip_param, a.flags, a.dual_clip_coeff);
-                const float wrow = pol_masks ? active * inv_act : inv_rows;
-                float ent = 0.f;
-#pragma unroll
-                for (int j = 0; j < MAX_OUT; ++j) if (j < n) ent -= pr[j] * nl[j];
-                loss0 += pg.loss * wrow; loss1 += ent * wrow; loss2 += pg.ratio;
-                const float dlp = pg.dlogp * wrow, went = a.entropy_coef * wrow;
-#pragma unroll
-                for (int j = 0; j < MAX_OUT; ++j)
-                    if (j < n) dl[j] = dlp * ((j == act ? 1.f : 0.f) - pr[j]) + went * pr[j] * (nl[j] + ent);
-            } else {
-                const float ret = a.returns[bi];
-                const float target = (a.flags & ORL_PPO_VALUENORM) ? (ret - vn_mean) / vn_std : ret;
-                const ValueTerm vt = value_term(out[0], a.value_preds[bi], target, a.clip_param, a.huber_delta, a.flags);
-                const float wrow = val_masks ? active * inv_act : inv_rows;
-                loss0 += vt.loss * wrow;
-                dl[0] = a.value_loss_coef * wrow * vt.dv;
+            for (int r = 0; r < C_R; ++r) {
+                const long long f = f0[r] + l, row = f / T, t = f % T;
+                bi[r] = (size_t)t * B + row;
+                const float* ob = obs + bi[r] * d;
+                x[r] = rw::V2{lane < d ? ob[lane] : 0.f, lane + 32 < d ? ob[lane + 32] : 0.f};
+                mk[r] = a.masks[bi[r]];
+                tape[r] = a.tape + ((size_t)cpos[r] * L + l) * rw::TAPE_W;
             }
-            float mine = 0.f;   // lane m < 8 stores dL/dout[m]
+            rw::step_forward<C_R>(W, scr, d, n, a.activation_id, x, h, mk, h2, out, tape, lane);
 #pragma unroll
-            for (int j = 0; j < MAX_OUT; ++j) if (lane == j) mine = dl[j];
-            if (lane < MAX_OUT) tape[rc::TP_DLOG + lane] = mine;
+            for (int r = 0; r < C_R; ++r) {
+                h[r] = h2[r];
+                float dl[MAX_OUT];
+#pragma unroll
+                for (int j = 0; j < MAX_OUT; ++j) dl[j] = 0.f;
+                const float active = a.active_masks[bi[r]];
+                const float keep = valid[r] ? 1.f : 0.f;
+                if (POLICY) {
+                    float nl[MAX_OUT], pr[MAX_OUT];
+                    log_softmax_n(out[r], n, nl, pr);
+                    const int act = (int)a.actions[bi[r]];
+                    float lp = nl[0];
+#pragma unroll
+                    for (int j = 1; j < MAX_OUT; ++j) if (j == act) lp = nl[j];
+                    const float adv = apply_adv_norm(advn, a.advantages[bi[r]]);
+                    const PgTerm pg = pg_term(lp, a.action_log_probs[bi[r]], adv, a.clip_param, a.flags, a.dual_clip_coeff);
+                    const float wrow = pol_masks ? active * inv_act : inv_rows;
+                    float ent = 0.f;
+#pragma unroll
+                    for (int j = 0; j < MAX_OUT; ++j) if (j < n) ent -= pr[j] * nl[j];
+                    loss0 += keep * pg.loss * wrow; loss1 += keep * ent * wrow; loss2 += keep * pg.ratio;
+                    const float dlp = pg.dlogp * wrow, went = a.entropy_coef * wrow;
+#pragma unroll
+                    for (int j = 0; j < MAX_OUT; ++j)
+                        if (j < n) dl[j] = dlp * ((j == act ? 1.f : 0.f) - pr[j]) + went * pr[j] * (nl[j] + ent);
+                } else {
+                    const float ret = a.returns[bi[r]];
+                    const float target = (a.flags & ORL_PPO_VALUENORM) ? (ret - vn_mean) / vn_std : ret;
+                    const ValueTerm vt = value_term(out[r][0], a.value_preds[bi[r]], target, a.clip_param, a.huber_delta, a.flags);
+                    const float wrow = val_masks ? active * inv_act : inv_rows;
+                    loss0 += keep * vt.loss * wrow;
+                    dl[0] = a.value_loss_coef * wrow * vt.dv;
+                }
+                float mine = 0.f;   // lane m < 8 stores dL/dout[m]
+#pragma unroll
+                for (int j = 0; j < MAX_OUT; ++j) if (lane == j) mine = dl[j];
+                if (lane < MAX_OUT) tape[r][rc::TP_DLOG + lane] = mine;
+            }
         }
         __syncwarp();   // tape scalars (lane 0) and dL/dout (lanes < 8) are read by every lane below
-        rw::V2 dh{0.f, 0.f};
-        for (int l = L - 1; l >= 0; --l)
-            dh = rw::step_backward(W, n, a.activation_id, a.tape + ((size_t)cpos * L + l) * rw::TAPE_W, dh, lane);
+        rw::V2 dh[C_R];
+#pragma unroll
+        for (int r = 0; r < C_R; ++r) dh[r] = rw::V2{0.f, 0.f};
+        for (int l = L - 1; l >= 0; --l) {
+            float* tape[C_R];
+#pragma unroll
+            for (int r = 0; r < C_R; ++r) tape[r] = a.tape + ((size_t)cpos[r] * L + l) * rw::TAPE_W;
+            rw::step_backward<C_R>(W, scr, n, a.activation_id, tape, dh, lane);
+        }
     }
     __shared__ float red[3][W_WPC];
     if (lane == 0) { red[0][warp] = loss0; red[1][warp] = loss1; red[2][warp] = loss2; }
@@ -447,10 +484,12 @@ __global__ void __launch_bounds__(1024) rnn_apply_kernel(const OrlRnnArgs a) {
     }
 }
 
-constexpr size_t W_SMEM = (size_t)rw::smem_net_floats() * sizeof(float);
+constexpr size_t w_smem(int rows_per_warp) {   // weights of one net + the per-warp mat-vec scratch
+    return (size_t)(rw::smem_net_floats() + rw::smem_scratch_floats(W_WPC, rows_per_warp)) * sizeof(float);
+}
 template <typename K>
-int warp_kernel_prepare(K kernel, const char* what) {
-    return orl::check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W_SMEM), what);
+int warp_kernel_prepare(K kernel, size_t smem, const char* what) {
+    return orl::check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), what);
 }
 int warp_grid(long long units) {   // persistent CTAs: one per SM, never more than the work needs
     const long long need = (units + W_WPC - 1) / W_WPC;
@@ -504,14 +543,14 @@ int orl_rnn_rollout(const OrlRnnArgs* ap, void* stream) {
         int e = 0;
         switch (a.env_kind) {
             case ORL_ENV_MPE_SPREAD:
-                if ((e = warp_kernel_prepare(rnn_rollout_warp_kernel<ORL_ENV_MPE_SPREAD>, "smem attr (rnn rollout)"))) return e;
-                rnn_rollout_warp_kernel<ORL_ENV_MPE_SPREAD><<<wg, W_NT, W_SMEM, st>>>(a); break;
+                if ((e = warp_kernel_prepare(rnn_rollout_warp_kernel<ORL_ENV_MPE_SPREAD>, w_smem(3), "smem attr (rnn rollout)"))) return e;
+                rnn_rollout_warp_kernel<ORL_ENV_MPE_SPREAD><<<wg, W_NT, w_smem(3), st>>>(a); break;
             case ORL_ENV_CARTPOLE:
-                if ((e = warp_kernel_prepare(rnn_rollout_warp_kernel<ORL_ENV_CARTPOLE>, "smem attr (rnn rollout)"))) return e;
-                rnn_rollout_warp_kernel<ORL_ENV_CARTPOLE><<<wg, W_NT, W_SMEM, st>>>(a); break;
+                if ((e = warp_kernel_prepare(rnn_rollout_warp_kernel<ORL_ENV_CARTPOLE>, w_smem(1), "smem attr (rnn rollout)"))) return e;
+                rnn_rollout_warp_kernel<ORL_ENV_CARTPOLE><<<wg, W_NT, w_smem(1), st>>>(a); break;
             default:
-                if ((e = warp_kernel_prepare(rnn_rollout_warp_kernel<ORL_ENV_GRIDWORLD>, "smem attr (rnn rollout)"))) return e;
-                rnn_rollout_warp_kernel<ORL_ENV_GRIDWORLD><<<wg, W_NT, W_SMEM, st>>>(a); break;
+                if ((e = warp_kernel_prepare(rnn_rollout_warp_kernel<ORL_ENV_GRIDWORLD>, w_smem(1), "smem attr (rnn rollout)"))) return e;
+                rnn_rollout_warp_kernel<ORL_ENV_GRIDWORLD><<<wg, W_NT, w_smem(1), st>>>(a); break;
         }
     }
     if (a.rng_counter) rnn_bump_counter_kernel<<<1, 1, 0, st>>>(a.rng_counter, (uint64_t)(a.t_end - a.t_begin));
@@ -524,8 +563,8 @@ int orl_rnn_critic(const OrlRnnArgs* ap, void* stream) {
     if (int e = check_common(a)) return e;
     ORL_CHECK_ARG(a.critic_params && a.critic_obs && a.rnn_states_critic && a.masks && a.value_preds, "null critic buffer");
     const int B = a.n_envs * a.n_agents;
-    if (int e = warp_kernel_prepare(rnn_critic_warp_kernel, "smem attr (rnn critic)")) return e;
-    rnn_critic_warp_kernel<<<warp_grid(B), W_NT, W_SMEM, (cudaStream_t)stream>>>(a);
+    if (int e = warp_kernel_prepare(rnn_critic_warp_kernel, w_smem(1), "smem attr (rnn critic)")) return e;
+    rnn_critic_warp_kernel<<<warp_grid(B), W_NT, w_smem(1), (cudaStream_t)stream>>>(a);
     return orl::check_cuda(cudaGetLastError(), "rnn_critic_warp_kernel launch");
 }
 
@@ -546,15 +585,15 @@ int orl_rnn_fwdbwd(const OrlRnnArgs* ap, void* stream) {
     int e = orl::check_cuda(cudaMemsetAsync(a.loss_acc, 0, 8 * sizeof(float), st), "memset loss_acc");
     if (e) return e;
     const long long rows = a.n_chunks * a.chunk_length;
-    const int cgrid = warp_grid(a.n_chunks);
+    const int cgrid = warp_grid((a.n_chunks + C_R - 1) / C_R);
     const int rb = ws_row_blocks(rows);
     float* partials = a.tape + ws_tape_floats(rows);
-    if ((e = warp_kernel_prepare(rnn_chunk_warp_kernel<true>, "smem attr (rnn chunk policy)"))) return e;
-    if ((e = warp_kernel_prepare(rnn_chunk_warp_kernel<false>, "smem attr (rnn chunk critic)"))) return e;
+    if ((e = warp_kernel_prepare(rnn_chunk_warp_kernel<true>, w_smem(C_R), "smem attr (rnn chunk policy)"))) return e;
+    if ((e = warp_kernel_prepare(rnn_chunk_warp_kernel<false>, w_smem(C_R), "smem attr (rnn chunk critic)"))) return e;
     for (int net = 0; net < 2; ++net) {
         const int d = net == 0 ? a.obs_dim : a.critic_obs_dim, n = net == 0 ? a.n_actions : 1;
-        if (net == 0) rnn_chunk_warp_kernel<true><<<cgrid, W_NT, W_SMEM, st>>>(a);
-        else rnn_chunk_warp_kernel<false><<<cgrid, W_NT, W_SMEM, st>>>(a);
+        if (net == 0) rnn_chunk_warp_kernel<true><<<cgrid, W_NT, w_smem(C_R), st>>>(a);
+        else rnn_chunk_warp_kernel<false><<<cgrid, W_NT, w_smem(C_R), st>>>(a);
         const TapeJobs jobs = make_jobs(d, n);
         tape_gemm_kernel<<<dim3(rb, jobs.n_gemm), TR_NT, 0, st>>>(a.tape, rows, jobs, partials, a.grads_stride);
         tape_colsum_kernel<<<dim3(rb, jobs.n_col), rc::G3, 0, st>>>(a.tape, rows, jobs, partials, a.grads_stride);
