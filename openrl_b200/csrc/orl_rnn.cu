@@ -199,16 +199,16 @@ __global__ void __launch_bounds__(W_NT, 1) rnn_critic_warp_kernel(const OrlRnnAr
 }
 
 // ---- update: one warp per C_R chunks; L forward steps (tape), per-step loss, L backward steps ----
-constexpr int C_R = 2;
-template <bool POLICY>
-__global__ void __launch_bounds__(W_NT, 1) rnn_chunk_warp_kernel(const OrlRnnArgs a) {
+template <bool POLICY, int C_R, int C_NT>
+__global__ void __launch_bounds__(C_NT, 1) rnn_chunk_warp_kernel(const OrlRnnArgs a) {
+    constexpr int C_WPC = C_NT / 32;
     extern __shared__ __align__(16) float smem[];
     const int B = a.n_envs * a.n_agents, T = a.episode_length, L = a.chunk_length;
     const int d = POLICY ? a.obs_dim : a.critic_obs_dim, n = POLICY ? a.n_actions : 1;
     const float* obs = POLICY ? a.policy_obs : a.critic_obs;
     const float* states = POLICY ? a.rnn_states : a.rnn_states_critic;
     const rc::Offsets o = rc::rnn_offsets(d, n);
-    const rw::SmemNet W = rw::load_net(smem, POLICY ? a.policy_params : a.critic_params, o, threadIdx.x, W_NT);
+    const rw::SmemNet W = rw::load_net(smem, POLICY ? a.policy_params : a.critic_params, o, threadIdx.x, C_NT);
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* scr = smem + rw::smem_net_floats() + warp * C_R * rw::SCR;
@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(W_NT, 1) rnn_chunk_warp_kernel(const OrlRnnArg
     }
 
     const long long n_groups = (a.n_chunks + C_R - 1) / C_R;
-    for (long long grp = (long long)blockIdx.x * W_WPC + warp; grp < n_groups; grp += (long long)gridDim.x * W_WPC) {
+    for (long long grp = (long long)blockIdx.x * C_WPC + warp; grp < n_groups; grp += (long long)gridDim.x * C_WPC) {
         long long cpos[C_R], f0[C_R];
         bool valid[C_R];
         rw::V2 h[C_R];
@@ -306,12 +306,12 @@ __global__ void __launch_bounds__(W_NT, 1) rnn_chunk_warp_kernel(const OrlRnnArg
             rw::step_backward<C_R>(W, scr, n, a.activation_id, tape, dh, lane);
         }
     }
-    __shared__ float red[3][W_WPC];
+    __shared__ float red[3][C_WPC];
     if (lane == 0) { red[0][warp] = loss0; red[1][warp] = loss1; red[2][warp] = loss2; }
     __syncthreads();
     if (threadIdx.x < 3) {
         float s = 0.f;
-        for (int w = 0; w < W_WPC; ++w) s += red[threadIdx.x][w];
+        for (int w = 0; w < C_WPC; ++w) s += red[threadIdx.x][w];
         if (POLICY) atomicAdd(a.loss_acc + threadIdx.x, s);
         else if (threadIdx.x == 0) atomicAdd(a.loss_acc + 3, s);
     }
@@ -327,43 +327,62 @@ constexpr int MAX_GEMM_JOBS = 5, MAX_COL_JOBS = 11;
 struct TapeJobs { TapeJob gemm[MAX_GEMM_JOBS]; TapeJob col[MAX_COL_JOBS]; int n_gemm, n_col; };
 constexpr int TR_NT = 256, TR_ROWS = 1024, TR_SUB = 32, TR_MI = rc::G3 / 16;   // 16 x 16 threads; thread tile (M/16) x 4
 
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src, bool valid) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int src_size = valid ? 16 : 0;   // 0: the 16 bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(gmem_src), "r"(src_size));
+}
+constexpr size_t TR_SMEM = 2 * (size_t)TR_SUB * (rc::G3 + rc::H) * sizeof(float);   // two stages of P and Q tiles
+
 __global__ void __launch_bounds__(TR_NT) tape_gemm_kernel(const float* __restrict__ tape, long long rows, TapeJobs jobs,
                                                           float* __restrict__ partials, int stride) {
+    extern __shared__ __align__(16) float tsm[];
     const TapeJob jb = jobs.gemm[blockIdx.y];
     const long long r_begin = (long long)blockIdx.x * TR_ROWS;
     const int rows_here = (int)min((long long)TR_ROWS, rows - r_begin);
-    __shared__ __align__(16) float Ps[TR_SUB][rc::G3];
-    __shared__ __align__(16) float Qs[TR_SUB][rc::H];
+    auto Ps = [&](int buf) { return tsm + buf * (TR_SUB * rc::G3); };
+    auto Qs = [&](int buf) { return tsm + 2 * TR_SUB * rc::G3 + buf * (TR_SUB * rc::H); };
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    const int MI = (jb.M + 15) >> 4;
+    const int MI = (jb.M + 15) >> 4, Mq = MI * 4;   // P columns are read in whole float4 up to 16*MI (fields are zero / foreign beyond M: discarded)
+    // stage loader: rows beyond the block's tail are zero-filled
+    auto load_stage = [&](int buf, int s0) {
+        const int sub = min(TR_SUB, rows_here - s0);
+        const float* base = tape + (size_t)(r_begin + s0) * rw::TAPE_W;
+        for (int i = tid; i < TR_SUB * Mq; i += TR_NT) {
+            const int r = i / Mq, c = i % Mq;
+            cp_async16(Ps(buf) + r * rc::G3 + 4 * c, base + (size_t)(r < sub ? r : 0) * rw::TAPE_W + jb.p_off + 4 * c, r < sub);
+        }
+        for (int i = tid; i < TR_SUB * (rc::H / 4); i += TR_NT) {
+            const int r = i >> 4, c = i & 15;
+            cp_async16(Qs(buf) + r * rc::H + 4 * c, base + (size_t)(r < sub ? r : 0) * rw::TAPE_W + jb.q_off + 4 * c, r < sub);
+        }
+        asm volatile("cp.async.commit_group;\n" ::);
+    };
     float acc[TR_MI][4];
 #pragma unroll
     for (int i = 0; i < TR_MI; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
-    for (int s0 = 0; s0 < rows_here; s0 += TR_SUB) {
-        const int sub = min(TR_SUB, rows_here - s0);
-        const int Mp = MI * 16;
-        for (int i = tid; i < TR_SUB * Mp; i += TR_NT) {
-            const int r = i / Mp, m = i % Mp;
-            Ps[r][m] = (r < sub && m < jb.M) ? tape[(size_t)(r_begin + s0 + r) * rw::TAPE_W + jb.p_off + m] : 0.f;
-        }
-        for (int i = tid; i < TR_SUB * rc::H; i += TR_NT) {
-            const int r = i >> 6, k = i & 63;
-            Qs[r][k] = (r < sub && k < jb.N) ? tape[(size_t)(r_begin + s0 + r) * rw::TAPE_W + jb.q_off + k] : 0.f;
-        }
+    const int n_sub = (rows_here + TR_SUB - 1) / TR_SUB;
+    load_stage(0, 0);
+    for (int s = 0; s < n_sub; ++s) {
+        const int buf = s & 1;
+        if (s + 1 < n_sub) { load_stage(buf ^ 1, (s + 1) * TR_SUB); asm volatile("cp.async.wait_group 1;\n" ::); }
+        else asm volatile("cp.async.wait_group 0;\n" ::);
         __syncthreads();
+        const float* P = Ps(buf);
+        const float* Q = Qs(buf);
 #pragma unroll 4
         for (int r = 0; r < TR_SUB; ++r) {
-            const float4 q = *reinterpret_cast<const float4*>(&Qs[r][4 * tx]);
+            const float4 q = *reinterpret_cast<const float4*>(Q + r * rc::H + 4 * tx);
 #pragma unroll
             for (int i = 0; i < TR_MI; ++i) {
                 if (i < MI) {
-                    const float p = Ps[r][ty + 16 * i];
+                    const float p = P[r * rc::G3 + ty + 16 * i];
                     acc[i][0] = fmaf(p, q.x, acc[i][0]); acc[i][1] = fmaf(p, q.y, acc[i][1]);
                     acc[i][2] = fmaf(p, q.z, acc[i][2]); acc[i][3] = fmaf(p, q.w, acc[i][3]);
                 }
             }
         }
-        __syncthreads();
+        __syncthreads();   // the stage just read is refilled by the next iteration's load
     }
     float* part = partials + (size_t)blockIdx.x * stride + jb.out_off;
 #pragma unroll
@@ -585,17 +604,22 @@ int orl_rnn_fwdbwd(const OrlRnnArgs* ap, void* stream) {
     int e = orl::check_cuda(cudaMemsetAsync(a.loss_acc, 0, 8 * sizeof(float), st), "memset loss_acc");
     if (e) return e;
     const long long rows = a.n_chunks * a.chunk_length;
-    const int cgrid = warp_grid((a.n_chunks + C_R - 1) / C_R);
     const int rb = ws_row_blocks(rows);
     float* partials = a.tape + ws_tape_floats(rows);
-    if ((e = warp_kernel_prepare(rnn_chunk_warp_kernel<true>, w_smem(C_R), "smem attr (rnn chunk policy)"))) return e;
-    if ((e = warp_kernel_prepare(rnn_chunk_warp_kernel<false>, w_smem(C_R), "smem attr (rnn chunk critic)"))) return e;
+    // two chunks per warp: every weight read from shared memory feeds two rows (four per warp with 8 warps / CTA
+    // measured 12 % slower on B200: profiles/r1_gru_perf.md)
+    constexpr int C_R = 2;
+    if ((e = orl::check_cuda(cudaFuncSetAttribute(tape_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TR_SMEM),
+                             "smem attr (tape gemm)"))) return e;
+    if ((e = warp_kernel_prepare(rnn_chunk_warp_kernel<true, C_R, W_NT>, w_smem(C_R), "smem attr (rnn chunk policy)"))) return e;
+    if ((e = warp_kernel_prepare(rnn_chunk_warp_kernel<false, C_R, W_NT>, w_smem(C_R), "smem attr (rnn chunk critic)"))) return e;
+    const int cgrid = warp_grid((a.n_chunks + C_R - 1) / C_R);
     for (int net = 0; net < 2; ++net) {
         const int d = net == 0 ? a.obs_dim : a.critic_obs_dim, n = net == 0 ? a.n_actions : 1;
-        if (net == 0) rnn_chunk_warp_kernel<true><<<cgrid, W_NT, w_smem(C_R), st>>>(a);
-        else rnn_chunk_warp_kernel<false><<<cgrid, W_NT, w_smem(C_R), st>>>(a);
+        if (net == 0) rnn_chunk_warp_kernel<true, C_R, W_NT><<<cgrid, W_NT, w_smem(C_R), st>>>(a);
+        else rnn_chunk_warp_kernel<false, C_R, W_NT><<<cgrid, W_NT, w_smem(C_R), st>>>(a);
         const TapeJobs jobs = make_jobs(d, n);
-        tape_gemm_kernel<<<dim3(rb, jobs.n_gemm), TR_NT, 0, st>>>(a.tape, rows, jobs, partials, a.grads_stride);
+        tape_gemm_kernel<<<dim3(rb, jobs.n_gemm), TR_NT, TR_SMEM, st>>>(a.tape, rows, jobs, partials, a.grads_stride);
         tape_colsum_kernel<<<dim3(rb, jobs.n_col), rc::G3, 0, st>>>(a.tape, rows, jobs, partials, a.grads_stride);
         const int total = rc::rnn_offsets(d, n).total;
         tape_partial_sum_kernel<<<(total + 255) / 256, 256, 0, st>>>(partials, rb, a.grads_stride, total,
