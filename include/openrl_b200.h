@@ -255,6 +255,10 @@ typedef struct OrlPpoArgs {
                                              actor_grad_norm, ratio}  (ppo.py:430-451) */
     int32_t head_kind;           /* ORL_HEAD_*: with GAUSSIAN actions / old_log_probs are (T*B, n) */
     float dual_clip_coeff;       /* cfg.dual_clip_coeff (used with ORL_PPO_DUAL_CLIP) */
+    int64_t norm_rows;           /* rows of the GLOBAL minibatch (all ranks): the 1/rows loss weights, the reported
+                                    ratio mean and the ValueNorm batch moments (mb_stats / norm_rows) refer to it, so
+                                    that SUM-all-reduced gradients equal the single-process gradients of the global
+                                    batch; 0 = batch_rows (single process) */
 } OrlPpoArgs;
 /* floats per partial row for given shapes (>= folded gradient size + 8 loss slots, multiple of 4) */
 int orl_ppo_stride(int obs_dim, int critic_obs_dim, int n_actions);   /* valid for both head kinds */
@@ -312,6 +316,7 @@ typedef struct OrlRnnArgs {
     float adam_beta1, adam_beta2, adam_eps, weight_decay, dual_clip_coeff;
     double vn_beta;
     float* train_info;
+    int64_t norm_rows;                                    /* row-steps of the GLOBAL minibatch (see OrlPpoArgs.norm_rows); 0 = n_chunks*L */
 } OrlRnnArgs;
 int orl_rnn_param_count(int obs_dim, int n_out);
 int orl_rnn_tape_width(void);

@@ -57,8 +57,6 @@ class PPOAlgorithm:
                 raise NotImplementedError(f"cfg.{name} is not built into the CUDA update yet (SURVEY.md §8f)")
         self.recurrent = bool(cfg.use_recurrent_policy)
         if self.recurrent:
-            if self.world_size > 1:
-                raise NotImplementedError("the recurrent update is single-GPU for now (DESIGN.md, recurrent path)")
             if self.head_kind != lib.HEAD_CATEGORICAL:
                 raise NotImplementedError("recurrent policies are built for Discrete action spaces")
             if not 1 <= cfg.data_chunk_length <= 4:
@@ -66,8 +64,10 @@ class PPOAlgorithm:
             self.use_tf32 = False
             self.flags &= ~lib.PPO_TF32
             self.rnn_stride = (max(self._lib.orl_rnn_param_count(self.d, self.n), self._lib.orl_rnn_param_count(self.dc, 1)) + 3) & ~3
-            self.rnn_grads = torch.zeros(2, self.rnn_stride, dtype=torch.float32, device=dev)
-            self.loss_acc = torch.zeros(8, dtype=torch.float32, device=dev)
+            # one bucket = gradients of both nets + the loss sums: a single all-reduce per update with >1 GPU
+            self.rnn_bucket = torch.zeros(2 * self.rnn_stride + 8, dtype=torch.float32, device=dev)
+            self.rnn_grads = self.rnn_bucket[:2 * self.rnn_stride].view(2, self.rnn_stride)
+            self.loss_acc = self.rnn_bucket[2 * self.rnn_stride:]
             self.tape = None
         self.gpu_launches = 0
         self.h2d_bytes = 0
@@ -92,6 +92,8 @@ class PPOAlgorithm:
         a.dual_clip_coeff = float(getattr(self.cfg, "dual_clip_coeff", 3.0))
         total = buf.episode_length * buf.n_rollout_threads * buf.num_agents
         a.batch_rows, a.row_begin, a.total_rows = int(batch_rows), int(row_begin), int(total)
+        # every rank holds an equal shard of the global minibatch: weights / batch moments refer to the global row count
+        a.norm_rows = int(batch_rows) * self.world_size if self.world_size > 1 else 0
         a.indices = lib.ptr(indices)
         a.policy_obs, a.critic_obs = lib.ptr(buf.policy_obs), lib.ptr(buf.critic_obs)
         a.actions, a.old_log_probs = lib.ptr(buf.actions), lib.ptr(buf.action_log_probs)
@@ -161,6 +163,8 @@ class PPOAlgorithm:
         a.dual_clip_coeff = float(getattr(cfg, "dual_clip_coeff", 3.0))
         a.vn_beta = 0.99999 if vn is None else vn.beta
         a.train_info = lib.ptr(self.train_info)
+        rows = int(chunk_ids.numel()) * cfg.data_chunk_length
+        a.norm_rows = rows * self.world_size if self.world_size > 1 else 0
         return a
 
     def _train_recurrent(self, buf):
@@ -199,8 +203,10 @@ class PPOAlgorithm:
                                                      lib.ptr(self.mb_stats), s), "orl_minibatch_stats")
                     mb_stats = self.mb_stats
                     self.gpu_launches += 1
+                    parallel.allreduce_sum_(mb_stats)
                 a = self._rnn_args(buf, ids, mb_stats)
                 lib.check(Lb.orl_rnn_fwdbwd(a, s), "orl_rnn_fwdbwd")
+                parallel.allreduce_sum_(self.rnn_bucket)   # gradients of both nets + loss sums (no-op on one GPU)
                 lib.check(Lb.orl_rnn_apply(a, s), "orl_rnn_apply")
                 self.gpu_launches += 9   # 2 x (chunk, tape gemm, tape colsum, partial sum) + apply
 

@@ -125,7 +125,7 @@ __device__ __forceinline__ void ppo_net_pass(const OrlPpoArgs& a, float* smem, i
     load_weights_folded<P_NT>(w, params, d, n, true);
 
     const bool pol_masks = a.flags & ORL_PPO_POLICY_ACTIVE_MASKS, val_masks = a.flags & ORL_PPO_VALUE_ACTIVE_MASKS;
-    const double rows_d = (double)a.batch_rows;
+    const double rows_d = (double)(a.norm_rows > 0 ? a.norm_rows : a.batch_rows);
     const float inv_rows = (float)(1.0 / rows_d);
     const float inv_act = (float)(1.0 / a.mb_stats[2]);
     AdvNorm advn;
@@ -470,13 +470,13 @@ __global__ void __launch_bounds__(1024) ppo_apply_kernel(const OrlPpoArgs a) {
             a.train_info[2] += ls[0];
             a.train_info[3] += ls[1];
             a.train_info[4] += norm;
-            a.train_info[5] += ls[2] / (float)a.batch_rows;
+            a.train_info[5] += ls[2] / (float)(a.norm_rows > 0 ? a.norm_rows : a.batch_rows);
         } else {
             a.train_info[0] += ls[0];
             a.train_info[1] += norm;
             if (a.flags & ORL_PPO_VALUENORM) {
                 float st[3];
-                vn_updated(a.vn_state, a.mb_stats, (double)a.batch_rows, a.vn_beta, st);
+                vn_updated(a.vn_state, a.mb_stats, (double)(a.norm_rows > 0 ? a.norm_rows : a.batch_rows), a.vn_beta, st);
                 a.vn_state[0] = st[0]; a.vn_state[1] = st[1]; a.vn_state[2] = st[2];
             }
         }

@@ -132,7 +132,7 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, uint8_t* smem, 
 
     // ---- minibatch constants ----
     const bool pol_masks = a.flags & ORL_PPO_POLICY_ACTIVE_MASKS, val_masks = a.flags & ORL_PPO_VALUE_ACTIVE_MASKS;
-    const double rows_d = (double)a.batch_rows;
+    const double rows_d = (double)(a.norm_rows > 0 ? a.norm_rows : a.batch_rows);
     const float inv_rows = (float)(1.0 / rows_d), inv_act = (float)(1.0 / a.mb_stats[2]);
     AdvNormTc an = {0.f, 1.f, 0.f, 1.f, false};
     float vn_mean = 0.f, vn_std = 1.f;

@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(C_NT, 1) rnn_chunk_warp_kernel(const OrlRnnArg
     float* scr = smem + rw::smem_net_floats() + warp * C_R * rw::SCR;
     float loss0 = 0.f, loss1 = 0.f, loss2 = 0.f;   // identical on every lane; lane 0's copy is reduced
 
-    const double rows_d = (double)a.n_chunks * L;
+    const double rows_d = a.norm_rows > 0 ? (double)a.norm_rows : (double)a.n_chunks * L;
     const float inv_rows = (float)(1.0 / rows_d);
     const float inv_act = (float)(1.0 / a.mb_stats[2]);
     const bool pol_masks = a.flags & ORL_PPO_POLICY_ACTIVE_MASKS, val_masks = a.flags & ORL_PPO_VALUE_ACTIVE_MASKS;
@@ -490,13 +490,13 @@ __global__ void __launch_bounds__(1024) rnn_apply_kernel(const OrlRnnArgs a) {
             a.train_info[2] += a.loss_acc[0];
             a.train_info[3] += a.loss_acc[1];
             a.train_info[4] += norm;
-            a.train_info[5] += a.loss_acc[2] / (float)((double)a.n_chunks * a.chunk_length);
+            a.train_info[5] += a.loss_acc[2] / (float)(a.norm_rows > 0 ? (double)a.norm_rows : (double)a.n_chunks * a.chunk_length);
         } else {
             a.train_info[0] += a.loss_acc[3];
             a.train_info[1] += norm;
             if (a.flags & ORL_PPO_VALUENORM) {
                 float st[3];
-                vn_updated(a.vn_state, a.mb_stats, (double)a.n_chunks * a.chunk_length, a.vn_beta, st);
+                vn_updated(a.vn_state, a.mb_stats, a.norm_rows > 0 ? (double)a.norm_rows : (double)a.n_chunks * a.chunk_length, a.vn_beta, st);
                 a.vn_state[0] = st[0]; a.vn_state[1] = st[1]; a.vn_state[2] = st[2];
             }
         }

@@ -129,6 +129,7 @@ class OrlPpoArgs(ctypes.Structure):
         ("vn_beta", _D),
         ("partials", _P), ("folded", _P), ("grads", _P), ("train_info", _P),
         ("head_kind", _c.c_int32), ("dual_clip_coeff", _F),
+        ("norm_rows", _c.c_int64),
     ]
 
 
@@ -172,6 +173,7 @@ class OrlRnnArgs(ctypes.Structure):
         ("adam_beta1", _F), ("adam_beta2", _F), ("adam_eps", _F), ("weight_decay", _F), ("dual_clip_coeff", _F),
         ("vn_beta", _D),
         ("train_info", _P),
+        ("norm_rows", _c.c_int64),
     ]
 
 

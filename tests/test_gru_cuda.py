@@ -148,6 +148,39 @@ def test_mpe_gru_runs_at_baseline_scale(cuda):
     assert all(r["rollout_episode_reward"] < 0 for r in roll)
 
 
+def test_recurrent_sharded_buckets_sum_to_global_bucket(cuda):
+    """Multi-GPU contract of the recurrent update on one GPU: two halves of the chunk list processed with
+    norm_rows = global row-steps give gradient buckets whose SUM is the bucket of the whole chunk list."""
+    import torch
+
+    from openrl_b200 import lib
+    from openrl_b200.utils.logger import Logger
+    from test_rollout_cuda import _product
+
+    d = np.load(os.path.join(GOLDEN, "trace_mpe_gru.npz"), allow_pickle=True)
+    cfg, env, net, agent = _product("simple_spread", int(d["meta/env_num"]), str(d["meta/flags"]).split(), golden=d)
+    agent.train(total_time_steps=0, logger=Logger(quiet=True))
+    drv = agent.driver
+    drv.actor_rollout()
+    drv.compute_returns()
+    tr, b = drv.trainer, drv.buffer.data
+    Lc = cfg.data_chunk_length
+    chunks = b.episode_length * b.n_rollout_threads * b.num_agents // Lc
+    ids = torch.randperm(chunks).cuda()
+    tr.tape = torch.empty(int(tr._lib.orl_rnn_workspace_floats(chunks * Lc, tr.rnn_stride)), dtype=torch.float32, device="cuda")
+
+    def bucket(part, norm_rows):
+        a = tr._rnn_args(b, part.contiguous(), b.gae_stats[5:8])
+        a.norm_rows = norm_rows
+        lib.check(tr._lib.orl_rnn_fwdbwd(a, lib.current_stream()), "orl_rnn_fwdbwd")
+        return tr.rnn_bucket.clone()
+
+    whole = bucket(ids, 0)
+    parts = bucket(ids[:chunks // 3], chunks * Lc) + bucket(ids[chunks // 3:], chunks * Lc)   # uneven split: odd chunk counts too
+    np.testing.assert_allclose(parts.cpu().numpy(), whole.cpu().numpy(), rtol=2e-4, atol=2e-6)
+    assert float(whole[:2 * tr.rnn_stride].abs().max()) > 1e-3
+
+
 def test_recurrent_limits_are_loud(cuda):
     from openrl_b200.configs.config import create_config_parser
     from openrl_b200.envs.common import make

@@ -146,6 +146,41 @@ def test_whole_buffer_minibatch_equals_permuted_minibatch(cuda):
     np.testing.assert_allclose(res[0][1], res[1][1], rtol=1e-4, atol=1e-6)
 
 
+@pytest.mark.parametrize("tf32", [False, True])
+def test_sharded_minibatch_buckets_sum_to_global_bucket(cuda, tf32):
+    """Multi-GPU contract on one GPU: two ranks each process half of the global minibatch with norm_rows = global
+    rows and global batch moments; the SUM of their gradient buckets (what the NCCL all-reduce produces) equals the
+    bucket of the whole minibatch processed by one rank."""
+    import torch
+
+    from openrl_b200 import lib
+
+    d = np.load(os.path.join(GOLDEN, "trace_cartpole_c1.npz"), allow_pickle=True)
+    cfg, net, trainer, buf = _setup(d)
+    if tf32:
+        trainer.flags |= lib.PPO_TF32
+    _load_buffer(buf, d, 0)
+    vn = net.module.get_critic_value_normalizer()
+    buf.data.compute_returns(buf.data.value_preds[-1].clone(), vn)
+    total = cfg.episode_length * int(d["meta/env_num"])
+    perm = torch.from_numpy(d["it0/perms"][0]).cuda()
+    L, s = trainer._lib, lib.current_stream()
+
+    def bucket(indices, norm_rows):
+        a = trainer._args(buf.data, indices.numel(), indices.contiguous(), 0)
+        a.norm_rows = norm_rows
+        a.mb_stats = lib.ptr(buf.data.gae_stats[5:8])       # global moments of the whole minibatch
+        lib.check(L.orl_ppo_fwdbwd(a, s), "fwdbwd")
+        lib.check(L.orl_ppo_reduce(a, s), "reduce")
+        return trainer.folded.clone()
+
+    whole = bucket(perm, 0)
+    half = total // 2
+    parts = bucket(perm[:half], total) + bucket(perm[half:], total)
+    scale = float(whole.abs().max())
+    np.testing.assert_allclose(parts.cpu().numpy(), whole.cpu().numpy(), rtol=2e-4, atol=2e-6 * max(scale, 1.0))
+
+
 def test_tf32_tensor_core_update_matches_fp32_update(cuda):
     """Fast mode (tcgen05, TF32 operands) vs parity mode (fp32 FFMA) on the same minibatch: losses are
     means over rows so they agree to ~1e-4; gradients to TF32 accuracy."""
