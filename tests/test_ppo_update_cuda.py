@@ -177,8 +177,10 @@ def test_sharded_minibatch_buckets_sum_to_global_bucket(cuda, tf32):
     whole = bucket(perm, 0)
     half = total // 2
     parts = bucket(perm[:half], total) + bucket(perm[half:], total)
-    scale = float(whole.abs().max())
-    np.testing.assert_allclose(parts.cpu().numpy(), whole.cpu().numpy(), rtol=2e-4, atol=2e-6 * max(scale, 1.0))
+    # bucket row = folded gradients + 8 tail slots: loss sums in 0..2 (3..7 are the tcgen05 kernel's phase-cycle counters)
+    used = trainer.stride - 5
+    got, want = parts.cpu().numpy()[:, :used], whole.cpu().numpy()[:, :used]
+    np.testing.assert_allclose(got, want, rtol=2e-4, atol=2e-6 * max(float(np.abs(want).max()), 1.0))
 
 
 def test_tf32_tensor_core_update_matches_fp32_update(cuda):
