@@ -290,7 +290,7 @@ typedef struct OrlRnnArgs {
     int32_t env_kind, n_envs, n_agents, episode_length;   /* N, A, T; rows B = N*A */
     int32_t t_begin, t_end;
     int32_t obs_dim, critic_obs_dim, n_actions, activation_id;
-    int32_t deterministic, chunk_length;                  /* L = cfg.data_chunk_length (<= 4) */
+    int32_t deterministic, chunk_length;                  /* L = cfg.data_chunk_length (<= 32) */
     int32_t flags;                                        /* ORL_PPO_* */
     int32_t env_table_len;
     int64_t n_chunks;                                     /* chunks in this minibatch */

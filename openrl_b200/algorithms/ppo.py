@@ -13,6 +13,7 @@ permutation is needed at all (a minibatch that is the whole buffer is a sum over
 import numpy as np
 import torch
 from .. import lib, parallel
+from ..buffers.replay_data import chunk_row_indices
 
 
 class PPOAlgorithm:
@@ -59,8 +60,8 @@ class PPOAlgorithm:
         if self.recurrent:
             if self.head_kind != lib.HEAD_CATEGORICAL:
                 raise NotImplementedError("recurrent policies are built for Discrete action spaces")
-            if not 1 <= cfg.data_chunk_length <= 4:
-                raise NotImplementedError("data_chunk_length must be in [1, 4] for the recurrent kernels")
+            if not 1 <= cfg.data_chunk_length <= 32:
+                raise NotImplementedError("data_chunk_length must be in [1, 32] for the recurrent kernels")
             self.use_tf32 = False
             self.flags &= ~lib.PPO_TF32
             self.rnn_stride = (max(self._lib.orl_rnn_param_count(self.d, self.n), self._lib.orl_rnn_param_count(self.dc, 1)) + 3) & ~3
@@ -185,7 +186,6 @@ class PPOAlgorithm:
             self.tape = torch.empty(need, dtype=torch.float32, device=self.device)
         whole = self.num_mini_batch == 1 and rows == total
         s, Lb = lib.current_stream(), self._lib
-        lane = torch.arange(L, device=self.device)
         for _ in range(self.ppo_epoch):
             if cfg.parity_mode:
                 perm = torch.randperm(data_chunks).to(self.device, non_blocking=True)   # global CPU generator
@@ -197,8 +197,7 @@ class PPOAlgorithm:
                 if whole:
                     mb_stats = buf.gae_stats[5:8]
                 else:
-                    f = (ids[:, None] * L + lane[None, :]).reshape(-1)
-                    bi = ((f % T) * B + f // T).contiguous()        # buffer row of (t, row) is t*B + row
+                    bi = chunk_row_indices(ids, L, T, B)
                     lib.check(Lb.orl_minibatch_stats(lib.ptr(bi), int(rows), lib.ptr(buf.returns), lib.ptr(buf.active_masks),
                                                      lib.ptr(self.mb_stats), s), "orl_minibatch_stats")
                     mb_stats = self.mb_stats

@@ -15,6 +15,20 @@ import torch
 from .. import lib
 
 
+def chunk_row_indices(chunk_ids, chunk_length, episode_length, rows):
+    """Buffer row index t*B + row of every step of the given data chunks, chunk-major / step-minor.
+
+    `recurrent_generator` (replay_data.py:1062-1258) flattens (T, N, A, ...) agent-major / time-minor
+    (`_cast`, buffers/utils/util.py:96-97): sample f = (n*A + a)*T + t; chunk c holds f in [c*L, c*L + L) and does
+    not stop at trajectory boundaries.  The device buffer keeps the (T, B) layout, so sample f is row
+    (f % T)*B + f // T."""
+    import torch
+
+    lane = torch.arange(chunk_length, device=chunk_ids.device)
+    f = (chunk_ids[:, None] * chunk_length + lane[None, :]).reshape(-1)
+    return ((f % episode_length) * rows + f // episode_length).contiguous()
+
+
 class ReplayData:
     def __init__(self, cfg, num_agents, obs_space, act_space, data_client=None, episode_length=None, device="cuda:0"):
         T = cfg.episode_length if episode_length is None else episode_length

@@ -28,7 +28,7 @@ namespace rc = orl_rnn;
 namespace rw = orl_rnnw;
 
 static_assert(rc::MAXN == MAX_OUT, "head width limits must agree");
-constexpr int LMAX = 4;      // data_chunk_length limit accepted by the host API (the tape is sized n_chunks * L rows)
+constexpr int LMAX = 32;     // data_chunk_length limit accepted by the host API (the chunk kernels loop over l; the tape is n_chunks * L rows)
 constexpr int RNN_NT = 64;   // threads per CTA of the sequential kernels
 
 __device__ __forceinline__ int pick_action(const OrlRnnArgs& a, const float (&pr)[MAX_OUT], int n, size_t grow, int row,
@@ -591,7 +591,7 @@ int orl_rnn_fwdbwd(const OrlRnnArgs* ap, void* stream) {
     ORL_CHECK_ARG(ap, "args");
     const OrlRnnArgs& a = *ap;
     if (int e = check_common(a)) return e;
-    ORL_CHECK_ARG(a.chunk_length >= 1 && a.chunk_length <= LMAX, "chunk_length (data_chunk_length) must be in [1, 4]");
+    ORL_CHECK_ARG(a.chunk_length >= 1 && a.chunk_length <= LMAX, "chunk_length (data_chunk_length) must be in [1, 32]");
     ORL_CHECK_ARG(a.n_chunks > 0 && a.chunk_ids, "chunks");
     ORL_CHECK_ARG(a.policy_params && a.critic_params && a.policy_obs && a.critic_obs && a.rnn_states && a.rnn_states_critic &&
                       a.actions && a.action_log_probs && a.masks && a.active_masks && a.value_preds && a.returns && a.advantages,

@@ -187,7 +187,7 @@ def test_recurrent_limits_are_loud(cuda):
     from openrl_b200.modules.common import PPONet
     from openrl_b200.runners.common import PPOAgent
 
-    cfg = create_config_parser().parse_args(["--use_recurrent_policy", "true", "--data_chunk_length", "10"])
+    cfg = create_config_parser().parse_args(["--use_recurrent_policy", "true", "--data_chunk_length", "100"])
     cfg.quiet = True
     agent = PPOAgent(PPONet(make("CartPole-v1", env_num=2), cfg=cfg, device="cuda:0"))
     with pytest.raises(NotImplementedError):

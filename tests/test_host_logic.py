@@ -97,3 +97,23 @@ def test_cpu_device_is_refused():
 
     with pytest.raises(RuntimeError, match="CUDA only"):
         PPONet(Env(), cfg=create_config_parser().parse_args([]), device="cpu")
+
+
+def test_chunk_row_indices_follow_the_reference_cast():
+    """Chunks of the recurrent generator address the (T, B) device buffer exactly like the reference's
+    agent-major / time-minor `_cast` flattening (buffers/utils/util.py:96-97), including chunks that straddle rows."""
+    import torch
+
+    from openrl_b200.buffers.replay_data import chunk_row_indices
+    from oracle.loop_ma import _cast
+
+    T, N, A, L = 25, 4, 3, 2
+    B = N * A
+    x = np.arange(T * B, dtype=np.int64).reshape(T, N, A, 1)   # value = its own buffer row index t*B + row
+    flat = _cast(x)[:, 0]                                       # reference order of the samples
+    chunks = (T * B) // L
+    ids = torch.randperm(chunks)
+    got = chunk_row_indices(ids, L, T, B).numpy().reshape(chunks, L)
+    want = np.stack([flat[c * L:c * L + L] for c in ids.numpy()])
+    assert np.array_equal(got, want)
+    assert any((w // 1)[0] % B != (w // 1)[1] % B for w in want)   # some chunks straddle two rows (T odd, L = 2)
