@@ -221,13 +221,14 @@ class OnPolicyDriver:
                 if cb.on_step() is False:
                     return {}, False
         batch_rew_infos = self.envs.batch_rewards(self.buffer)
+        cont = True
         if cb is not None:
-            cb.on_rollout_end()
+            cont = cb.on_rollout_end() is not False   # callbacks without per-step hooks stop training here
         if self.envs.use_monitor:
             info = self.envs.statistics(self.buffer)
             info.update(batch_rew_infos)
-            return info, True
-        return batch_rew_infos, True
+            return info, cont
+        return batch_rew_infos, cont
 
     def _host_rollout(self, cb):
         """Per-step loop for host-stepped envs (onpolicy_driver.py:154-203): device act -> D2H actions

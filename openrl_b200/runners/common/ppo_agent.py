@@ -86,6 +86,13 @@ class PPOAgent:
         actions, _ = self.net.act(obs.reshape(N * A, -1), deterministic=deterministic, episode_starts=episode_starts)
         return actions.view(N, A, 1).cpu().numpy().astype(np.int64), None
 
+    def get_env(self):
+        return self._env
+
+    @property
+    def logger(self):
+        return getattr(self, "_logger", None)
+
     def set_env(self, env):
         self.net.reset(env)
         self._env = env

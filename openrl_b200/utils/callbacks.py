@@ -53,10 +53,12 @@ class BaseCallback:
         pass
 
     def on_rollout_end(self):
-        self._on_rollout_end()
+        """Returning False stops training (how callbacks that do not need per-step locals end a run: the device
+        driver collects a whole rollout in one launch and never calls on_step for them)."""
+        return self._on_rollout_end()
 
     def _on_rollout_end(self):
-        pass
+        return None
 
     def update_locals(self, locals_):
         self.locals.update(locals_)
@@ -98,8 +100,10 @@ class CallbackList(BaseCallback):
         return cont
 
     def _on_rollout_end(self):
+        cont = True
         for c in self.callbacks:
-            c.on_rollout_end()
+            cont = (c.on_rollout_end() is not False) and cont
+        return cont
 
     def _on_training_end(self):
         for c in self.callbacks:
@@ -119,3 +123,96 @@ class StopTrainingOnMaxSteps(BaseCallback):
 
     def _on_step(self):
         return self.n_calls < self.max_calls
+
+
+class EvalCallback(BaseCallback):
+    """Periodic evaluation on a second vector env (reference: openrl/utils/callbacks/eval_callback.py:53-284).
+
+    `eval_freq` counts vector-env steps like the reference's `n_calls % eval_freq`; because this callback does not
+    look at per-step locals the device driver keeps collecting whole rollouts in one launch and the evaluation runs
+    at the first rollout boundary at or after each multiple of `eval_freq`.  Logs Eval/episode_reward(_std),
+    Eval/episode_length(_std) through the agent's logger, appends to `<log_path>/evaluations.npz`, saves the best
+    model to `<best_model_save_path>/best_model` and calls `callbacks_on_new_best` / `callbacks_after_eval`
+    (their on_step() returning False stops training)."""
+
+    needs_per_step = False
+
+    def __init__(self, eval_env, callbacks_on_new_best=None, callbacks_after_eval=None, n_eval_episodes=5, eval_freq=10000,
+                 log_path=None, best_model_save_path=None, deterministic=True, render=False, asynchronous=True, verbose=1,
+                 warn=True, stop_logic="OR", close_env_at_end=True):
+        super().__init__(verbose=verbose)
+        if isinstance(eval_env, (str, dict)):
+            from ..envs.common import make
+            spec = {"id": eval_env, "env_num": 1} if isinstance(eval_env, str) else eval_env
+            eval_env = make(spec["id"], env_num=spec.get("env_num", 1))
+        self.eval_env = eval_env
+        self.callbacks_on_new_best, self.callback = callbacks_on_new_best, callbacks_after_eval
+        self.n_eval_episodes, self.eval_freq = n_eval_episodes, eval_freq
+        self.deterministic, self.render, self.warn = deterministic, render, warn
+        self.close_env_at_end = close_env_at_end
+        self.best_mean_reward = self.last_mean_reward = -float("inf")
+        self.best_model_save_path = best_model_save_path
+        self.log_path = None if log_path is None else __import__("os").path.join(str(log_path), "evaluations")
+        self.evaluations_results, self.evaluations_time_steps, self.evaluations_length = [], [], []
+        self._evals_done = 0
+
+    def _init_callback(self):
+        import os
+        if self.best_model_save_path is not None:
+            os.makedirs(self.best_model_save_path, exist_ok=True)
+        if self.log_path is not None:
+            os.makedirs(os.path.dirname(self.log_path), exist_ok=True)
+        for cb in (self.callbacks_on_new_best, self.callback):
+            if cb is not None:
+                cb.set_parent(self)
+                cb.init_callback(self.agent)
+
+    def _on_rollout_end(self):
+        import os
+
+        import numpy as np
+
+        from .evaluation import evaluate_policy
+
+        self.num_time_steps = self.agent.num_time_steps
+        if self.eval_freq <= 0:
+            return True
+        vec_steps = self.num_time_steps // max(1, getattr(self.agent, "env_num", 1))
+        due = vec_steps // self.eval_freq
+        if due <= self._evals_done:
+            return True
+        self._evals_done = due
+        rewards, lengths = evaluate_policy(self.agent, self.eval_env, n_eval_episodes=self.n_eval_episodes, render=self.render,
+                                           deterministic=self.deterministic, return_episode_rewards=True, warn=self.warn)
+        if self.log_path is not None:
+            self.evaluations_time_steps.append(self.num_time_steps)
+            self.evaluations_results.append(rewards)
+            self.evaluations_length.append(lengths)
+            np.savez(self.log_path, timesteps=self.evaluations_time_steps, results=self.evaluations_results,
+                     ep_lengths=self.evaluations_length)
+        mean_reward, std_reward = float(np.mean(rewards)), float(np.std(rewards))
+        self.last_mean_reward = mean_reward
+        info = {"Eval/episode_reward": mean_reward, "Eval/episode_reward_std": std_reward,
+                "Eval/episode_length": float(np.mean(lengths)), "Eval/episode_length_std": float(np.std(lengths))}
+        if self.verbose >= 1:
+            print(f"Eval num_timesteps={self.num_time_steps}, episode_reward={mean_reward:.2f} +/- {std_reward:.2f}")
+        cont = True
+        if mean_reward > self.best_mean_reward:
+            self.best_mean_reward = mean_reward
+            if self.best_model_save_path is not None:
+                self.agent.save(os.path.join(self.best_model_save_path, "best_model"))
+                with open(os.path.join(self.best_model_save_path, "best_model_info.txt"), "w") as f:
+                    f.write(f"best model at step: {self.num_time_steps}\n")
+                    f.write(f"best model reward: {mean_reward}\n")
+            if self.callbacks_on_new_best is not None:
+                cont = self.callbacks_on_new_best.on_step() is not False
+        if self.callback is not None:
+            cont = (self.callback.on_step() is not False) and cont
+        logger = getattr(self.agent, "logger", None)
+        if logger is not None:
+            logger.log_info(info, self.num_time_steps)
+        return cont
+
+    def _on_training_end(self):
+        if self.close_env_at_end and hasattr(self.eval_env, "close"):
+            self.eval_env.close()

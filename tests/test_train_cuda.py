@@ -135,3 +135,29 @@ def test_gridworld_train_matches_reference_trace(cuda):
     assert np.array_equal(b.actions.cpu().numpy(), d[f"it{last}/actions"])
     assert np.array_equal(b.policy_obs.cpu().numpy()[1:], d[f"it{last}/policy_obs"][1:].astype(np.float32))
     assert np.array_equal(b.rewards.cpu().numpy(), d[f"it{last}/rewards"])
+
+
+def test_eval_callback_on_device(cuda, tmp_path):
+    """EvalCallback (reference utils/callbacks/eval_callback.py:53-284) through the device path: a second device
+    vec-env, agent.act with episode_starts, best-model checkpoint, training env restored, one-launch rollouts kept."""
+    from openrl_b200.configs.config import create_config_parser
+    from openrl_b200.envs.common import make
+    from openrl_b200.modules.common import PPONet
+    from openrl_b200.runners.common import PPOAgent
+    from openrl_b200.utils.callbacks import EvalCallback
+    from openrl_b200.utils.logger import Logger
+
+    cfg = create_config_parser().parse_args(["--episode_length", "64", "--ppo_epoch", "2", "--log_interval", "1"])
+    cfg.quiet = True
+    env = make("CartPole-v1", env_num=4)
+    agent = PPOAgent(PPONet(env, cfg=cfg, device="cuda:0"))
+    ev = make("CartPole-v1", env_num=3)
+    cb = EvalCallback(ev, n_eval_episodes=3, eval_freq=64, best_model_save_path=str(tmp_path / "best"), verbose=0,
+                      close_env_at_end=False)
+    logger = Logger(quiet=True)
+    agent.train(total_time_steps=64 * 4 * 2, callback=cb, logger=logger)
+    evals = [h[1] for h in logger.history if "Eval/episode_reward" in h[1]]
+    assert len(evals) == 2 and all(e["Eval/episode_reward"] >= 8 and e["Eval/episode_length"] >= 8 for e in evals), evals
+    assert (tmp_path / "best" / "best_model" / "module.pt").exists()
+    assert agent.get_env() is env and agent.env_num == 4
+    assert agent.driver.gpu_launches < 40        # whole-rollout launches, not 64 per-step launches per iteration
