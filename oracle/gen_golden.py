@@ -228,6 +228,12 @@ def main():
                    "--use_recurrent_policy", "true", "--use_valuenorm", "true", "--use_adv_normalize", "true",
                    "--log_interval", "1000"],
                   2, "mpe_gru")
+    if a.only in ("", "cartpole_gru"):
+        # single-agent recurrent PPO: episodes end mid-rollout (masks == 0 inside chunks), chunks of 4, two minibatches
+        gen_trace("CartPole-v1", 8,
+                  ["--seed", "0", "--episode_length", "32", "--ppo_epoch", "2", "--num_mini_batch", "2",
+                   "--use_recurrent_policy", "true", "--data_chunk_length", "4", "--log_interval", "1000"],
+                  2, "cartpole_gru")
     if a.only in ("", "gaussian"):
         gen_trace("IdentityEnvcontinuous", 4,
                   ["--seed", "0", "--episode_length", "16", "--ppo_epoch", "2", "--num_mini_batch", "2", "--log_interval", "1000"],

@@ -24,6 +24,11 @@ from . import gae as ogae
 from . import nets, ppo
 
 
+def _obs_pair(obs):
+    """Dict observation spaces feed policy / critic separately; plain spaces give both nets the same array."""
+    return (obs["policy"], obs["critic"]) if isinstance(obs, dict) else (obs, obs)
+
+
 def _cast(x):
     """(T, N, A, d) -> (N*A*T, d), agent-major / time-minor (buffers/utils/util.py:96-97)."""
     return x.transpose(1, 2, 0, 3).reshape(-1, *x.shape[3:])
@@ -37,7 +42,8 @@ class MATrainer:
         torch.manual_seed(cfg.seed)
         self.env = oenvs.ENVS[env_id](env_num)
         self.env.reset(seed=cfg.seed)
-        A, d, dc, n = self.env.agent_num, self.env.obs_dim, self.env.critic_obs_dim, self.env.n_actions
+        A, d, n = self.env.agent_num, self.env.obs_dim, self.env.n_actions
+        dc = getattr(self.env, "critic_obs_dim", d)
         self.A = A
         self.pol = nets.init_policy(cfg, d, "Discrete", n)
         self.cri = nets.init_critic(cfg, dc)
@@ -51,9 +57,7 @@ class MATrainer:
             rnn_states_critic=f(T + 1, N, A, 1, H), value_preds=f(T + 1, N, A, 1), returns=f(T + 1, N, A, 1),
             masks=one(T + 1, N, A, 1), bad_masks=one(T + 1, N, A, 1), active_masks=one(T + 1, N, A, 1),
             action_masks=one(T + 1, N, A, n), actions=f(T, N, A, 1), action_log_probs=f(T, N, A, 1), rewards=f(T, N, A, 1))
-        obs = self.env.reset()
-        self.buf.policy_obs[0] = obs["policy"]
-        self.buf.critic_obs[0] = obs["critic"]
+        self.buf.policy_obs[0], self.buf.critic_obs[0] = _obs_pair(self.env.reset())
 
     def rollout(self):
         cfg, b, N, A = self.cfg, self.buf, self.N, self.A
@@ -80,8 +84,7 @@ class MATrainer:
             active = np.ones((N, A, 1), np.float32)
             active[dones] = 0.0
             active[dones_env] = 1.0
-            b.policy_obs[step + 1] = obs2["policy"]
-            b.critic_obs[step + 1] = obs2["critic"]
+            b.policy_obs[step + 1], b.critic_obs[step + 1] = _obs_pair(obs2)
             b.actions[step] = actions
             b.action_log_probs[step] = logp.numpy().reshape(N, A, 1)
             b.value_preds[step] = values.numpy().reshape(N, A, 1)

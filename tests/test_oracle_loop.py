@@ -48,15 +48,16 @@ def test_oracle_reproduces_reference_trace(tag, env_id):
         np.testing.assert_allclose(tr.vn.state(), d[f"it{it}/vn_after_update"], rtol=1e-6)
 
 
-@pytest.mark.parametrize("tag", ["mpe_mlp", "mpe_gru"])
-def test_multi_agent_oracle_reproduces_reference_trace(tag):
+@pytest.mark.parametrize("tag,env_id", [("mpe_mlp", "simple_spread"), ("mpe_gru", "simple_spread"), ("cartpole_gru", "CartPole-v1")])
+def test_multi_agent_oracle_reproduces_reference_trace(tag, env_id):
     """MAPPO on simple_spread (3 agents, shared nets; feed-forward and GRU + chunked BPTT with
-    data_chunk_length 2) vs the unmodified reference."""
+    data_chunk_length 2) and single-agent recurrent PPO on CartPole-v1 (episodes ending inside chunks of 4,
+    two minibatches) vs the unmodified reference."""
     from oracle import loop_ma
 
     d = np.load(os.path.join(GOLDEN, f"trace_{tag}.npz"), allow_pickle=True)
     cfg = loop.cfg_from_flags(str(d["meta/flags"]))
-    tr = loop_ma.MATrainer(cfg, "simple_spread", int(d["meta/env_num"]))
+    tr = loop_ma.MATrainer(cfg, env_id, int(d["meta/env_num"]))
     for mk, prm in (("policy", tr.pol), ("critic", tr.cri)):
         for k, v in prm.items():
             np.testing.assert_allclose(v.detach().numpy(), d[f"init/{mk}.{k}"], rtol=0, atol=1e-6, err_msg=k)

@@ -161,3 +161,13 @@ def test_eval_callback_on_device(cuda, tmp_path):
     assert (tmp_path / "best" / "best_model" / "module.pt").exists()
     assert agent.get_env() is env and agent.env_num == 4
     assert agent.driver.gpu_launches < 40        # whole-rollout launches, not 64 per-step launches per iteration
+
+
+def test_recurrent_cartpole_matches_reference_trace(cuda):
+    """Single-agent recurrent PPO vs the unmodified reference (tests/golden/trace_cartpole_gru.npz: 8 envs, T=32,
+    data_chunk_length 4, two minibatches per epoch): episodes end INSIDE chunks here, so the masked hidden-state
+    carry and its backward are exercised (the simple_spread trace only has episode ends at rollout boundaries).
+    Added at the end of round 1 after the GPU budget was spent: first run is the driver's."""
+    from test_gru_cuda import check_recurrent_trace
+
+    check_recurrent_trace("cartpole_gru", "CartPole-v1")
