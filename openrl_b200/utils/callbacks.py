@@ -216,3 +216,96 @@ class EvalCallback(BaseCallback):
     def _on_training_end(self):
         if self.close_env_at_end and hasattr(self.eval_env, "close"):
             self.eval_env.close()
+
+
+class CheckpointCallback(BaseCallback):
+    """agent.save(<save_path>/<name_prefix>_<num_time_steps>_steps) every `save_freq` vector-env steps
+    (reference: utils/callbacks/checkpoint_callback.py:26-100).  Needs no per-step locals: the check runs at rollout
+    boundaries, so the device driver keeps its one-launch rollouts."""
+
+    needs_per_step = False
+
+    def __init__(self, save_freq, save_path, name_prefix="rl_model", save_replay_buffer=False, verbose=0):
+        super().__init__(verbose)
+        if save_replay_buffer:
+            raise NotImplementedError("on-policy agents have no replay buffer to checkpoint")
+        self.save_freq, self.save_path, self.name_prefix = save_freq, str(save_path), name_prefix
+        self._saves_done = 0
+
+    def _init_callback(self):
+        import os
+        os.makedirs(self.save_path, exist_ok=True)
+
+    def _on_rollout_end(self):
+        import os
+        self.num_time_steps = self.agent.num_time_steps
+        due = (self.num_time_steps // max(1, getattr(self.agent, "env_num", 1))) // self.save_freq
+        if due > self._saves_done:
+            self._saves_done = due
+            path = os.path.join(self.save_path, f"{self.name_prefix}_{self.num_time_steps}_steps")
+            self.agent.save(path)
+            if self.verbose >= 2:
+                print(f"Saving model checkpoint to {path}")
+        return True
+
+
+class StopTrainingOnRewardThreshold(BaseCallback):
+    """Child of EvalCallback (`callbacks_on_new_best`): stop once the best mean evaluation reward reaches the threshold
+    (reference: utils/callbacks/stop_callback.py:23-53)."""
+
+    def __init__(self, reward_threshold, verbose=0):
+        super().__init__(verbose)
+        self.reward_threshold = reward_threshold
+
+    def _on_step(self):
+        assert self.parent is not None, "StopTrainingOnRewardThreshold must be used with an EvalCallback"
+        cont = bool(self.parent.best_mean_reward < self.reward_threshold)
+        if self.verbose >= 1 and not cont:
+            print(f"Stopping training because the mean reward {self.parent.best_mean_reward:.2f} is above the threshold "
+                  f"{self.reward_threshold}")
+        return cont
+
+
+class StopTrainingOnNoModelImprovement(BaseCallback):
+    """Child of EvalCallback (`callbacks_after_eval`): stop after more than `max_no_improvement_evals` consecutive
+    evaluations without a new best mean reward, counting only after `min_evals` evaluations
+    (reference: utils/callbacks/stop_callback.py:107-160)."""
+
+    def __init__(self, max_no_improvement_evals, min_evals=0, verbose=0):
+        super().__init__(verbose)
+        self.max_no_improvement_evals, self.min_evals = max_no_improvement_evals, min_evals
+        self.last_best_mean_reward = -float("inf")
+        self.no_improvement_evals = 0
+
+    def _on_step(self):
+        assert self.parent is not None, "StopTrainingOnNoModelImprovement must be used with an EvalCallback"
+        cont = True
+        if self.n_calls > self.min_evals:
+            if self.parent.best_mean_reward > self.last_best_mean_reward:
+                self.no_improvement_evals = 0
+            else:
+                self.no_improvement_evals += 1
+                cont = self.no_improvement_evals <= self.max_no_improvement_evals
+        self.last_best_mean_reward = self.parent.best_mean_reward
+        return cont
+
+
+class StopTrainingOnMaxEpisodes(BaseCallback):
+    """Stop after max_episodes * n_envs finished episodes, counted from the per-step `dones` local
+    (reference: utils/callbacks/stop_callback.py:56-104) — so this one keeps the per-step launch mode."""
+
+    needs_per_step = True
+
+    def __init__(self, max_episodes, verbose=0):
+        super().__init__(verbose)
+        self.max_episodes, self.n_episodes, self._total = max_episodes, 0, max_episodes
+
+    def _init_callback(self):
+        self._total = self.max_episodes * getattr(self.agent, "env_num", 1)
+
+    def _on_step(self):
+        import numpy as np
+        assert "dones" in self.locals, "`dones` is not among the step locals"
+        d = np.asarray(self.locals["dones"])
+        self.n_episodes += int(np.all(d.reshape(d.shape[0], -1), axis=1).sum())
+        return self.n_episodes < self._total

@@ -112,3 +112,40 @@ def test_eval_callback_triggers_at_rollout_boundaries_saves_best_and_can_stop(tm
     assert cbs.on_rollout_end() is False
     cbs.on_training_end()
     assert eval_env.closed
+
+
+def test_checkpoint_and_stop_callbacks(tmp_path):
+    from openrl_b200.utils.callbacks import (CheckpointCallback, StopTrainingOnMaxEpisodes, StopTrainingOnNoModelImprovement,
+                                             StopTrainingOnRewardThreshold)
+
+    train_env, eval_env = ScriptedVecEnv([5, 5, 5, 5]), ScriptedVecEnv([3])
+    agent = ScriptedAgent(train_env)
+    ck = CheckpointCallback(save_freq=16, save_path=str(tmp_path / "ckpt"), name_prefix="m")
+    ev = EvalCallback(eval_env, callbacks_on_new_best=StopTrainingOnRewardThreshold(100.0),
+                      callbacks_after_eval=StopTrainingOnNoModelImprovement(max_no_improvement_evals=1, min_evals=0),
+                      n_eval_episodes=1, eval_freq=8, verbose=0, close_env_at_end=False)
+    cbs = CallbackList([ck, ev])
+    assert cbs.needs_per_step is False
+    cbs.init_callback(agent)
+    cbs.on_training_start({}, {})
+    conts = []
+    for _ in range(4):                               # rollouts of 8 vector steps on 4 envs
+        agent.num_time_steps += 32
+        conts.append(cbs.on_rollout_end())
+    # evaluations: best = 3.0 at the first, then no improvement twice -> stop at the third evaluation
+    assert conts[:3] == [True, True, False]
+    assert [os.path.basename(p) for p in agent.saved if "ckpt" in p] == ["m_64_steps", "m_128_steps"]   # vec steps 16, 32
+    assert os.path.isdir(tmp_path / "ckpt")
+    # episode counter on per-step locals: 2 episodes per env over 4 envs
+    mx = StopTrainingOnMaxEpisodes(max_episodes=2)
+    assert mx.needs_per_step is True
+    mx.init_callback(agent)
+    mx.on_training_start({}, {})
+    env = ScriptedVecEnv([2, 2, 2, 2], agents=1)
+    env.reset()
+    res = []
+    for _ in range(6):
+        _, _, dones, _ = env.step(np.zeros((4, 1, 1), np.int64))
+        mx.update_locals({"dones": dones})
+        res.append(mx.on_step())
+    assert res == [True, True, True, False, False, False]   # 8 episodes reached at the 4th step
