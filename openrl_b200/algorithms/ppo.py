@@ -232,6 +232,12 @@ class PPOAlgorithm:
             self._lrs_host = lrs
             self.h2d_bytes += 8
         self.train_info.zero_()
+        if not getattr(buf, "returns_ready", True):
+            # train() on a buffer whose returns were never computed (the reference's algorithm tests call it on a fresh
+            # buffer, tests/test_algorithm/test_ppo_algorithm.py:76-82): the reference derives the advantages inside
+            # train_ppo from whatever the buffer holds; here that is the GAE launch with the bootstrap value of slot T
+            buf.compute_returns(None, self.algo_module.get_critic_value_normalizer())
+            self.gpu_launches += 1
         parallel.allreduce_sum_(buf.gae_stats)  # global advantage / return moments (ppo.py:402-409 semantics)
         if self.recurrent:
             return self._train_recurrent(buf)

@@ -73,6 +73,7 @@ class ReplayData:
         else:
             self.rnn_states = self.rnn_states_critic = None
         self.step = 0
+        self.returns_ready = False   # set by compute_returns, cleared by after_update (see PPOAlgorithm.train_async)
         self._lib = lib.load()
 
     def init_buffer(self, raw_obs, action_masks=None):
@@ -82,6 +83,7 @@ class ReplayData:
 
     def after_update(self):
         """replay_data.py:300-318 — slot T becomes slot 0 of the next rollout."""
+        self.returns_ready = False
         self.policy_obs[0].copy_(self.policy_obs[-1])
         if self.critic_obs is not self.policy_obs:
             self.critic_obs[0].copy_(self.critic_obs[-1])
@@ -110,3 +112,4 @@ class ReplayData:
                                     lib.ptr(self.bad_masks), lib.ptr(self.active_masks), lib.ptr(nv), lib.ptr(vn),
                                     lib.ptr(self.returns), lib.ptr(self.advantages), lib.ptr(self.gae_stats), T, B,
                                     float(self.gamma), float(self.gae_lambda), flags, lib.current_stream()), "orl_gae")
+        self.returns_ready = True

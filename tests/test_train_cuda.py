@@ -171,3 +171,25 @@ def test_recurrent_cartpole_matches_reference_trace(cuda):
     from test_gru_cuda import check_recurrent_trace
 
     check_recurrent_trace("cartpole_gru", "CartPole-v1")
+
+
+def test_algorithm_train_on_fresh_buffer(cuda):
+    """The reference's algorithm-level seam (tests/test_algorithm/test_ppo_algorithm.py:36-82): build the module and a
+    NormalReplayBuffer from spaces, call PPOAlgorithm(cfg, module).train(buffer.data) on the untouched buffer.
+    Added at the end of round 1 after the GPU budget was spent: first run is the driver's."""
+    from openrl_b200 import spaces
+    from openrl_b200.algorithms.ppo import PPOAlgorithm
+    from openrl_b200.buffers import NormalReplayBuffer
+    from openrl_b200.configs.config import create_config_parser
+    from openrl_b200.modules.ppo_module import PPOModule
+
+    cfg = create_config_parser().parse_args(["--use_share_model", "false"])
+    obs_space = spaces.Box(low=-np.inf, high=np.inf, shape=(4,), dtype=np.float32)   # (the reference's fixture uses shape (1,))
+    act_space = spaces.Discrete(2)
+    module = PPOModule(cfg, policy_input_space=obs_space, critic_input_space=obs_space, act_space=act_space,
+                       share_model=cfg.use_share_model, device="cuda:0")
+    buffer = NormalReplayBuffer(cfg, num_agents=1, obs_space=obs_space, act_space=act_space, data_client=None, episode_length=100)
+    info = PPOAlgorithm(cfg, module).train(buffer.data)
+    assert set(info) == {"value_loss", "critic_grad_norm", "policy_loss", "dist_entropy", "actor_grad_norm", "ratio"}
+    assert np.isfinite(list(info.values())).all(), info
+    assert abs(info["dist_entropy"] - np.log(2)) < 1e-2
