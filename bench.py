@@ -30,6 +30,7 @@ N_ENVS, T, EPOCHS, MINIBATCH = 4096, 128, 4, 1
 FLAGS = ["--seed", "0", "--episode_length", str(T), "--ppo_epoch", str(EPOCHS), "--num_mini_batch", str(MINIBATCH),
          "--log_interval", "1000000", "--log_each_episode", "false"]
 WORKLOAD = f"CartPole-v1 PPO, {N_ENVS} envs/GPU, T={T}, {EPOCHS} epochs x {MINIBATCH} minibatch, MLP 64x64"
+METRIC = "env-steps/sec (collect+update), CartPole-v1 PPO"
 
 
 def peaks():
@@ -294,8 +295,9 @@ def _best_cpu_threads(n_envs):
 
 
 def cpu_baseline_sample(n_envs=256, iters=1):
-    """Oracle port of the reference path on the host cores, bounded sample of the same workload
-    (same T / epochs / nets, fewer envs: the per-env Python loop makes cost linear in envs)."""
+    """cpu_baseline leg: the unmodified reference (`kind: reference`, baseline/_ref through
+    oracle/run_reference.py, SyncVectorEnv, 128 of the 4096 envs, all host cores) with the oracle port
+    (oracle/loop.py) timed beside it as a second, labelled number."""
     from oracle import loop as oloop
 
     threads = _best_cpu_threads(n_envs)
@@ -306,38 +308,88 @@ def cpu_baseline_sample(n_envs=256, iters=1):
     for _ in range(iters):
         tr.iteration()
     dt = time.perf_counter() - t0
-    return {"value": n_envs * T * iters / dt, "unit": "env-steps/s", "cores": threads, "kind": "port",
-            "sample": f"{iters} iteration(s) of {n_envs} envs x T={T}, {EPOCHS} epochs (oracle/loop.py, torch-CPU + numpy); "
-                      f"torch threads chosen by a 1-iteration calibration"}
+    port = {"value": n_envs * T * iters / dt, "unit": "env-steps/s", "cores": threads, "kind": "port",
+            "sample": f"{iters} iteration(s) of {n_envs} envs x T={T}, {EPOCHS} epochs (oracle/loop.py, torch-CPU + numpy)"}
+    if not reference_available():
+        return {**port, "note": "baseline/_ref missing: port only"}
+    try:
+        ref = reference_run(REF_ENVS, 5, 3)
+    except Exception as e:  # noqa: BLE001
+        return {**port, "note": f"reference run failed ({str(e)[-200:]}): port only"}
+    return {"value": ref["env_steps_per_s"], "unit": "env-steps/s", "cores": ref["torch_threads"], "kind": "reference",
+            "sample": f"5 PPOAgent.train iterations (after 3 warm-up) of {REF_ENVS} of the {N_ENVS} envs x T={T}, {EPOCHS} epochs; unmodified "
+                      f"reference from baseline/_ref, SyncVectorEnv, {ref['host_cores']} host cores", "port": port}
+
+
+def reference_run(envs, iters, warmup, asynchronous=False, timeout=900):
+    """One timed run of the UNMODIFIED reference (baseline/_ref, oracle/run_reference.py) in a fresh
+    process: `PPOAgent.train` on the host cores, all of them (the child resets torchrun's OMP_NUM_THREADS=1)."""
+    cmd = [sys.executable, os.path.join(ROOT, "oracle", "run_reference.py"), "--env", "CartPole-v1", "--envs", str(envs),
+           "--T", str(T), "--epochs", str(EPOCHS), "--minibatch", str(MINIBATCH), "--iters", str(iters), "--warmup", str(warmup)]
+    if asynchronous:
+        cmd.append("--async")
+    env = {k: v for k, v in os.environ.items() if k not in ("OMP_NUM_THREADS", "MKL_NUM_THREADS")}
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    if r.returncode != 0 or not lines:
+        raise RuntimeError(f"reference run failed (rc {r.returncode}): {r.stderr[-800:]}")
+    return json.loads(lines[-1])
+
+
+def reference_available():
+    return os.path.isfile(os.path.join(ROOT, "baseline", "_ref", "openrl", "__init__.py"))
+
+
+REF_ENVS = 128   # north_star's target point; the reference's per-env Python loop makes cost linear in envs
 
 
 def run_reference(args):
+    """Reference arm: the unmodified reference through its own public API (`make` -> `PPONet` ->
+    `PPOAgent.train`, SyncVectorEnv) on the box's host cores.  Each step = one iteration of a bounded
+    sample (128 of the 4096 envs; a 4096-env reference iteration takes ~30 s); the AsyncVectorEnv
+    ("SubprocVecEnv", one process per env) run and the oracle port are reported beside it."""
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     if rank != 0:
         return
-    import torch
+    steps, warmup = args.steps, max(args.warmup, 3)
+    base = {"impl": "reference", "metric": METRIC, "unit": "env-steps/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD}}
+    if reference_available():
+        sync = reference_run(REF_ENVS, steps, warmup, asynchronous=False)
+        value, kind = sync["env_steps_per_s"], "reference"
+        extra = {"sync_128": sync}
+        try:   # the north_star's "SubprocVecEnv" path: 128 worker processes + the learner
+            extra["async_128"] = reference_run(REF_ENVS, max(2, min(steps, 3)), 1, asynchronous=True)
+        except Exception as e:  # noqa: BLE001
+            extra["async_128"] = {"error": str(e)[-300:]}
+        try:
+            extra["sync_8_c1"] = reference_run(8, 5, 2, asynchronous=False)
+            extra["async_8_c1"] = reference_run(8, 5, 2, asynchronous=True)
+        except Exception as e:  # noqa: BLE001
+            extra["c1"] = {"error": str(e)[-300:]}
+        extra["not_run"] = "AsyncVectorEnv at 4096 envs = 4097 processes: infeasible on this host; Sync at 4096 envs is ~30 s/iteration"
+        cores, sample = sync["torch_threads"], (f"each step = one PPOAgent.train iteration of {REF_ENVS} of the {N_ENVS} envs x T={T}, {EPOCHS} epochs, "
+                                                 f"unmodified reference (baseline/_ref) + SyncVectorEnv, {sync['host_cores']} host cores")
+        dt = sync["seconds"]
+    else:
+        from oracle import loop as oloop
 
-    from oracle import loop as oloop
-
-    n_envs = 256
-    threads = _best_cpu_threads(n_envs)
-    cfg = oloop.cfg_from_flags(" ".join(FLAGS))
-    tr = oloop.Trainer(cfg, "CartPole-v1", n_envs)
-    for _ in range(min(args.warmup, 2)):
-        tr.iteration()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        tr.iteration()
-    dt = time.perf_counter() - t0
-    value = n_envs * T * args.steps / dt
-    cb = {"value": value, "unit": "env-steps/s", "cores": threads, "kind": "port",
-          "sample": f"each step = one iteration of {n_envs} of the {N_ENVS} envs x T={T}, {EPOCHS} epochs (oracle/loop.py)"}
-    print(json.dumps({
-        "impl": "reference", "metric": "env-steps/sec (collect+update), CartPole-v1 PPO", "value": value, "unit": "env-steps/s",
-        "n_gpus": world, "steps": args.steps, "warmup": min(args.warmup, 2), "ms_per_step": dt / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD}, "cpu_baseline": cb,
-        "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        n_envs = 256
+        threads = _best_cpu_threads(n_envs)
+        cfg = oloop.cfg_from_flags(" ".join(FLAGS))
+        tr = oloop.Trainer(cfg, "CartPole-v1", n_envs)
+        for _ in range(warmup):
+            tr.iteration()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            tr.iteration()
+        dt = time.perf_counter() - t0
+        value, kind, cores, extra = n_envs * T * steps / dt, "port", threads, {"note": "baseline/_ref missing: oracle port timed instead"}
+        sample = f"each step = one iteration of {n_envs} of the {N_ENVS} envs x T={T}, {EPOCHS} epochs (oracle/loop.py)"
+    cb = {"value": value, "unit": "env-steps/s", "cores": cores, "kind": kind, "sample": sample}
+    print(json.dumps({**base, "value": value, "ms_per_step": dt / steps * 1e3, "cpu_baseline": cb, "reference_runs": extra,
+                      "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
 def main():
