@@ -238,11 +238,11 @@ def run_ours(args):
     flops_update = 53e3 * N_ENVS * T * EPOCHS  # fwd+bwd of both nets, SURVEY.md §8d
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
     fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
-    cpu = cpu_baseline_sample(n_envs=256, iters=1)
+    cpu = None if args.no_cpu_baseline else cpu_baseline_sample(n_envs=256, iters=1)
     out = {
         "metric": "env-steps/sec (collect+update), CartPole-v1 PPO", "value": value, "unit": "env-steps/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_s / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (policy/critic/losses), f64 (CartPole state)",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (policy/critic/losses; fc3 GEMMs as split-fp16 tcgen05 MMAs with fp32 accumulate = fp32-class accuracy), f64 (CartPole state)",
         "data": "synthetic: device-resident CartPole-v1, random-init nets, seed 0",
         "config": {"workload": WORKLOAD, "global_envs": N_ENVS * world, "rollout_T": T, "parallelism": f"env-shard dp{world}",
                    "l2": "256 MB L2 flush between timed iterations; inside an iteration the 25 MB buffer is re-read by design",
@@ -258,7 +258,7 @@ def run_ours(args):
                      "config_shape": {**gae["config"], "frac": gae["config"]["GBps"] / hbm_peak,
                                       "in_step_avg_s": gae_in_step,
                                       "in_step_GBps": N_ENVS * T * 24 / max(gae_in_step, 1e-12) / 1e9}},
-        "update_kernel": {"kernel": "ppo_fwdbwd_tc_kernel (tcgen05 TF32, fast mode)" if drv.trainer.use_tf32 else "ppo_fwdbwd_kernel (fp32 FFMA)",
+        "update_kernel": {"kernel": "ppo_fwdbwd_tc_kernel (tcgen05, split-fp16 operands, fp32 accumulate)" if drv.trainer.use_tensor_cores else "ppo_fwdbwd_kernel (fp32 FFMA)",
                           "bound": "issue/latency (row-wise LayerNorm + loss work between three small MMAs per 128-row tile)",
                           "avg_s_per_iteration": upd_s, "algorithmic_flop_per_row": 53e3,
                           "achieved_tflops": flops_update / max(upd_s, 1e-12) / 1e12, "fp32_peak_tflops_at_clock": fp32_peak,
@@ -398,6 +398,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="development: skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -210,9 +210,13 @@ int orl_critic_values(const float* critic_params, int obs_dim, int activation_id
 #define ORL_PPO_A2C 256               /* A2CAlgorithm.prepare_loss (openrl/algorithms/a2c.py:39-140): policy loss
                                          -adv * log-prob instead of the clipped surrogate; ratio reported as 0 */
 #define ORL_PPO_DUAL_CLIP 512         /* cfg.dual_clip_ppo: ratio = min(ratio, dual_clip_coeff) (ppo.py:304-305) */
-#define ORL_PPO_TF32 128              /* fast mode: the 64x64 GEMMs of the trunk on tcgen05 tensor cores
-                                         (TF32 operands, FP32 accumulate in TMEM); obs widths <= 8.
-                                         Without it everything is fp32 FFMA (1e-4 loss parity mode). */
+#define ORL_PPO_TENSORCORE 128        /* the 64x64 GEMMs of the trunk (forward, backward-data, weight gradients) on tcgen05
+                                         tensor cores with split-fp16 operands (x = hi + lo, three MMA passes, FP32
+                                         accumulate in TMEM): fp32-class accuracy, same 1e-4 loss-parity bar as the FFMA
+                                         kernel.  Categorical heads, obs widths <= 8, |obs| < 65504.  Minibatch tiles are
+                                         staged by TMA when `indices` is NULL, by cp.async gathers otherwise.
+                                         Without the flag everything is fp32 FFMA. */
+#define ORL_PPO_TF32 ORL_PPO_TENSORCORE /* round-1 name of the flag */
 
 typedef struct OrlPpoArgs {
     int32_t obs_dim;         /* d  policy obs width  (<= 64) */

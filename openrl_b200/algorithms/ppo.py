@@ -13,7 +13,7 @@ permutation is needed at all (a minibatch that is the whole buffer is a sum over
 import numpy as np
 import torch
 from .. import lib, parallel
-from ..buffers.replay_data import chunk_row_indices
+from ..buffers.replay_data import ReplayData, chunk_row_indices
 
 
 class PPOAlgorithm:
@@ -29,8 +29,14 @@ class PPOAlgorithm:
         pol, cri = init_module.models["policy"], init_module.models["critic"]
         self.d, self.dc, self.n = pol.obs_dim, cri.obs_dim, pol.n_actions
         self.stride = self._lib.orl_ppo_stride(self.d, self.dc, self.n)
+        self.head_kind = pol.head_kind
+        self.recurrent = bool(cfg.use_recurrent_policy)
+        # tensor-core update (tcgen05, split fp16, fp32-class accuracy): Categorical heads, obs widths <= 8
+        self.use_tensor_cores = (bool(getattr(cfg, "use_tensor_cores", True)) and bool(getattr(cfg, "use_tf32", True))
+                                 and max(self.d, self.dc) <= 8 and self.head_kind == lib.HEAD_CATEGORICAL and not self.recurrent)
         sm = torch.cuda.get_device_properties(self.device).multi_processor_count
-        self.grid_per_net = max(1, sm // 2)
+        # CTAs per net: the tensor-core kernel runs two 256-thread CTAs per SM, the FFMA kernel one
+        self.grid_per_net = max(1, sm if self.use_tensor_cores else sm // 2)
         dev = self.device
         self.partials = torch.zeros(2 * self.grid_per_net, self.stride, dtype=torch.float32, device=dev)
         self.folded = torch.zeros(2, self.stride, dtype=torch.float32, device=dev)
@@ -45,25 +51,19 @@ class PPOAlgorithm:
                       | (lib.PPO_VALUENORM if (cfg.use_valuenorm and cri.value_normalizer is not None) else 0)
                       | (lib.PPO_ADV_NORMALIZE if cfg.use_adv_normalize else 0)
                       | (lib.PPO_MAX_GRAD_NORM if cfg.use_max_grad_norm else 0))
-        self.head_kind = pol.head_kind
-        self.use_tf32 = (bool(getattr(cfg, "use_tf32", True)) and not cfg.parity_mode and max(self.d, self.dc) <= 8
-                         and self.head_kind == lib.HEAD_CATEGORICAL)
-        if self.use_tf32:
-            self.flags |= lib.PPO_TF32
+        if self.use_tensor_cores:
+            self.flags |= lib.PPO_TENSORCORE
         if getattr(cfg, "dual_clip_ppo", False):
             self.flags |= lib.PPO_DUAL_CLIP
         for name in ("use_joint_action_loss", "use_policy_vhead", "use_share_model", "use_popart",
                      "use_amp", "use_deepspeed", "use_naive_recurrent_policy"):
             if getattr(cfg, name, False):
                 raise NotImplementedError(f"cfg.{name} is not built into the CUDA update yet (SURVEY.md §8f)")
-        self.recurrent = bool(cfg.use_recurrent_policy)
         if self.recurrent:
             if self.head_kind != lib.HEAD_CATEGORICAL:
                 raise NotImplementedError("recurrent policies are built for Discrete action spaces")
             if not 1 <= cfg.data_chunk_length <= 32:
                 raise NotImplementedError("data_chunk_length must be in [1, 32] for the recurrent kernels")
-            self.use_tf32 = False
-            self.flags &= ~lib.PPO_TF32
             self.rnn_stride = (max(self._lib.orl_rnn_param_count(self.d, self.n), self._lib.orl_rnn_param_count(self.dc, 1)) + 3) & ~3
             # one bucket = gradients of both nets + the loss sums: a single all-reduce per update with >1 GPU
             self.rnn_bucket = torch.zeros(2 * self.rnn_stride + 8, dtype=torch.float32, device=dev)
@@ -212,6 +212,10 @@ class PPOAlgorithm:
     def train(self, buffer, turn_on=True):
         """train_ppo (ppo.py:383-458).  `buffer` is the device ReplayData whose returns/advantages
         were produced by `compute_returns` (orl_gae).  Returns the averaged metrics (one D2H read)."""
+        if not isinstance(buffer, ReplayData):
+            # a HOST buffer (the reference's numpy ReplayData): upload it once, then the device path
+            buffer = ReplayData.from_host(buffer, self.cfg, self.algo_module.get_critic_value_normalizer(), device=self.device)
+            self.h2d_bytes += buffer.h2d_bytes
         self.train_async(buffer)
         return self.read_train_info()
 

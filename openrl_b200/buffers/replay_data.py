@@ -76,6 +76,76 @@ class ReplayData:
         self.returns_ready = False   # set by compute_returns, cleared by after_update (see PPOAlgorithm.train_async)
         self._lib = lib.load()
 
+    @classmethod
+    def from_host(cls, host, cfg, value_normalizer=None, device="cuda:0"):
+        """Upload a HOST rollout buffer — the reference's numpy `ReplayData` or any object with its attribute names
+        (replay_data.py:40-184) — into a device ReplayData: the algorithm-level seam
+        `PPOAlgorithm(cfg, module).train(buffer.data)` (tests/test_algorithm/test_ppo_algorithm.py:76-82).
+        `returns` are taken as the host buffer holds them; the advantages and their moments are rebuilt on the
+        device exactly as train_ppo does (ppo.py:384-409: returns[:-1] - denormalize(value_preds[:-1]))."""
+        import numpy as np
+
+        from .. import spaces
+
+        def arr(name):
+            v = getattr(host, name)
+            if isinstance(v, dict) or hasattr(v, "keys"):       # Dict observations: ObsData of per-key arrays
+                v = v["policy" if name == "policy_obs" else "critic"]
+            return np.ascontiguousarray(np.asarray(v, dtype=np.float32))
+
+        pobs, cobs = arr("policy_obs"), arr("critic_obs")
+        T, N, A = pobs.shape[0] - 1, pobs.shape[1], pobs.shape[2]
+        acts = arr("actions")
+        am = getattr(host, "action_masks", None)
+        if am is not None:
+            act_space = spaces.Discrete(int(np.asarray(am).shape[-1]))
+        else:
+            act_space = spaces.Box(-np.inf, np.inf, (acts.shape[-1],), np.float32)
+        same = pobs.shape == cobs.shape and np.array_equal(pobs, cobs)
+        box = lambda d: spaces.Box(-np.inf, np.inf, (d,), np.float32)   # noqa: E731
+        obs_space = box(pobs.shape[-1]) if same else spaces.Dict({"policy": box(pobs.shape[-1]), "critic": box(cobs.shape[-1])})
+        import copy
+
+        c2 = copy.copy(cfg)
+        c2.n_rollout_threads = N
+        self = cls(c2, A, obs_space, act_space, episode_length=T, device=device)
+        staged = 0
+        for name in ("value_preds", "returns", "masks", "bad_masks", "active_masks", "actions", "action_log_probs", "rewards"):
+            h = torch.from_numpy(arr(name))
+            getattr(self, name).copy_(h.view_as(getattr(self, name)), non_blocking=False)
+            staged += h.numel() * 4
+        self.policy_obs.copy_(torch.from_numpy(pobs).view_as(self.policy_obs))
+        if self.critic_obs is not self.policy_obs:
+            self.critic_obs.copy_(torch.from_numpy(cobs).view_as(self.critic_obs))
+        staged += pobs.size * 4 + (0 if same else cobs.size * 4)
+        if am is not None:
+            amh = torch.from_numpy(np.ascontiguousarray(np.asarray(am, dtype=np.float32)))
+            self.action_masks.copy_(amh.view_as(self.action_masks))
+            self.action_masks_trivial = bool((amh == 1).all())
+            staged += amh.numel() * 4
+        if self.recurrent:
+            for name in ("rnn_states", "rnn_states_critic"):
+                getattr(self, name).copy_(torch.from_numpy(arr(name)).view_as(getattr(self, name)))
+        self.h2d_bytes = staged
+        self.rebuild_advantages(value_normalizer)
+        return self
+
+    def rebuild_advantages(self, value_normalizer=None):
+        """advantages = returns[:-1] - denormalize(value_preds[:-1]) and the moment vector `gae_stats` that
+        orl_gae would have produced (ppo.py:384-409); used when returns come from outside (host buffers)."""
+        vp = self.value_preds[:-1]
+        if (self._use_popart or self._use_valuenorm) and value_normalizer is not None:
+            m, var = value_normalizer.running_mean_var()
+            vp = vp * torch.sqrt(var) + m
+        self.advantages.copy_(self.returns[:-1] - vp)
+        adv = self.advantages.double().view(-1)
+        act = (self.active_masks[:-1].view(-1) != 0).double()
+        ret = self.returns[:-1].double().view(-1)
+        self.gae_stats.copy_(torch.stack([adv.sum(), (adv * adv).sum(), torch.tensor(float(adv.numel()), dtype=torch.float64, device=self.device),
+                                          (adv * act).sum(), (adv * adv * act).sum(), ret.sum(), (ret * ret).sum(),
+                                          self.active_masks[:-1].double().sum()]))
+        self.returns_ready = True
+
     def init_buffer(self, raw_obs, action_masks=None):
         """replay_data.py:286-298 — slot 0 <- first observation (host array or device tensor)."""
         obs = torch.as_tensor(raw_obs, dtype=torch.float32).to(self.device)

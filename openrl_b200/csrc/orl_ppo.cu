@@ -549,7 +549,7 @@ extern "C" int orl_ppo_fwdbwd(const OrlPpoArgs* args, void* stream) {
     ORL_CHECK_ARG(a.head_kind == ORL_HEAD_CATEGORICAL || a.head_kind == ORL_HEAD_GAUSSIAN, "head_kind");
     if (a.flags & ORL_PPO_TF32) {
         if (a.head_kind != ORL_HEAD_CATEGORICAL) {
-            orl::set_last_error("orl_ppo_fwdbwd: ORL_PPO_TF32 supports categorical heads only");
+            orl::set_last_error("orl_ppo_fwdbwd: ORL_PPO_TENSORCORE supports categorical heads only");
             return ORL_ERR_UNSUPPORTED;
         }
         return orl::launch_ppo_fwdbwd_tc(a, reinterpret_cast<cudaStream_t>(stream));

@@ -1,25 +1,44 @@
-// PPO minibatch forward+backward on the 5th-gen tensor cores (tcgen05, TF32 in / FP32 accumulate in
-// TMEM) — the "fast mode" sibling of ppo_fwdbwd_kernel (orl_ppo.cu), producing the same folded
-// partial gradients and loss sums.  Selected with ORL_PPO_TF32; obs widths <= 8 (CartPole, GridWorld).
+// PPO minibatch forward+backward on the 5th-gen tensor cores (tcgen05, split-fp16 operands, FP32
+// accumulate in TMEM) — produces the same folded partial gradients and loss sums as ppo_fwdbwd_kernel
+// (orl_ppo.cu) at fp32-class accuracy (orl_tc16.cuh).  Selected with ORL_PPO_TENSORCORE; categorical
+// heads, obs widths <= 8 (CartPole, GridWorld).  Reference: openrl/algorithms/ppo.py:46-361.
 //
-// CTA = 512 threads = 128 tile rows x 4 column quarters: warps w, w+4, w+8, w+12 own the same 32 rows
-// (the TMEM lane quadrant w%4) and 16 columns each, so every row-wise operation (fc1 with K = d <= 8,
-// LayerNorm forward/backward, head, loss) is thread-local apart from a handful of two-float
-// exchanges through shared memory (named barriers per row group), and the three 64-wide GEMMs of the row tile go to the tensor
-// core, issued by one elected thread:
-//     GEMM1  Z3 [128x64]  = n1 [128x64]  . W3f^T            (M=128, N=64, K=64)    fwd fc3
-//     GEMM2  dN1[128x64]  = dZ3[128x64]  . W3f              (M=128, N=64, K=64)    bwd-data fc3
-//     GEMM3  G  [128x80] += [dZ3^T;dZ1^T][128x128] . [n1^T;X^T;1^T]^T  (M=128, N=80, K=128 rows)
-// GEMM3's accumulator stays in TMEM for the whole kernel: rows 0..63 are G3 = dZ3^T n1 (cols 0..63)
-// and db3 (col 72, the ones row); rows 64..127 are G1 = dZ1^T X (cols 64..64+d) and db1 (col 72).
-// Operands are staged by the row-owning threads in the canonical no-swizzle K-major layout
-// (orl_tc.cuh) — transposed operands are written with conflict-free scalar stores thanks to a
-// 16-byte pad on the panel stride.  GH = dL^T n3 (n x 64) is a small FFMA reduction.
-// TF32 operands are rounded to nearest on store (the MMA truncates); accumulation is fp32.
+// CTA = 256 threads = 128 tile rows x 2 column halves, TWO CTAs per SM (<= 113 KB shared memory, 256
+// TMEM columns each): warps w and w+4 own the same 32 rows (TMEM lane quadrant w%4) and 32 columns
+// each, so every row-wise operation (fc1 with K = d <= 8, LayerNorm forward/backward, head, loss) is
+// thread-local apart from three two-float exchanges and one head exchange through shared memory
+// (named barriers per row group).  While one CTA waits on its MMAs or barriers the other CTA of the
+// SM issues — the inter-tile overlap is done by the hardware CTA scheduler.
+//
+// All matrix operands live in row-major panel buffers (orl_tc16.cuh) as fp16 hi/lo pairs, written by
+// the row-owning threads with 16-byte stores and read K-major or MN-major by descriptor only:
+//   R1 = [ n1 (8 panels) | CST = (1, mu3, std3, 0..) | X ]   rows = tile rows       (dZ1 reuses the n1 panels)
+//   R2 = [ dZ3 (8 panels) | U = dL * rstd3 ]                  rows = tile rows
+//   W  = W3f [64 out rows][64 in features]
+// Four GEMMs per 128-row tile, each as three MMA passes (Al.Bh, Ah.Bl, Ah.Bh), issued by one thread:
+//   GEMM1  Z3 [128x64]  = n1 . W3f^T                 A = R1 K-major,  B = W K-major     (fwd fc3)
+//   GEMM2  dN1[128x64]  = dZ3 . W3f                  A = R2 K-major,  B = W MN-major    (bwd-data fc3)
+//   GEMM3a Ga [128x80] += R2^T . R1                  both MN-major, K = 128 tile rows:
+//            lanes 0..63  : G3 = dZ3^T n1 (cols 0..63), db3 (col 64 = the ones column)
+//            lanes 64..71 : Q = U^T n1, su = U^T 1, smu = U^T mu3, sdl = U^T std3  (-> GH, dbh, below)
+//   GEMM3b Gb [128x16] += dZ1^T . [CST | X]          both MN-major: db1 (col 0), G1 = dZ1^T X (cols 8..15)
+// Ga / Gb stay in TMEM for the whole kernel.  GH = dL^T n3 needs no n3 tile: with n3 = (Z3 + b3f - mu3) rstd3
+// and Z3 = n1 W3f^T,   GH[j][k] = sum_i Q[j][i] W3f[k][i] + b3f[k] su[j] - smu[j]   (evaluated once at the end).
+// Backward operands are scaled by S = 2^e (~ minibatch rows / 16) so that 1/rows-weighted gradients sit in
+// the fp16 range; the accumulators are multiplied by 1/S (exact) when flushed.
+//
+// Minibatch tiles are staged in shared memory one tile ahead: TMA (cp.async.bulk.tensor: the 128 x d
+// observation tile and the scalar columns, zero-filled past the end) when the minibatch is a contiguous
+// row range, per-thread cp.async gathers when it is an index list (shuffled minibatches).
+#include <cuda.h>
+
 #include <algorithm>
+#include <cstring>
+#include <map>
+#include <mutex>
 
 #include "orl_mlp.cuh"
-#include "orl_tc.cuh"
+#include "orl_tc16.cuh"
 
 namespace orl {
 int ppo_stride_host(int obs_dim, int critic_obs_dim, int n_actions);
@@ -29,79 +48,83 @@ namespace {
 using namespace orl;
 using namespace orl::tc;
 
-constexpr int T_M = 128, T_NT = 512;   // four threads per row: thread = (row, column quarter)
-constexpr int T_Q = T_NT / T_M;        // threads per row
-constexpr int T_CH = 8 / T_Q;          // 8-column chunks per thread
-constexpr int NB3 = 80;                       // rows of B3: 64 (n1^T) + 8 (X^T) + 8 (ones / zero)
-constexpr uint32_t LBO_A = 128 * 16 + 16;     // panel stride of 128-row tiles (padded)
-constexpr uint32_t LBO_B3 = NB3 * 16 + 16;
-constexpr uint32_t LBO_W = 64 * 16 + 16;
+constexpr int T_M = 128, T_NT = 256;
+constexpr int CW = 32;                         // columns per thread
+constexpr uint32_t PANEL = T_M * 16;           // 8 fp16 features of 128 rows
+constexpr uint32_t PANEL_W = H * 16;
+constexpr int R1_PANELS = 10, R2_PANELS = 9;
+constexpr int P_CST = 8, P_X = 9, P_U = 8;
 constexpr int N_LOSS_TC = 8;
+// shared-memory carve-up (bytes)
+constexpr uint32_t OFF_R1H = 0, OFF_R1L = OFF_R1H + R1_PANELS * PANEL, OFF_R2H = OFF_R1L + R1_PANELS * PANEL,
+                   OFF_R2L = OFF_R2H + R2_PANELS * PANEL, OFF_WH = OFF_R2L + R2_PANELS * PANEL, OFF_WL = OFF_WH + 8 * PANEL_W,
+                   OFF_STAGE = OFF_WL + 8 * PANEL_W;
+static_assert(OFF_STAGE % 128 == 0, "TMA destination alignment");
+static_assert(OFF_R2L + 16 * PANEL <= OFF_STAGE + 4096, "the 16-panel A descriptors stay inside the allocation");
+constexpr int N_SCAL = 4;                      // scalar columns staged per row
 
-__device__ __forceinline__ uint32_t poff(uint32_t lbo, int row, int col) { return (uint32_t)(col >> 2) * lbo + row * 16 + (col & 3) * 4; }
-__device__ __forceinline__ void pst(uint8_t* t, uint32_t lbo, int row, int col, float v) { *reinterpret_cast<float*>(t + poff(lbo, row, col)) = v; }
-__device__ __forceinline__ float pld(const uint8_t* t, uint32_t lbo, int row, int col) { return *reinterpret_cast<const float*>(t + poff(lbo, row, col)); }
-__device__ __forceinline__ uint64_t kdesc(const uint8_t* tile, uint32_t lbo, int k0) {
-    return desc_common(smem_u32(tile) + (uint32_t)(k0 >> 2) * lbo, lbo, 128);
-}
+struct TcMaps {   // TMA descriptors of the flattened rollout buffers (built by the launcher)
+    CUtensorMap obs_p, obs_c, actions, old_logp, adv, value_preds, returns, active;
+};
 
 struct AdvNormTc { float m0, s0, m1, s1; bool two; };
 
-// NOUT: head width known at compile time (1 critic, 2, 5) or 8 = generic (runtime n <= 8)
 #define FOR_OUT(j) _Pragma("unroll") for (int j = 0; j < NOUT; ++j) if (NOUT != 8 || j < n)
-
-// row-group barrier: the T_Q warps that share rows [32g, 32g+32) (g = warp % 4)
-#define ROWGROUP_SYNC() asm volatile("bar.sync %0, %1;" ::"r"(1 + (warp & 3)), "r"(32 * T_Q) : "memory")
-// exchange: the T_Q column slices of a row publish two partial sums and read the others'
-#define PAIR_SUM2(v0, v1)                                                          \
-    do {                                                                           \
-        xch[(half * T_M + row) * 8 + 0] = (v0); xch[(half * T_M + row) * 8 + 1] = (v1); \
-        ROWGROUP_SYNC();                                                           \
-        float t0_ = 0.f, t1_ = 0.f;                                                \
-        _Pragma("unroll") for (int q_ = 0; q_ < T_Q; ++q_) { t0_ += xch[(q_ * T_M + row) * 8 + 0]; t1_ += xch[(q_ * T_M + row) * 8 + 1]; } \
-        (v0) = t0_; (v1) = t1_;                                                    \
-        ROWGROUP_SYNC();                                                           \
+// row-group barrier: the two warps that share rows [32g, 32g+32) (g = warp % 4)
+#define ROWGROUP_SYNC()                                                        \
+    do {                                                                       \
+        switch (warp & 3) {                                                    \
+            case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;       \
+            case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;       \
+            case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;       \
+            default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;      \
+        }                                                                      \
     } while (0)
 
-template <bool POLICY, int NOUT>
-__device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, uint8_t* smem, int cta, int G, int stride) {
+__host__ __device__ inline uint32_t tc_stage_bytes(int d) { return (uint32_t)((T_M * d * 4 + 127) & ~127) + N_SCAL * T_M * 4; }
+__host__ __device__ inline uint32_t tc_small_off(int d) { return OFF_STAGE + tc_stage_bytes(d); }
+// fp32 weights: w1t[8][64] b1[64] b3f[64] whf[8][64] bhf[8] swh[8]; exchange: xs[2][128][2] xh[2][128][8]; 5 mbarriers + tmem holder
+constexpr uint32_t SMALL_FLOATS = 8 * H + H + H + MAX_OUT * H + 2 * MAX_OUT;
+constexpr uint32_t XCH_FLOATS = 2 * T_M * 2 + 2 * T_M * 8;
+__host__ __device__ inline uint32_t tc_smem_bytes(int d) { return tc_small_off(d) + 4 * (SMALL_FLOATS + XCH_FLOATS) + 5 * 8 + 16; }
+
+template <bool POLICY, int NOUT, bool TMA>
+__device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, const TcMaps& maps, uint8_t* smem, int cta, int G, int stride) {
     const int d = POLICY ? a.obs_dim : a.critic_obs_dim;
     const int n = POLICY ? (NOUT == 8 ? a.n_actions : NOUT) : 1;
     const float* params = POLICY ? a.policy_params : a.critic_params;
     const float* obs = POLICY ? a.policy_obs : a.critic_obs;
     const int tid = threadIdx.x, warp = tid >> 5;
-    const int row = tid & 127, half = tid >> 7;   // this thread: tile row, column slice `half`
-    constexpr int CW = 8 * T_CH;                  // columns per thread
-    const int cb = CW * half;                     // first column of the slice
+    const int row = tid & 127, half = tid >> 7;   // this thread: tile row, column half
+    const int cb = CW * half;                     // first column of the half
     const NetOffsets po = net_offsets(d, n);
 
-    // ---- shared memory carve-up (all tensor-core tiles 128-byte aligned) ----
-    uint8_t* A12 = smem;                         // n1 -> dZ3 : rows m, cols 64
-    uint8_t* A3 = A12 + 16 * LBO_A;              // rows 0..63 dZ3^T, 64..127 dZ1^T ; cols m
-    uint8_t* B3 = A3 + 32 * LBO_A;               // rows 0..63 n1^T, 64..71 X^T, 72 ones ; cols m
-    uint8_t* B1 = B3 + 32 * LBO_B3;              // W3f   rows j, cols k
-    uint8_t* B2 = B1 + 16 * LBO_W;               // W3f^T rows k, cols j
-    uint8_t* N3s = B2 + 16 * LBO_W;              // n3 rows (fp32) for the GH reduction: rows m, cols 64
-    float* w1t = reinterpret_cast<float*>(N3s + 16 * LBO_A);  // [8][64] k-major, zero padded
+    uint8_t* R1h = smem + OFF_R1H; uint8_t* R1l = smem + OFF_R1L;
+    uint8_t* R2h = smem + OFF_R2H; uint8_t* R2l = smem + OFF_R2L;
+    uint8_t* Wh = smem + OFF_WH;   uint8_t* Wl = smem + OFF_WL;
+    float* st_obs = reinterpret_cast<float*>(smem + OFF_STAGE);                        // [128][d]
+    float* st_sc = reinterpret_cast<float*>(smem + OFF_STAGE + ((T_M * d * 4 + 127) & ~127));   // [4][128]
+    float* w1t = reinterpret_cast<float*>(smem + tc_small_off(d));   // [8][64] k-major, zero padded
     float* b1s = w1t + 8 * H;
     float* b3f = b1s + H;
     float* whf = b3f + H;                        // [8][64] folded head
     float* bhf = whf + MAX_OUT * H;
     float* swh = bhf + MAX_OUT;                  // [8] row sums of whf
-    float* DLs = swh + MAX_OUT;                  // [128][8]
-    float* xch = DLs + T_M * 8;                  // [T_Q][128][8] row exchange
-    float* red = xch + T_Q * T_M * 8;            // [64]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(red + 32);  // 3 mbarriers
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 3);
+    float* xs = swh + MAX_OUT;                   // [2][128][2] statistics exchange
+    float* xh = xs + 2 * T_M * 2;                // [2][128][8] head exchange (flush scratch afterwards)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xh + 2 * T_M * 8);  // 0..3 MMA groups, 4 staging
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 5);
 
-    // ---- stage weights (folded; tensor-core copies rounded to TF32) ----
+    // ---- stage weights (folded); the fc3 matrix as split fp16 ----
     for (int i = tid; i < 8 * H; i += T_NT) { const int k = i / H, j = i % H; w1t[i] = (k < d) ? params[po.w1 + j * d + k] : 0.f; }
     for (int i = tid; i < H; i += T_NT) b1s[i] = params[po.b1 + i];
-    for (int i = tid; i < H * H; i += T_NT) {
-        const int j = i / H, k = i % H;
-        const float v = to_tf32(params[po.w3 + i] * params[po.g1 + k]);
-        pst(B1, LBO_W, j, k, v);
-        pst(B2, LBO_W, k, j, v);
+    for (int i = tid; i < H * H / 2; i += T_NT) {
+        const int j = (2 * i) / H, k = (2 * i) % H;
+        uint32_t hi, lo;
+        split2(params[po.w3 + 2 * i] * params[po.g1 + k], params[po.w3 + 2 * i + 1] * params[po.g1 + k + 1], hi, lo);
+        const uint32_t off = (uint32_t)(k >> 3) * PANEL_W + j * 16 + (k & 7) * 2;
+        *reinterpret_cast<uint32_t*>(Wh + off) = hi;
+        *reinterpret_cast<uint32_t*>(Wl + off) = lo;
     }
     for (int i = tid; i < MAX_OUT * H; i += T_NT) { const int j = i / H, k = i % H; whf[i] = (j < n) ? params[po.wh + j * H + k] * params[po.g3 + k] : 0.f; }
     for (int j = tid; j < H; j += T_NT) {
@@ -117,9 +140,17 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, uint8_t* smem, 
         if (j < n) for (int k = 0; k < H; ++k) rs += params[po.wh + j * H + k] * params[po.g3 + k];
         swh[j] = rs;
     }
-    // constant rows of B3: ones row 72, zero rows 64+d..71 and 73..79 (this thread's column m = tid)
-    if (half == 0) for (int r = 64; r < NB3; ++r) pst(B3, LBO_B3, r, row, r == 72 ? 1.0f : 0.f);
-    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); }
+    // panels that are read before their first per-tile write: zero them (U of lanes beyond n, X beyond d are rewritten per tile)
+    if (half == 0) {
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(R1h + P_CST * PANEL + row * 16) = z; *reinterpret_cast<uint4*>(R1l + P_CST * PANEL + row * 16) = z;
+        *reinterpret_cast<uint4*>(R1h + P_X * PANEL + row * 16) = z;   *reinterpret_cast<uint4*>(R1l + P_X * PANEL + row * 16) = z;
+        *reinterpret_cast<uint4*>(R2h + P_U * PANEL + row * 16) = z;   *reinterpret_cast<uint4*>(R2l + P_U * PANEL + row * 16) = z;
+    }
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
+    }
     if (warp == 0) tmem_alloc(tmem_holder, 256);
     fence_proxy_async();
     tcgen05_fence_before();
@@ -127,13 +158,17 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, uint8_t* smem, 
     tcgen05_fence_after();
     const uint32_t tmem = *tmem_holder;
     const uint32_t tmem_row = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    const uint32_t idesc64 = make_idesc_tf32(128, 64, false, false);
-    const uint32_t idesc80 = make_idesc_tf32(128, NB3, false, false);
+    constexpr uint32_t TM_Z = 0, TM_GA = 64, TM_GB = 144;
 
     // ---- minibatch constants ----
     const bool pol_masks = a.flags & ORL_PPO_POLICY_ACTIVE_MASKS, val_masks = a.flags & ORL_PPO_VALUE_ACTIVE_MASKS;
     const double rows_d = (double)(a.norm_rows > 0 ? a.norm_rows : a.batch_rows);
     const float inv_rows = (float)(1.0 / rows_d), inv_act = (float)(1.0 / a.mb_stats[2]);
+    // operand scale of the backward GEMMs: 2^e ~ rows / 16 (row weights are ~ 1/rows)
+    int sexp = 0;
+    while (sexp < 40 && (double)(1ll << sexp) < rows_d) ++sexp;
+    sexp = max(sexp - 4, 0);
+    const float S = exp2f((float)sexp), invS = exp2f(-(float)sexp);
     AdvNormTc an = {0.f, 1.f, 0.f, 1.f, false};
     float vn_mean = 0.f, vn_std = 1.f;
     if (POLICY) {  // ppo.py:402-409
@@ -160,58 +195,75 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, uint8_t* smem, 
         vn_mean = s.mean; vn_std = s.std;
     }
 
-    float gh_acc[1] = {0.f};                  // GH output o = tid  (j = o/64, k = o%64), o < n*64 <= 512
-    float dbh_acc = 0.f;                        // threads with k == 0: sum_m dL[m][j]
+    // ---- MMA descriptors (constant parts) ----
+    const uint64_t dK_A = desc_const(PANEL, 128), dK_W = desc_const(PANEL_W, 128);      // K-major
+    const uint64_t dMN_A = desc_const(128, PANEL), dMN_W = desc_const(128, PANEL_W);    // MN-major
+    const uint32_t id_g1 = make_idesc_f16(128, 64, false, false), id_g2 = make_idesc_f16(128, 64, false, true);
+    const uint32_t id_3a = make_idesc_f16(128, 80, true, true), id_3b = make_idesc_f16(128, 16, true, true);
+    const uint32_t aR1h = smem_u32(R1h), aR1l = smem_u32(R1l), aR2h = smem_u32(R2h), aR2l = smem_u32(R2l), aWh = smem_u32(Wh), aWl = smem_u32(Wl);
+
+    // ---- staging of the minibatch rows, one tile ahead ----
+    const long long n_tiles = (a.batch_rows + T_M - 1) / T_M;
+    const float* sc0 = POLICY ? a.actions : a.value_preds;
+    const float* sc1 = POLICY ? a.old_log_probs : a.returns;
+    const float* sc2 = POLICY ? a.advantages : nullptr;
+    const uint32_t stage_tx = (uint32_t)(T_M * d * 4) + (POLICY ? 4u : 3u) * T_M * 4;
+    auto issue_tma = [&](long long tile) {   // one thread
+        const int r0 = (int)(a.row_begin + tile * T_M);
+        mbar_expect_tx(&bars[4], stage_tx);
+        tma_load_2d(st_obs, POLICY ? &maps.obs_p : &maps.obs_c, 0, r0, &bars[4]);
+        tma_load_1d(st_sc + 0 * T_M, POLICY ? &maps.actions : &maps.value_preds, r0, &bars[4]);
+        tma_load_1d(st_sc + 1 * T_M, POLICY ? &maps.old_logp : &maps.returns, r0, &bars[4]);
+        if (POLICY) tma_load_1d(st_sc + 2 * T_M, &maps.adv, r0, &bars[4]);
+        tma_load_1d(st_sc + 3 * T_M, &maps.active, r0, &bars[4]);
+    };
+    auto issue_gather = [&](long long gi) {   // every thread: half 0 the observation row, half 1 the scalars
+        const bool v = gi >= 0;
+        const long long g = v ? gi : 0;
+        if (half == 0) {
+            if ((d & 3) == 0) {
+                for (int k = 0; k < d; k += 4) cp_async16(st_obs + row * d + k, obs + g * d + k, v);
+            } else {
+                for (int k = 0; k < d; ++k) cp_async4(st_obs + row * d + k, obs + g * d + k, v);
+            }
+        } else {
+            cp_async4(st_sc + 0 * T_M + row, sc0 + g, v);
+            cp_async4(st_sc + 1 * T_M + row, sc1 + g, v);
+            if (POLICY) cp_async4(st_sc + 2 * T_M + row, sc2 + g, v);
+            cp_async4(st_sc + 3 * T_M + row, a.active_masks + g, v);
+        }
+        cp_async_commit();
+    };
+    auto row_index = [&](long long tile) -> long long {   // global row of this thread's tile row, -1 past the end
+        if (tile >= n_tiles) return -1;
+        const long long r = tile * T_M + row;
+        if (r >= a.batch_rows) return -1;
+        return a.indices ? a.indices[r] : a.row_begin + r;
+    };
+    long long gi_next = -1;
+    if (TMA) {
+        if (tid == 0 && cta < n_tiles) { tma_prefetch_desc(POLICY ? &maps.obs_p : &maps.obs_c); issue_tma(cta); }
+    } else {
+        issue_gather(row_index(cta));
+        gi_next = row_index(cta + G);
+    }
+    long long gi = row_index(cta);
+
     float loss0 = 0.f, loss1 = 0.f, loss2 = 0.f;
     uint32_t it = 0;
-    // cycle attribution of the tile pipeline (thread 0 only; written to the spare loss slots 3..7 of the
-    // partial row and read by tools/tc_phase_profile.py): [0] gather+fc1+LN1 until GEMM1 is issued,
-    // [1] wait GEMM1, [2] LN3+head+loss+dZ3 until GEMM2 is issued, [3] wait GEMM2, [4] LN1-bwd, GEMM3 issue, GH
-    uint32_t prof[5] = {0u, 0u, 0u, 0u, 0u};
-    uint32_t tprev = (uint32_t)clock();
-#define PROF_MARK(i) do { if (tid == 0) { const uint32_t now_ = (uint32_t)clock(); prof[i] += now_ - tprev; tprev = now_; } } while (0)
-
-    const long long n_tiles = (a.batch_rows + T_M - 1) / T_M;
-    bool nx_valid; long long nx_gi; float nx_x[8], nx_a = 0.f, nx_b = 0.f, nx_c = 0.f, nx_act = 0.f;
-    {   // row data of the first tile
-        const long long r0 = (long long)cta * T_M + row;
-        nx_valid = (cta < n_tiles) && r0 < a.batch_rows;
-        nx_gi = nx_valid ? (a.indices ? a.indices[r0] : a.row_begin + r0) : -1;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) nx_x[k] = (nx_valid && k < d) ? obs[nx_gi * d + k] : 0.f;
-        if (nx_valid) {
-            if (POLICY) { nx_a = a.actions[nx_gi]; nx_b = a.old_log_probs[nx_gi]; nx_c = a.advantages[nx_gi]; }
-            else { nx_a = a.value_preds[nx_gi]; nx_b = a.returns[nx_gi]; }
-            nx_act = a.active_masks[nx_gi];
-        }
-    }
     for (long long tile = cta; tile < n_tiles; tile += G, ++it) {
         const uint32_t par = it & 1u;
-        const bool valid = nx_valid;
-        const long long gi = nx_gi;
+        // ---- this tile's rows from the staging buffer ----
+        if (TMA) mbar_wait(&bars[4], par);
+        else { cp_async_wait_all(); __syncthreads(); }
+        const bool valid = gi >= 0;
         float x[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) x[k] = nx_x[k];
-        float row_a = nx_a, row_b = nx_b, row_c = nx_c, active = nx_act;
-        {   // prefetch the NEXT tile's row data (index -> observation / scalars: two dependent global
-            // round trips) so that it overlaps this tile's work
-            const long long rn = (tile + G) * T_M + row;
-            nx_valid = (tile + G < n_tiles) && rn < a.batch_rows;
-            nx_gi = nx_valid ? (a.indices ? a.indices[rn] : a.row_begin + rn) : -1;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) nx_x[k] = (nx_valid && k < d) ? obs[nx_gi * d + k] : 0.f;
-            nx_a = nx_b = nx_c = nx_act = 0.f;
-            if (nx_valid) {
-                if (POLICY) { nx_a = a.actions[nx_gi]; nx_b = a.old_log_probs[nx_gi]; nx_c = a.advantages[nx_gi]; }
-                else { nx_a = a.value_preds[nx_gi]; nx_b = a.returns[nx_gi]; }
-                nx_act = a.active_masks[nx_gi];
-            }
-        }
+        for (int k = 0; k < 8; ++k) x[k] = (k < d) ? st_obs[row * d + k] : 0.f;
+        const float row_a = st_sc[0 * T_M + row], row_b = st_sc[1 * T_M + row];
+        const float row_c = POLICY ? st_sc[2 * T_M + row] : 0.f, active = st_sc[3 * T_M + row];
 
-        // Row-wise phases: this thread owns CW = 16 columns [cb, cb+16) of its row and keeps them in
-        // registers across the passes (n1 until the LayerNorm-1 backward, n3 until dZ3); the row's other
-        // slices live in the 3 sibling threads, reached through the two-float exchanges.
-        // ---- fc1 + activation + LayerNorm-1 ----
+        // ---- fc1 + activation + LayerNorm-1 (this thread: columns [cb, cb+32) of its row) ----
         float n1[CW];
 #pragma unroll
         for (int q4 = 0; q4 < CW; q4 += 4) {
@@ -237,49 +289,67 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, uint8_t* smem, 
             n1[i] = act_fwd(n1[i], a.activation_id);
             s += n1[i]; sq = fmaf(n1[i], n1[i], sq);
         }
-        __syncthreads();    // orders this tile after every thread's GH reads (N3s, DLs) of the previous tile
-        PAIR_SUM2(s, sq);
+        {   // exchange 1 (slot xs): LayerNorm-1 statistics
+            *reinterpret_cast<float2*>(xs + (half * T_M + row) * 2) = make_float2(s, sq);
+            ROWGROUP_SYNC();
+            const float2 o = *reinterpret_cast<const float2*>(xs + ((half ^ 1) * T_M + row) * 2);
+            s += o.x; sq += o.y;
+        }
         const float mu1 = s * (1.f / H);
         const float rstd1 = 1.0f / sqrtf(fmaxf(sq * (1.f / H) - mu1 * mu1, 0.f) + LN_EPS);
+#pragma unroll
+        for (int i = 0; i < CW; ++i) n1[i] = (n1[i] - mu1) * rstd1;
 
-        // previous tile's GEMM3 must have finished reading A3 / B3
-        if (it > 0) mbar_wait(&bars[2], (it - 1) & 1u);
-        // n1 row slice (GEMM1 A operand) and n1^T (GEMM3 B operand), TF32-rounded
+        // previous tile's GEMM3b must have finished reading R1
+        if (it > 0) mbar_wait(&bars[3], (it - 1) & 1u);
 #pragma unroll
-        for (int q4 = 0; q4 < CW; q4 += 4) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) n1[q4 + i] = to_tf32((n1[q4 + i] - mu1) * rstd1);
-            *reinterpret_cast<float4*>(A12 + poff(LBO_A, row, cb + q4)) = make_float4(n1[q4], n1[q4 + 1], n1[q4 + 2], n1[q4 + 3]);
-            uint8_t* bt = B3 + poff(LBO_B3, cb + q4, row);
-            *reinterpret_cast<float*>(bt) = n1[q4]; *reinterpret_cast<float*>(bt + 16) = n1[q4 + 1];
-            *reinterpret_cast<float*>(bt + 32) = n1[q4 + 2]; *reinterpret_cast<float*>(bt + 48) = n1[q4 + 3];
+        for (int q8 = 0; q8 < CW; q8 += 8) {
+            const uint32_t off = (uint32_t)((cb + q8) >> 3) * PANEL + row * 16;
+            split_store8(R1h + off, R1l + off, n1 + q8, 1.0f);
         }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) if (half == 0 && k < d) pst(B3, LBO_B3, 64 + k, row, to_tf32(x[k]));
+        if (half == 0) split_store8(R1h + P_X * PANEL + row * 16, R1l + P_X * PANEL + row * 16, x, 1.0f);
         fence_proxy_async();
         tcgen05_fence_before();
         __syncthreads();
         if (warp == 0 && elect_one()) {   // GEMM1: Z3 = n1 . W3f^T
             tcgen05_fence_after();
 #pragma unroll
-            for (int kk = 0; kk < 8; ++kk) mma_tf32(tmem, kdesc(A12, LBO_A, kk * 8), kdesc(B1, LBO_W, kk * 8), idesc64, kk > 0);
+            for (int pass = 0; pass < 3; ++pass) {
+                const uint32_t aa = pass == 0 ? aR1l : aR1h, bb = pass == 1 ? aWl : aWh;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                    mma_f16(tmem + TM_Z, desc_at(dK_A, aa + 2 * kk * PANEL), desc_at(dK_W, bb + 2 * kk * PANEL_W), id_g1, (pass | kk) > 0);
+            }
             mma_commit(&bars[0]);
+            if (TMA && tile + G < n_tiles) issue_tma(tile + G);   // the staging buffer was consumed before the barrier above
+        }
+        long long gi_cur = gi;
+        if (!TMA) {
+            issue_gather(gi_next);
+            gi = gi_next;
+            gi_next = row_index(tile + 2 * G);
+        } else {
+            gi = row_index(tile + G);
         }
 
-        PROF_MARK(0);
         mbar_wait(&bars[0], par);
         tcgen05_fence_after();
-        PROF_MARK(1);
 
-        // ---- Z3 (TMEM) + b3f -> LayerNorm-3 -> n3 (registers; a copy goes to N3s for the GH reduction) ----
+        // ---- Z3 (TMEM) + b3f -> LayerNorm-3 -> n3 (registers only) ----
         float n3[CW];
-        tmem_ld_row16(tmem_row + cb, n3);
+        tmem_ld_row32(tmem_row + TM_Z + cb, n3);
         float s3 = 0.f, q3 = 0.f;
 #pragma unroll
         for (int i = 0; i < CW; ++i) { n3[i] += b3f[cb + i]; s3 += n3[i]; q3 = fmaf(n3[i], n3[i], q3); }
-        PAIR_SUM2(s3, q3);
+        {   // exchange 2 (slot xs; the barrier before GEMM1 separates it from exchange 1)
+            *reinterpret_cast<float2*>(xs + (half * T_M + row) * 2) = make_float2(s3, q3);
+            ROWGROUP_SYNC();
+            const float2 o = *reinterpret_cast<const float2*>(xs + ((half ^ 1) * T_M + row) * 2);
+            s3 += o.x; q3 += o.y;
+        }
         const float mu3 = s3 * (1.f / H);
-        const float rstd3 = 1.0f / sqrtf(fmaxf(q3 * (1.f / H) - mu3 * mu3, 0.f) + LN_EPS);
+        const float var3 = fmaxf(q3 * (1.f / H) - mu3 * mu3, 0.f) + LN_EPS;
+        const float rstd3 = 1.0f / sqrtf(var3);
         float out[MAX_OUT];
 #pragma unroll
         for (int j = 0; j < MAX_OUT; ++j) out[j] = 0.f;
@@ -287,29 +357,22 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, uint8_t* smem, 
         for (int q4 = 0; q4 < CW; q4 += 4) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) n3[q4 + i] = (n3[q4 + i] - mu3) * rstd3;
-            *reinterpret_cast<float4*>(N3s + poff(LBO_A, row, cb + q4)) = make_float4(n3[q4], n3[q4 + 1], n3[q4 + 2], n3[q4 + 3]);
             FOR_OUT(j) {
                 const float4 wv = *reinterpret_cast<const float4*>(whf + j * H + cb + q4);
                 out[j] = fmaf(n3[q4], wv.x, fmaf(n3[q4 + 1], wv.y, fmaf(n3[q4 + 2], wv.z, fmaf(n3[q4 + 3], wv.w, out[j]))));
             }
         }
-        {   // exchange of the partial head dots
-            FOR_OUT(j) xch[(half * T_M + row) * 8 + j] = out[j];
+        {   // exchange 3 (slot xh): partial head dots
+            FOR_OUT(j) xh[(half * T_M + row) * 8 + j] = out[j];
             ROWGROUP_SYNC();
-            FOR_OUT(j) {
-                float t_ = 0.f;
-#pragma unroll
-                for (int q_ = 0; q_ < T_Q; ++q_) t_ += xch[(q_ * T_M + row) * 8 + j];
-                out[j] = t_;
-            }
-            ROWGROUP_SYNC();
+            FOR_OUT(j) out[j] += xh[((half ^ 1) * T_M + row) * 8 + j];
         }
         // dot[j] = sum_k Whf[j][k] n3[k] (needed by the LayerNorm-3 backward); logits add the folded bias
         float dot[MAX_OUT];
 #pragma unroll
         for (int j = 0; j < MAX_OUT; ++j) { dot[j] = out[j]; out[j] += (j < NOUT && j < n) ? bhf[j] : 0.f; }
 
-        // ---- head loss + dL/dhead ----
+        // ---- head loss + dL/dhead (both halves compute it; half 0 accumulates the sums) ----
         float dl[MAX_OUT];
 #pragma unroll
         for (int j = 0; j < MAX_OUT; ++j) dl[j] = 0.f;
@@ -319,7 +382,7 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, uint8_t* smem, 
                 if (a.action_masks) {
 #pragma unroll
                     for (int j = 0; j < MAX_OUT; ++j)
-                        if (j < n && a.action_masks[gi * n + j] == 0.f) { out[j] = -6e4f; masked |= 1u << j; }
+                        if (j < n && a.action_masks[gi_cur * n + j] == 0.f) { out[j] = -6e4f; masked |= 1u << j; }
                 }
                 float nl[MAX_OUT], pr[MAX_OUT];
                 log_softmax_n(out, n, nl, pr);
@@ -363,141 +426,163 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, uint8_t* smem, 
             }
         }
         // ---- dn3 = dL . Whf ; LayerNorm-3 backward -> dZ3 (single pass: the two row means are
-        //      mean(dn3) = sum_j dL[j] rowsum(Whf[j]) / 64 and mean(dn3 n3) = sum_j dL[j] dot[j] / 64) ----
+        //      mean(dn3) = sum_j dL[j] rowsum(Whf[j]) / 64 and mean(dn3 n3) = sum_j dL[j] dot[j] / 64), scaled by S ----
         float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < MAX_OUT; ++j) dl[j] *= S;
         FOR_OUT(j) { m1 = fmaf(dl[j], swh[j], m1); m2 = fmaf(dl[j], dot[j], m2); }
         m1 *= (1.f / H); m2 *= (1.f / H);
 #pragma unroll
-        for (int q4 = 0; q4 < CW; q4 += 4) {
-            float g4[4] = {0.f, 0.f, 0.f, 0.f};
-            FOR_OUT(j) {
-                const float4 wv = *reinterpret_cast<const float4*>(whf + j * H + cb + q4);
-                g4[0] = fmaf(dl[j], wv.x, g4[0]); g4[1] = fmaf(dl[j], wv.y, g4[1]); g4[2] = fmaf(dl[j], wv.z, g4[2]); g4[3] = fmaf(dl[j], wv.w, g4[3]);
+        for (int q8 = 0; q8 < CW; q8 += 8) {
+            float g8[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) g8[i] = 0.f;
+#pragma unroll
+            for (int q4 = 0; q4 < 8; q4 += 4) {
+                FOR_OUT(j) {
+                    const float4 wv = *reinterpret_cast<const float4*>(whf + j * H + cb + q8 + q4);
+                    g8[q4] = fmaf(dl[j], wv.x, g8[q4]); g8[q4 + 1] = fmaf(dl[j], wv.y, g8[q4 + 1]);
+                    g8[q4 + 2] = fmaf(dl[j], wv.z, g8[q4 + 2]); g8[q4 + 3] = fmaf(dl[j], wv.w, g8[q4 + 3]);
+                }
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) g4[i] = to_tf32(rstd3 * (g4[i] - m1 - n3[q4 + i] * m2));
-            *reinterpret_cast<float4*>(A12 + poff(LBO_A, row, cb + q4)) = make_float4(g4[0], g4[1], g4[2], g4[3]);   // dZ3 row
-            uint8_t* at = A3 + poff(LBO_A, cb + q4, row);                                                              // dZ3^T
-#pragma unroll
-            for (int i = 0; i < 4; ++i) *reinterpret_cast<float*>(at + 16 * i) = g4[i];
+            for (int i = 0; i < 8; ++i) g8[i] = rstd3 * (g8[i] - m1 - n3[q8 + i] * m2);
+            const uint32_t off = (uint32_t)((cb + q8) >> 3) * PANEL + row * 16;
+            split_store8(R2h + off, R2l + off, g8, 1.0f);   // dZ3 row slice
         }
         if (half == 0) {
-            *reinterpret_cast<float4*>(DLs + row * 8) = make_float4(dl[0], dl[1], dl[2], dl[3]);
-            *reinterpret_cast<float4*>(DLs + row * 8 + 4) = make_float4(dl[4], dl[5], dl[6], dl[7]);
+            float u8[8], c8[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { u8[j] = dl[j] * rstd3; c8[j] = 0.f; }
+            c8[0] = 1.0f; c8[1] = mu3; c8[2] = var3 * rstd3;   // std3 = var3 / sqrt(var3)
+            split_store8(R2h + P_U * PANEL + row * 16, R2l + P_U * PANEL + row * 16, u8, 1.0f);
+            split_store8(R1h + P_CST * PANEL + row * 16, R1l + P_CST * PANEL + row * 16, c8, 1.0f);
         }
         fence_proxy_async();
         tcgen05_fence_before();
         __syncthreads();
-        if (warp == 0 && elect_one()) {   // GEMM2: dN1 = dZ3 . W3f
+        if (warp == 0 && elect_one()) {   // GEMM2: dN1 = dZ3 . W3f ; GEMM3a: Ga += R2^T . R1
             tcgen05_fence_after();
 #pragma unroll
-            for (int kk = 0; kk < 8; ++kk) mma_tf32(tmem, kdesc(A12, LBO_A, kk * 8), kdesc(B2, LBO_W, kk * 8), idesc64, kk > 0);
+            for (int pass = 0; pass < 3; ++pass) {
+                const uint32_t aa = pass == 0 ? aR2l : aR2h, bb = pass == 1 ? aWl : aWh;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                    mma_f16(tmem + TM_Z, desc_at(dK_A, aa + 2 * kk * PANEL), desc_at(dMN_W, bb + kk * 256), id_g2, (pass | kk) > 0);
+            }
             mma_commit(&bars[1]);
+#pragma unroll
+            for (int pass = 0; pass < 3; ++pass) {
+                const uint32_t aa = pass == 0 ? aR2l : aR2h, bb = pass == 1 ? aR1l : aR1h;
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk)
+                    mma_f16(tmem + TM_GA, desc_at(dMN_A, aa + kk * 256), desc_at(dMN_A, bb + kk * 256), id_3a, (it | pass | kk) > 0);
+            }
+            mma_commit(&bars[2]);
         }
-        PROF_MARK(2);
         mbar_wait(&bars[1], par);
         tcgen05_fence_after();
-        PROF_MARK(3);
-        // ---- dN1 (TMEM) -> LayerNorm-1 backward -> activation backward -> dZ1^T ----
+        // ---- dN1 (TMEM) -> LayerNorm-1 backward -> activation backward -> dZ1 (into the n1 panels of R1) ----
         {
             float g[CW];
-            tmem_ld_row16(tmem_row + cb, g);
+            tmem_ld_row32(tmem_row + TM_Z + cb, g);
             float t1 = 0.f, t2 = 0.f;
 #pragma unroll
             for (int i = 0; i < CW; ++i) { t1 += g[i]; t2 = fmaf(g[i], n1[i], t2); }
-            PAIR_SUM2(t1, t2);
+            {   // exchange 4 (slot xs; the barrier before GEMM2 separates it from exchange 2)
+                *reinterpret_cast<float2*>(xs + (half * T_M + row) * 2) = make_float2(t1, t2);
+                ROWGROUP_SYNC();
+                const float2 o = *reinterpret_cast<const float2*>(xs + ((half ^ 1) * T_M + row) * 2);
+                t1 += o.x; t2 += o.y;
+            }
             t1 *= (1.f / H); t2 *= (1.f / H);
             const float std1 = 1.0f / rstd1;
-            uint8_t* at = A3 + poff(LBO_A, 64 + cb, row);
 #pragma unroll
             for (int i = 0; i < CW; ++i) {
                 const float da = rstd1 * (g[i] - t1 - n1[i] * t2);
                 const float aval = fmaf(n1[i], std1, mu1);                          // activation output
-                *reinterpret_cast<float*>(at + 16 * i) = to_tf32(da * act_bwd(aval, (posmask >> i) & 1u, a.activation_id));
+                g[i] = da * act_bwd(aval, (posmask >> i) & 1u, a.activation_id);
+            }
+            mbar_wait(&bars[2], par);   // GEMM3a has finished reading n1 from R1
+#pragma unroll
+            for (int q8 = 0; q8 < CW; q8 += 8) {
+                const uint32_t off = (uint32_t)((cb + q8) >> 3) * PANEL + row * 16;
+                split_store8(R1h + off, R1l + off, g + q8, 1.0f);
             }
         }
         fence_proxy_async();
         tcgen05_fence_before();
         __syncthreads();
-        if (warp == 0 && elect_one()) {   // GEMM3: G += [dZ3^T; dZ1^T] . [n1^T; X^T; 1^T]^T   (K = 128 tile rows)
+        if (warp == 0 && elect_one()) {   // GEMM3b: Gb += dZ1^T . [CST | X]
             tcgen05_fence_after();
 #pragma unroll
-            for (int kk = 0; kk < 16; ++kk) mma_tf32(tmem + 64, kdesc(A3, LBO_A, kk * 8), kdesc(B3, LBO_B3, kk * 8), idesc80, (it | kk) > 0);
-            mma_commit(&bars[2]);
-        }
-        // ---- GH += dL^T n3 (FFMA reduction over the tile rows, n3 read back from N3s) ----
-        {
-            const int o = tid;
-            if (o < n * H) {
-                const int j = o >> 6, k = o & 63;
-                float acc = gh_acc[0], accb = dbh_acc;
-                const uint8_t* np = N3s + poff(LBO_A, 0, k);
-#pragma unroll 8
-                for (int m = 0; m < T_M; ++m) {
-                    const float dlv = DLs[m * 8 + j];
-                    acc = fmaf(dlv, *reinterpret_cast<const float*>(np + m * 16), acc);
-                    if (k == 0) accb += dlv;     // dbh[j] = sum_m dL[m][j], carried by the k == 0 thread of row j
-                }
-                gh_acc[0] = acc; dbh_acc = accb;
+            for (int pass = 0; pass < 3; ++pass) {
+                const uint32_t aa = pass == 0 ? aR1l : aR1h, bb = (pass == 1 ? aR1l : aR1h) + P_CST * PANEL;
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk)
+                    mma_f16(tmem + TM_GB, desc_at(dMN_A, aa + kk * 256), desc_at(dMN_A, bb + kk * 256), id_3b, (it | pass | kk) > 0);
             }
+            mma_commit(&bars[3]);
         }
-        PROF_MARK(4);
     }
 
-    // ---- flush: G (TMEM) -> partial folded gradients ----
+    // ---- flush: Ga / Gb (TMEM) -> partial folded gradients ----
     float* part = a.partials + (size_t)((POLICY ? 0 : G) + cta) * stride;
     const FoldOffsets fo = fold_offsets(d, n);
+    float* qs = xh;              // [8][64] Q rows, then su[8], smu[8], sdl[8]
+    float* qsu = qs + MAX_OUT * H;
     if (it > 0) {
-        mbar_wait(&bars[2], (it - 1) & 1u);
+        mbar_wait(&bars[3], (it - 1) & 1u);
         tcgen05_fence_after();
-        {   // G columns [16*half, 16*half+16) of this row
-            uint32_t r16[16];
-            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                         : "=r"(r16[0]), "=r"(r16[1]), "=r"(r16[2]), "=r"(r16[3]), "=r"(r16[4]), "=r"(r16[5]), "=r"(r16[6]), "=r"(r16[7]),
-                           "=r"(r16[8]), "=r"(r16[9]), "=r"(r16[10]), "=r"(r16[11]), "=r"(r16[12]), "=r"(r16[13]), "=r"(r16[14]), "=r"(r16[15])
-                         : "r"(tmem_row + 64 + 16 * half));
-            tmem_ld_wait();
-            if (row < 64) {
+        {   // Ga columns [32*half, 32*half+32) of this lane
+            float v[32];
+            tmem_ld_row32(tmem_row + TM_GA + 32 * half, v);
+            if (row < H) {
 #pragma unroll
-                for (int c = 0; c < 16; ++c) part[fo.g3 + row * H + 16 * half + c] = __uint_as_float(r16[c]);
+                for (int c = 0; c < 32; ++c) part[fo.g3 + row * H + 32 * half + c] = v[c] * invS;
+            } else if (row < H + n) {
+#pragma unroll
+                for (int c = 0; c < 32; ++c) qs[(row - H) * H + 32 * half + c] = v[c];
             }
         }
         if (half == 0) {
-            uint32_t r16[16];
-            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                         : "=r"(r16[0]), "=r"(r16[1]), "=r"(r16[2]), "=r"(r16[3]), "=r"(r16[4]), "=r"(r16[5]), "=r"(r16[6]), "=r"(r16[7]),
-                           "=r"(r16[8]), "=r"(r16[9]), "=r"(r16[10]), "=r"(r16[11]), "=r"(r16[12]), "=r"(r16[13]), "=r"(r16[14]), "=r"(r16[15])
-                         : "r"(tmem_row + 128));
-            tmem_ld_wait();
-            if (row < 64) {
-                part[fo.db3 + row] = __uint_as_float(r16[8]);
-            } else {
-                const int j = row - 64;
+            float c8[8];
+            tmem_ld_row8(tmem_row + TM_GA + 64, c8);
+            if (row < H) part[fo.db3 + row] = c8[0] * invS;
+            else if (row < H + n) { qsu[row - H] = c8[0]; qsu[8 + row - H] = c8[1]; qsu[16 + row - H] = c8[2]; }
+            float g16[16];
+            tmem_ld_row16(tmem_row + TM_GB, g16);
+            if (row < H) {
+                part[fo.db1 + row] = g16[0] * invS;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) if (c < d) part[fo.g1 + j * d + c] = __uint_as_float(r16[c]);
-                part[fo.db1 + j] = __uint_as_float(r16[8]);
+                for (int c = 0; c < 8; ++c) if (c < d) part[fo.g1 + row * d + c] = g16[8 + c] * invS;
             }
         }
+        __syncthreads();
+        // GH[j][k] = sum_i Q[j][i] W3f[k][i] + b3f[k] su[j] - smu[j] ; dbh[j] = sdl[j]
+        for (int o = tid; o < n * H; o += T_NT) {
+            const int j = o >> 6, k = o & 63;
+            float acc = 0.f;
+            for (int i = 0; i < H; ++i) acc = fmaf(qs[j * H + i], params[po.w3 + k * H + i] * params[po.g1 + i], acc);
+            acc = fmaf(b3f[k], qsu[j], acc) - qsu[8 + j];
+            part[fo.gh + o] = acc * invS;
+            if (k == 0) { part[fo.dbh + j] = qsu[16 + j] * invS; part[fo.dls + j] = 0.f; }
+        }
     } else {
-        for (int i = tid; i < fo.gh; i += T_NT) part[i] = 0.f;   // G1, db1, G3, db3 of an idle CTA
+        for (int i = tid; i < fo.total; i += T_NT) part[i] = 0.f;   // an idle CTA
     }
-#pragma unroll
-    { const int o = tid; if (o < n * H) part[fo.gh + o] = gh_acc[0]; }
-    if (tid < n * H && (tid & 63) == 0) { part[fo.dbh + (tid >> 6)] = dbh_acc; part[fo.dls + (tid >> 6)] = 0.f; }
     {
         float v[3] = {loss0, loss1, loss2};
+        float* red = xs;
         const int lane = tid & 31;
+        __syncthreads();
 #pragma unroll
-        for (int k = 0; k < 3; ++k) { const float sv = warp_sum(v[k]); if (lane == 0) red[k * 16 + warp] = sv; }
+        for (int k = 0; k < 3; ++k) { const float sv = warp_sum(v[k]); if (lane == 0) red[k * 8 + warp] = sv; }
         __syncthreads();
         if (tid < N_LOSS_TC) {
             float sv = 0.f;
-            if (tid < 3) for (int wv = 0; wv < T_NT / 32; ++wv) sv += red[tid * 16 + wv];
+            if (tid < 3) for (int wv = 0; wv < T_NT / 32; ++wv) sv += red[tid * 8 + wv];
             part[stride - N_LOSS_TC + tid] = sv;
-        }
-        if (tid == 0) {
-#pragma unroll
-            for (int i = 0; i < 5; ++i) part[stride - N_LOSS_TC + 3 + i] = (float)prof[i];
         }
     }
     tcgen05_fence_before();
@@ -505,16 +590,77 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, uint8_t* smem, 
     if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
-__global__ void __launch_bounds__(T_NT, 1) ppo_fwdbwd_tc_kernel(const OrlPpoArgs a, int stride) {
+template <bool TMA>
+__global__ void __launch_bounds__(T_NT, 2) ppo_fwdbwd_tc_kernel(const OrlPpoArgs a, const __grid_constant__ TcMaps maps, int stride) {
     extern __shared__ __align__(1024) uint8_t smem_tc[];
     const int G = a.grid_per_net;
     if ((int)blockIdx.x < G) {
-        if (a.n_actions == 2) tc_net_pass<true, 2>(a, smem_tc, blockIdx.x, G, stride);
-        else if (a.n_actions == 5) tc_net_pass<true, 5>(a, smem_tc, blockIdx.x, G, stride);
-        else tc_net_pass<true, 8>(a, smem_tc, blockIdx.x, G, stride);
+        if (a.n_actions == 2) tc_net_pass<true, 2, TMA>(a, maps, smem_tc, blockIdx.x, G, stride);
+        else if (a.n_actions == 5) tc_net_pass<true, 5, TMA>(a, maps, smem_tc, blockIdx.x, G, stride);
+        else tc_net_pass<true, 8, TMA>(a, maps, smem_tc, blockIdx.x, G, stride);
     } else {
-        tc_net_pass<false, 1>(a, smem_tc, blockIdx.x - G, G, stride);
+        tc_net_pass<false, 1, TMA>(a, maps, smem_tc, blockIdx.x - G, G, stride);
     }
+}
+
+// ---- host: TMA descriptors of the flattened rollout buffers ----
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+bool make_map_rows(CUtensorMap* m, const float* base, long long rows, int width) {   // (rows, width) fp32, box = 128 rows x width
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn || !base) return false;
+    if (width == 1) {
+        cuuint64_t dims[1] = {(cuuint64_t)rows};
+        cuuint64_t strides[1] = {0};
+        cuuint32_t box[1] = {T_M}, es[1] = {1};
+        return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 1, const_cast<float*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)width, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)width * 4};
+    cuuint32_t box[2] = {(cuuint32_t)width, T_M}, es[2] = {1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+struct MapKey {
+    const void* p[8]; long long rows; int d, dc;
+    bool operator<(const MapKey& o) const {
+        for (int i = 0; i < 8; ++i) if (p[i] != o.p[i]) return p[i] < o.p[i];
+        if (rows != o.rows) return rows < o.rows;
+        if (d != o.d) return d < o.d;
+        return dc < o.dc;
+    }
+};
+// descriptors are pure functions of (pointers, shapes): cache them so the steady state does no driver calls
+const TcMaps* maps_for(const OrlPpoArgs& a) {
+    static std::map<MapKey, TcMaps> cache;
+    static std::mutex mu;
+    MapKey k{{a.policy_obs, a.critic_obs, a.actions, a.old_log_probs, a.advantages, a.value_preds, a.returns, a.active_masks},
+             a.total_rows, a.obs_dim, a.critic_obs_dim};
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(k);
+    if (it != cache.end()) return &it->second;
+    TcMaps m;
+    const bool ok = make_map_rows(&m.obs_p, a.policy_obs, a.total_rows, a.obs_dim) && make_map_rows(&m.obs_c, a.critic_obs, a.total_rows, a.critic_obs_dim) &&
+                    make_map_rows(&m.actions, a.actions, a.total_rows, 1) && make_map_rows(&m.old_logp, a.old_log_probs, a.total_rows, 1) &&
+                    make_map_rows(&m.adv, a.advantages, a.total_rows, 1) && make_map_rows(&m.value_preds, a.value_preds, a.total_rows, 1) &&
+                    make_map_rows(&m.returns, a.returns, a.total_rows, 1) && make_map_rows(&m.active, a.active_masks, a.total_rows, 1);
+    if (!ok) return nullptr;
+    if (cache.size() > 64) cache.clear();
+    return &cache.emplace(k, m).first->second;
 }
 
 }  // namespace
@@ -522,20 +668,36 @@ __global__ void __launch_bounds__(T_NT, 1) ppo_fwdbwd_tc_kernel(const OrlPpoArgs
 namespace orl {
 int launch_ppo_fwdbwd_tc(const OrlPpoArgs& a, cudaStream_t st) {
     if (a.obs_dim > 8 || a.critic_obs_dim > 8) {
-        set_last_error("orl_ppo_fwdbwd: ORL_PPO_TF32 supports observation widths <= 8 (got %d / %d)", a.obs_dim, a.critic_obs_dim);
+        set_last_error("orl_ppo_fwdbwd: ORL_PPO_TENSORCORE supports observation widths <= 8 (got %d / %d)", a.obs_dim, a.critic_obs_dim);
         return ORL_ERR_UNSUPPORTED;
     }
-    const size_t smem = 16 * LBO_A + 32 * LBO_A + 32 * LBO_B3 + 2 * 16 * LBO_W + 16 * LBO_A +
-                        sizeof(float) * (8 * H + H + H + MAX_OUT * H + 2 * MAX_OUT + T_M * 8 + T_Q * T_M * 8 + 64) + 3 * 8 + 16 + 128;
+    const int dmax = std::max(a.obs_dim, a.critic_obs_dim);
+    const size_t smem = tc_smem_bytes(dmax);
     static bool attr_set = false;
     if (!attr_set) {
-        int e = check_cuda(cudaFuncSetAttribute(ppo_fwdbwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
-                           "cudaFuncSetAttribute(ppo_fwdbwd_tc)");
+        int e = check_cuda(cudaFuncSetAttribute(ppo_fwdbwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 116 * 1024), "cudaFuncSetAttribute(ppo_fwdbwd_tc)");
         if (e) return e;
+        e = check_cuda(cudaFuncSetAttribute(ppo_fwdbwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 116 * 1024), "cudaFuncSetAttribute(ppo_fwdbwd_tc)");
+        if (e) return e;
+        cudaFuncSetAttribute(ppo_fwdbwd_tc_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(ppo_fwdbwd_tc_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         attr_set = true;
     }
     const int stride = ppo_stride_host(a.obs_dim, a.critic_obs_dim, a.n_actions);
-    ppo_fwdbwd_tc_kernel<<<2 * a.grid_per_net, T_NT, smem, st>>>(a, stride);
+    // TMA staging: contiguous row range, rows of 16-byte multiples (d % 4 == 0), 16-byte aligned bases
+    const bool tma_ok = a.indices == nullptr && (a.obs_dim % 4 == 0) && (a.critic_obs_dim % 4 == 0) &&
+                        ((reinterpret_cast<uintptr_t>(a.policy_obs) | reinterpret_cast<uintptr_t>(a.critic_obs) | reinterpret_cast<uintptr_t>(a.actions) |
+                          reinterpret_cast<uintptr_t>(a.old_log_probs) | reinterpret_cast<uintptr_t>(a.advantages) | reinterpret_cast<uintptr_t>(a.value_preds) |
+                          reinterpret_cast<uintptr_t>(a.returns) | reinterpret_cast<uintptr_t>(a.active_masks)) & 15) == 0 &&
+                        a.row_begin + (((a.batch_rows + T_M - 1) / T_M) * T_M) < (1ll << 31);
+    const TcMaps* maps = tma_ok ? maps_for(a) : nullptr;
+    if (maps) {
+        ppo_fwdbwd_tc_kernel<true><<<2 * a.grid_per_net, T_NT, smem, st>>>(a, *maps, stride);
+    } else {
+        TcMaps none;
+        memset(&none, 0, sizeof(none));
+        ppo_fwdbwd_tc_kernel<false><<<2 * a.grid_per_net, T_NT, smem, st>>>(a, none, stride);
+    }
     return check_cuda(cudaGetLastError(), "ppo_fwdbwd_tc_kernel");
 }
 }  // namespace orl

@@ -28,8 +28,11 @@ class HostVecEnv:
         self.h2d_bytes = 0
         self.d2h_bytes = 0
         N, A = self.parallel_env_num, self.agent_num
+        if not hasattr(self.observation_space, "shape") or self.observation_space.shape is None:
+            raise NotImplementedError("HostVecEnv stages flat Box observations; Dict observation spaces are not supported")
         d = self.observation_space.shape[0]
         self.obs_dim = d
+        self._discrete = hasattr(self.action_space, "n")
         self._stage = torch.empty(N * A * (d + 2), dtype=torch.float32, pin_memory=torch.cuda.is_available())
 
     def reset(self, seed=None, options=None):
@@ -50,6 +53,8 @@ class HostVecEnv:
         N, A, d = self.parallel_env_num, self.agent_num, self.obs_dim
         a = actions_dev.cpu().numpy().reshape(N, A, -1)          # D2H (synchronises the stream)
         self.d2h_bytes += a.nbytes
+        if self._discrete:                                       # the reference hands integer indices to env.step
+            a = a.astype(np.int64)
         obs, rewards, dones, infos = self.env.step(a)
         st = self._stage.numpy()
         B = N * A

@@ -191,5 +191,6 @@ ENV_NONE, ENV_CARTPOLE, ENV_GRIDWORLD, ENV_MPE_SPREAD = 0, 1, 2, 3
 HEAD_CATEGORICAL, HEAD_GAUSSIAN = 0, 1
 GAE_USE_GAE, GAE_PROPER_TIME_LIMITS, GAE_DENORM = 1, 2, 4
 PPO_HUBER, PPO_CLIP_VALUE, PPO_VALUE_ACTIVE_MASKS, PPO_POLICY_ACTIVE_MASKS = 1, 2, 4, 8
-PPO_VALUENORM, PPO_ADV_NORMALIZE, PPO_MAX_GRAD_NORM, PPO_TF32 = 16, 32, 64, 128
+PPO_VALUENORM, PPO_ADV_NORMALIZE, PPO_MAX_GRAD_NORM, PPO_TENSORCORE = 16, 32, 64, 128
+PPO_TF32 = PPO_TENSORCORE   # round-1 name
 PPO_A2C, PPO_DUAL_CLIP = 256, 512

@@ -54,6 +54,7 @@ class PPOModule:
         self.optimizers["critic"] = FusedAdamState(self.models["critic"].flat_params, cfg.critic_lr, cfg.opti_eps,
                                                    cfg.weight_decay)
         self.adam_steps = torch.zeros(2, dtype=torch.int32, device=self.device)
+        self._act_calls = 0   # Philox step of the next stochastic act() call
         self._lib = lib.load()
 
     # -- reference surface -----------------------------------------------------------------
@@ -78,10 +79,17 @@ class PPOModule:
         return out
 
     def act(self, obs, rnn_states_actor=None, masks=None, action_masks=None, deterministic=False, exp_noise=None,
-            rng_seed=0, rng_step=0):
+            rng_seed=None, rng_step=None):
         """PolicyNetwork.forward_original on a (rows, d) batch (ppo_module.py:195-210):
-        returns (actions (rows,1) float CUDA tensor, log-probs (rows,1))."""
+        returns (actions (rows,1) float CUDA tensor, log-probs (rows,1)).
+        Stochastic calls draw Philox noise keyed by (cfg.seed, call counter): every call sees fresh noise
+        (the reference samples from torch's advancing global generator)."""
         pol = self.models["policy"]
+        if rng_seed is None:
+            rng_seed = (int(getattr(self.cfg, "seed", 0)) + 0x51ED270B) & 0xFFFFFFFFFFFF
+        if rng_step is None:
+            rng_step = self._act_calls
+            self._act_calls += 1
         obs = torch.as_tensor(obs, dtype=torch.float32).to(self.device).contiguous().view(-1, pol.obs_dim)
         rows = obs.shape[0]
         if getattr(pol, "recurrent", False):

@@ -11,6 +11,27 @@ from ...buffers import NormalReplayBuffer
 from ...drivers.onpolicy_driver import OnPolicyDriver
 from ...utils.callbacks import BaseCallback, CallbackList
 from ...utils.logger import Logger
+from ... import lib
+
+
+def prepare_action_masks(info, agent_num=1):
+    """openrl/envs/vec_env/utils/util.py:54-88: per-env `info["action_masks"]` ((n,) or (A, n)) -> (N*A, n);
+    None when any env carries no mask (all actions available)."""
+    if info is None:
+        return None
+    rows = []
+    for env_info in info:
+        for a in range(agent_num):
+            if env_info is None or "action_masks" not in env_info:
+                return None
+            m = np.asarray(env_info["action_masks"])
+            if m.ndim == 2:
+                rows.append(m[a])
+            elif m.ndim == 1:
+                rows.append(m)
+            else:
+                raise ValueError(m.ndim)
+    return np.asarray(rows, dtype=np.float32)
 
 
 class PPOAgent:
@@ -83,8 +104,13 @@ class PPOAgent:
             observation = observation["policy"]
         obs = np.asarray(observation, dtype=np.float32)
         N, A = obs.shape[0], obs.shape[1]
-        actions, _ = self.net.act(obs.reshape(N * A, -1), deterministic=deterministic, episode_starts=episode_starts)
-        return actions.view(N, A, 1).cpu().numpy().astype(np.int64), None
+        action_masks = prepare_action_masks(info, agent_num=self.agent_num) if info is not None else None
+        actions, rnn_state = self.net.act(obs.reshape(N * A, -1), action_masks=action_masks, deterministic=deterministic,
+                                          episode_starts=episode_starts)
+        out = actions.view(N, A, -1).cpu().numpy()   # np.split(_t2n(action), env_num): (N, A, act_shape)
+        if self.net.module.models["policy"].head_kind == lib.HEAD_CATEGORICAL:
+            out = out.astype(np.int64)                # Categorical.sample() yields integer indices
+        return out, rnn_state
 
     def get_env(self):
         return self._env

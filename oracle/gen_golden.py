@@ -96,9 +96,11 @@ def flat_params(module):
     return out
 
 
-def gen_trace(env_id, env_num, flags, iters, tag):
+def gen_trace(env_id, env_num, flags, iters, tag, algo="ppo", ref_flags=None):
+    """`flags` is recorded in the golden (canonical `--name value` form); `ref_flags` is what the reference's own parser
+    is given when it spells an option differently (its store_false switches, config.py:679-772)."""
     rec = {}
-    cfg = create_config_parser().parse_args(flags)
+    cfg = create_config_parser().parse_args(ref_flags if ref_flags is not None else flags)
     env = make(env_id, env_num=env_num)
     net = PPONet(env, cfg=cfg)
     agent = PPOAgent(net)
@@ -185,7 +187,12 @@ def gen_trace(env_id, env_num, flags, iters, tag):
     ReplayData.recurrent_generator = rg
     OnPolicyDriver._inner_loop = inner
     try:
-        agent.train(total_time_steps=cfg.episode_length * env_num * iters)
+        if algo == "a2c":   # the reference's A2CAgent.train == PPOAgent.train(train_algo_class=A2CAlgorithm) (a2c_agent.py:66-77)
+            from openrl.algorithms.a2c import A2CAlgorithm
+
+            agent.train(total_time_steps=cfg.episode_length * env_num * iters, train_algo_class=A2CAlgorithm)
+        else:
+            agent.train(total_time_steps=cfg.episode_length * env_num * iters)
     finally:
         OnPolicyDriver.compute_returns = orig_compute_returns
         PPOAlgorithm.ppo_update = orig_ppo_update
@@ -198,6 +205,7 @@ def gen_trace(env_id, env_num, flags, iters, tag):
     rec["meta/env_id"] = np.array(env_id)
     rec["meta/env_num"] = np.int64(env_num)
     rec["meta/iters"] = np.int64(iters)
+    rec["meta/algo"] = np.array(algo)
     name = f"trace_{tag}.npz"
     np.savez_compressed(os.path.join(OUT, name), **rec)
     print("wrote", name, "iters", state["it"], "bytes", os.path.getsize(os.path.join(OUT, name)))
@@ -238,11 +246,37 @@ def main():
         gen_trace("IdentityEnvcontinuous", 4,
                   ["--seed", "0", "--episode_length", "16", "--ppo_epoch", "2", "--num_mini_batch", "2", "--log_interval", "1000"],
                   2, "identity_continuous")
+    if a.only in ("", "flags"):
+        gen_flag_variants()
     if a.only in ("", "mpe_mlp"):
         gen_trace("simple_spread", 4,
                   ["--seed", "0", "--episode_length", "25", "--ppo_epoch", "2", "--lr", "7e-4", "--critic_lr", "7e-4",
                    "--use_valuenorm", "true", "--use_adv_normalize", "true", "--log_interval", "1000"],
                   2, "mpe_mlp")
+
+
+# Loss / return option branches of the hot path (ppo.py:178-220,254-339, a2c.py:39-140, replay_data.py:320-423):
+# one short CartPole trace each, so that every branch of oracle/ppo.py + oracle/gae.py is pinned to the reference.
+FLAG_VARIANTS = {   # name: (canonical flags, the reference parser's spelling, algorithm)
+    "a2c": (["--ppo_epoch", "1"], None, "a2c"),
+    "dual_clip": (["--dual_clip_ppo", "true", "--dual_clip_coeff", "1.02"], None, "ppo"),
+    "no_huber": (["--use_huber_loss", "false"], ["--use_huber_loss"], "ppo"),
+    "no_value_clip": (["--use_clipped_value_loss", "false"], ["--use_clipped_value_loss"], "ppo"),
+    "proper_time_limits": (["--use_proper_time_limits", "true"], None, "ppo"),
+    "no_gae": (["--use_gae", "false"], None, "ppo"),
+    "no_valuenorm": (["--use_valuenorm", "false"], None, "ppo"),
+    "adv_norm_no_masks": (["--use_adv_normalize", "true", "--use_value_active_masks", "false", "--use_policy_active_masks", "false"],
+                          ["--use_adv_normalize", "true", "--use_value_active_masks", "false", "--use_policy_active_masks"], "ppo"),
+    "no_grad_clip_wd": (["--use_max_grad_norm", "false", "--weight_decay", "0.01", "--activation_id", "0"],
+                        ["--use_max_grad_norm", "--weight_decay", "0.01", "--activation_id", "0"], "ppo"),
+}
+
+
+def gen_flag_variants():
+    base = ["--seed", "0", "--episode_length", "24", "--ppo_epoch", "2", "--num_mini_batch", "2", "--log_interval", "1000"]
+    for name, (extra, ref_extra, algo) in FLAG_VARIANTS.items():
+        gen_trace("CartPole-v1", 6, base + extra, 2, f"flag_{name}", algo=algo,
+                  ref_flags=None if ref_extra is None else base + ref_extra)
 
 
 if __name__ == "__main__":

@@ -46,7 +46,7 @@ def test_header_flag_values_match_python():
              "ORL_PPO_HUBER": lib.PPO_HUBER, "ORL_PPO_CLIP_VALUE": lib.PPO_CLIP_VALUE,
              "ORL_PPO_VALUE_ACTIVE_MASKS": lib.PPO_VALUE_ACTIVE_MASKS, "ORL_PPO_POLICY_ACTIVE_MASKS": lib.PPO_POLICY_ACTIVE_MASKS,
              "ORL_PPO_VALUENORM": lib.PPO_VALUENORM, "ORL_PPO_ADV_NORMALIZE": lib.PPO_ADV_NORMALIZE,
-             "ORL_PPO_MAX_GRAD_NORM": lib.PPO_MAX_GRAD_NORM, "ORL_PPO_TF32": lib.PPO_TF32, "ORL_PPO_A2C": lib.PPO_A2C,
+             "ORL_PPO_MAX_GRAD_NORM": lib.PPO_MAX_GRAD_NORM, "ORL_PPO_TENSORCORE": lib.PPO_TENSORCORE, "ORL_PPO_A2C": lib.PPO_A2C,
              "ORL_PPO_DUAL_CLIP": lib.PPO_DUAL_CLIP}
     for k, v in pairs.items():
         assert defs[k] == v, k

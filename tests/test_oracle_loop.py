@@ -82,3 +82,37 @@ def test_multi_agent_oracle_reproduces_reference_trace(tag, env_id):
         for mk, prm in (("policy", tr.pol), ("critic", tr.cri)):
             for k, v in prm.items():
                 np.testing.assert_allclose(v.detach().numpy(), d[f"it{it}/params/{mk}.{k}"], rtol=2e-4, atol=2e-6, err_msg=k)
+
+
+FLAG_TAGS = ["a2c", "dual_clip", "no_huber", "no_value_clip", "proper_time_limits", "no_gae", "no_valuenorm", "adv_norm_no_masks",
+             "no_grad_clip_wd"]
+
+
+@pytest.mark.parametrize("tag", FLAG_TAGS)
+def test_oracle_reproduces_reference_flag_variants(tag):
+    """Every loss / return option branch of the hot path (A2C, dual clip, MSE value loss, unclipped value loss,
+    proper time limits, plain discounted returns, no ValueNorm, advantage normalisation without active masks,
+    no gradient clip + weight decay + tanh) pinned to a trace of the unmodified reference
+    (oracle/gen_golden.py FLAG_VARIANTS)."""
+    d = np.load(os.path.join(GOLDEN, f"trace_flag_{tag}.npz"), allow_pickle=True)
+    cfg = loop.cfg_from_flags(str(d["meta/flags"]))
+    cfg.a2c = str(d["meta/algo"]) == "a2c"
+    if cfg.a2c:
+        cfg.num_mini_batch = 1   # A2CAlgorithm.__init__ (a2c.py:37)
+    tr = loop.Trainer(cfg, "CartPole-v1", int(d["meta/env_num"]))
+    for k, v in _params(tr).items():
+        assert np.array_equal(v, d[f"init/{k}"]), k
+    for it in range(int(d["meta/iters"])):
+        tr.rollout()
+        b = tr.buf
+        assert np.array_equal(b.actions, d[f"it{it}/actions"])
+        assert np.array_equal(b.obs, d[f"it{it}/policy_obs"])
+        tr.compute_returns()
+        np.testing.assert_allclose(b.value_preds, d[f"it{it}/value_preds"], rtol=0, atol=1e-5)
+        np.testing.assert_allclose(b.returns[:-1], d[f"it{it}/returns"][:-1], rtol=1e-5, atol=1e-5)
+        updates, perms = tr.train()
+        assert np.array_equal(perms, d[f"it{it}/perms"])
+        np.testing.assert_allclose(updates, d[f"it{it}/updates"], rtol=1e-4, atol=1e-6)
+        tr.after_update()
+        for k, v in _params(tr).items():
+            np.testing.assert_allclose(v, d[f"it{it}/params/{k}"], rtol=1e-4, atol=1e-6, err_msg=k)

@@ -110,7 +110,7 @@ def test_update_flag_matrix_vs_oracle(cuda, flags):
         np.testing.assert_allclose(got[col], want[col], rtol=2e-4, atol=5e-6, err_msg=name)
     for mk, params in (("policy", pol), ("critic", cri)):
         for k, v in net.module.models[mk].named_parameters():
-            np.testing.assert_allclose(v.detach().cpu().numpy(), params[k].detach().numpy(), rtol=1e-3, atol=3e-6,
+            np.testing.assert_allclose(v.detach().cpu().numpy(), params[k].detach().numpy(), rtol=1e-3, atol=0.05 * max(cfg.lr, cfg.critic_lr),
                                        err_msg=f"{mk}.{k}")
     if vn is not None:
         np.testing.assert_allclose(vn.state.cpu().numpy(), ovn.state(), rtol=1e-5)
@@ -130,7 +130,7 @@ def test_fast_mode_multi_minibatch_and_odd_sizes(cuda):
     agent = PPOAgent(PPONet(env, cfg=cfg, device="cuda:0"))
     logger = Logger(quiet=True)
     agent.train(total_time_steps=37 * 53 * 4, logger=logger)
-    assert agent.driver.trainer.use_tf32
+    assert agent.driver.trainer.use_tensor_cores
     logs = [h[1] for h in logger.history if "value_loss" in h[1]]
     assert len(logs) == 4 and all(np.isfinite(list(l.values())).all() for l in logs)
     assert all(abs(l["ratio"] - 1.0) < 0.05 for l in logs)
@@ -167,7 +167,7 @@ def test_save_load_roundtrip_and_lr_decay(cuda, tmp_path):
 
 
 @pytest.mark.parametrize("n_actions", [2, 3, 5, 8])
-def test_tf32_kernel_head_width_templates(cuda, n_actions):
+def test_tensor_core_kernel_head_width_templates(cuda, n_actions):
     """The tcgen05 kernel is instantiated for head widths 2, 5 and a generic (runtime n <= 8) variant:
     each must agree with the fp32 kernel on the same synthetic minibatch (incl. a partial last tile)."""
     import torch
@@ -193,8 +193,7 @@ def test_tf32_kernel_head_width_templates(cuda, n_actions):
         net = PPONet(Env(), cfg=cfg, device="cuda:0")
         cfg.n_rollout_threads = N
         trainer = PPOAlgorithm(cfg, net.module, agent_num=1, device=net.device)
-        if tf32:
-            trainer.flags |= lib.PPO_TF32
+        trainer.flags = (trainer.flags | lib.PPO_TENSORCORE) if tf32 else (trainer.flags & ~lib.PPO_TENSORCORE)
         buf = NormalReplayBuffer(cfg, 1, Env.observation_space, Env.action_space, device=net.device)
         b = buf.data
         g = torch.Generator().manual_seed(5)
@@ -212,7 +211,7 @@ def test_tf32_kernel_head_width_templates(cuda, n_actions):
         trainer.ppo_update(b, T * N, None, 0, mb_stats=b.gae_stats[5:8])
         torch.cuda.synchronize()
         res.append((trainer.train_info.cpu().numpy().copy(), trainer.grads.cpu().numpy().copy()))
-    np.testing.assert_allclose(res[1][0], res[0][0], rtol=3e-3, atol=2e-5)
+    np.testing.assert_allclose(res[1][0], res[0][0], rtol=1e-4, atol=1e-6)
     for net_i in range(2):
         g32, gtc = res[0][1][net_i], res[1][1][net_i]
-        assert np.linalg.norm(gtc - g32) <= 1e-2 * np.linalg.norm(g32), (n_actions, net_i)
+        assert np.linalg.norm(gtc - g32) <= 1e-4 * np.linalg.norm(g32), (n_actions, net_i)

@@ -76,7 +76,7 @@ def test_first_iteration_updates_match_reference(cuda, tag):
         for k, v in net.module.models[mk].state_dict().items():
             gk = f"it0/params/{mk}.{k}"
             if gk in d:
-                np.testing.assert_allclose(v.cpu().numpy(), d[gk], rtol=1e-3, atol=2e-6, err_msg=gk)
+                np.testing.assert_allclose(v.cpu().numpy(), d[gk], rtol=1e-3, atol=0.05 * cfg.lr, err_msg=gk   # a near-zero gradient element may move by a few % of one Adam step)
     np.testing.assert_allclose(vn.state.cpu().numpy(), d["it0/vn_after_update"], rtol=1e-5)
 
 
@@ -157,8 +157,7 @@ def test_sharded_minibatch_buckets_sum_to_global_bucket(cuda, tf32):
 
     d = np.load(os.path.join(GOLDEN, "trace_cartpole_c1.npz"), allow_pickle=True)
     cfg, net, trainer, buf = _setup(d)
-    if tf32:
-        trainer.flags |= lib.PPO_TF32
+    trainer.flags = (trainer.flags | lib.PPO_TENSORCORE) if tf32 else (trainer.flags & ~lib.PPO_TENSORCORE)
     _load_buffer(buf, d, 0)
     vn = net.module.get_critic_value_normalizer()
     buf.data.compute_returns(buf.data.value_preds[-1].clone(), vn)
@@ -177,15 +176,13 @@ def test_sharded_minibatch_buckets_sum_to_global_bucket(cuda, tf32):
     whole = bucket(perm, 0)
     half = total // 2
     parts = bucket(perm[:half], total) + bucket(perm[half:], total)
-    # bucket row = folded gradients + 8 tail slots: loss sums in 0..2 (3..7 are the tcgen05 kernel's phase-cycle counters)
-    used = trainer.stride - 5
-    got, want = parts.cpu().numpy()[:, :used], whole.cpu().numpy()[:, :used]
+    got, want = parts.cpu().numpy(), whole.cpu().numpy()   # folded gradients + 8 tail slots (loss sums in 0..2, rest zero)
     np.testing.assert_allclose(got, want, rtol=2e-4, atol=2e-6 * max(float(np.abs(want).max()), 1.0))
 
 
-def test_tf32_tensor_core_update_matches_fp32_update(cuda):
-    """Fast mode (tcgen05, TF32 operands) vs parity mode (fp32 FFMA) on the same minibatch: losses are
-    means over rows so they agree to ~1e-4; gradients to TF32 accuracy."""
+def test_tensor_core_update_matches_fp32_update(cuda):
+    """tcgen05 update (split-fp16 operands, fp32 accumulate) vs the fp32 FFMA update on the same shuffled minibatch
+    (gather staging): the six scalars within the 1e-4 parity bar, gradients to fp32-class accuracy."""
     import torch
 
     from openrl_b200 import lib
@@ -194,8 +191,7 @@ def test_tf32_tensor_core_update_matches_fp32_update(cuda):
     res = []
     for tf32 in (False, True):
         cfg, net, trainer, buf = _setup(d)
-        if tf32:
-            trainer.flags |= lib.PPO_TF32
+        trainer.flags = (trainer.flags | lib.PPO_TENSORCORE) if tf32 else (trainer.flags & ~lib.PPO_TENSORCORE)
         _load_buffer(buf, d, 0)
         vn = net.module.get_critic_value_normalizer()
         buf.data.compute_returns(buf.data.value_preds[-1].clone(), vn)
@@ -207,14 +203,14 @@ def test_tf32_tensor_core_update_matches_fp32_update(cuda):
         res.append((trainer.train_info.cpu().numpy().copy(), trainer.grads.cpu().numpy().copy(),
                     net.module.models["policy"].flat_params.cpu().numpy().copy()))
     info32, info_tc = res[0][0], res[1][0]
-    np.testing.assert_allclose(info_tc, info32, rtol=2e-3, atol=1e-5)
+    np.testing.assert_allclose(info_tc, info32, rtol=1e-4, atol=1e-6)
     for net_i in range(2):
         g32, gtc = res[0][1][net_i], res[1][1][net_i]
-        assert np.linalg.norm(gtc - g32) <= 5e-3 * np.linalg.norm(g32), (np.linalg.norm(gtc - g32), np.linalg.norm(g32))
-    np.testing.assert_allclose(res[1][2], res[0][2], rtol=0, atol=2e-3)
+        assert np.linalg.norm(gtc - g32) <= 1e-4 * np.linalg.norm(g32), (np.linalg.norm(gtc - g32), np.linalg.norm(g32))
+    np.testing.assert_allclose(res[1][2], res[0][2], rtol=0, atol=2e-5)
 
 
-def test_tf32_partial_tile_and_idle_ctas(cuda):
+def test_tensor_core_partial_tile_and_idle_ctas(cuda):
     """Minibatch smaller than one tile (rows < 128) and far fewer tiles than CTAs."""
     import torch
 
@@ -224,8 +220,7 @@ def test_tf32_partial_tile_and_idle_ctas(cuda):
     res = []
     for tf32 in (False, True):
         cfg, net, trainer, buf = _setup(d)
-        if tf32:
-            trainer.flags |= lib.PPO_TF32
+        trainer.flags = (trainer.flags | lib.PPO_TENSORCORE) if tf32 else (trainer.flags & ~lib.PPO_TENSORCORE)
         _load_buffer(buf, d, 0)
         vn = net.module.get_critic_value_normalizer()
         buf.data.compute_returns(buf.data.value_preds[-1].clone(), vn)
@@ -235,4 +230,28 @@ def test_tf32_partial_tile_and_idle_ctas(cuda):
         trainer.ppo_update(buf.data, 100, idx)
         torch.cuda.synchronize()
         res.append(trainer.train_info.cpu().numpy().copy())
-    np.testing.assert_allclose(res[1], res[0], rtol=3e-3, atol=1e-5)
+    np.testing.assert_allclose(res[1], res[0], rtol=1e-4, atol=1e-6)
+
+
+def test_algorithm_train_accepts_host_numpy_replay_data(cuda, monkeypatch):
+    """The reference's algorithm-level seam with a HOST buffer (tests/test_algorithm/test_ppo_algorithm.py:76-82:
+    `PPOAlgorithm(cfg, module).train(buffer.data)`, buffer = numpy ReplayData): the golden rollout of iteration 0
+    handed over as plain numpy arrays under the reference's attribute names must reproduce the reference's
+    updates of that iteration (same minibatch permutations)."""
+    import types
+
+    import torch
+
+    d = np.load(os.path.join(GOLDEN, "trace_cartpole.npz"), allow_pickle=True)
+    cfg, net, trainer, buf = _setup(d)
+    host = types.SimpleNamespace(**{k: d[f"it0/{k}"].copy() for k in
+                                    ("policy_obs", "critic_obs", "value_preds", "returns", "masks", "bad_masks", "active_masks",
+                                     "actions", "action_log_probs", "rewards", "action_masks")})
+    # the golden value_preds were recorded after compute_returns (normalised predictions, as train_ppo sees them)
+    perms = [torch.from_numpy(p) for p in d["it0/perms"]]
+    monkeypatch.setattr(torch, "randperm", lambda *a, **k: perms.pop(0))
+    info = trainer.train(host)
+    want = d["it0/updates"].mean(axis=0)
+    for col, name in enumerate(["value_loss", "critic_grad_norm", "policy_loss", "dist_entropy", "actor_grad_norm", "ratio"]):
+        np.testing.assert_allclose(info[name], want[col], rtol=1e-4, atol=2e-6, err_msg=name)
+    assert trainer.h2d_bytes > 0

@@ -40,7 +40,7 @@ def test_train_matches_reference_trace(cuda, tag):
         for k, v in net.module.models[mk].state_dict().items():
             gk = f"it{last}/params/{mk}.{k}"
             if gk in d:
-                np.testing.assert_allclose(v.cpu().numpy(), d[gk], rtol=2e-3, atol=5e-6, err_msg=gk)
+                np.testing.assert_allclose(v.cpu().numpy(), d[gk], rtol=2e-3, atol=0.05 * cfg.lr, err_msg=gk)
 
 
 @pytest.mark.parametrize("use_tf32", ["true", "false"])
@@ -60,7 +60,7 @@ def test_cartpole_learns(cuda, use_tf32):
     env = make("CartPole-v1", env_num=9)
     agent = PPOAgent(PPONet(env, cfg=cfg, device="cuda:0"))
     agent.train(total_time_steps=20000)
-    assert agent.driver.trainer.use_tf32 == (use_tf32 == "true")
+    assert agent.driver.trainer.use_tensor_cores == (use_tf32 == "true")
     ev = make("CartPole-v1", env_num=64)
     obs, _ = ev.reset(seed=123)
     totals = np.zeros(64)
@@ -193,3 +193,35 @@ def test_algorithm_train_on_fresh_buffer(cuda):
     assert set(info) == {"value_loss", "critic_grad_norm", "policy_loss", "dist_entropy", "actor_grad_norm", "ratio"}
     assert np.isfinite(list(info.values())).all(), info
     assert abs(info["dist_entropy"] - np.log(2)) < 1e-2
+
+
+FLAG_TAGS = ["a2c", "dual_clip", "no_huber", "no_value_clip", "proper_time_limits", "no_gae", "no_valuenorm", "adv_norm_no_masks",
+             "no_grad_clip_wd"]
+
+
+@pytest.mark.parametrize("tag", FLAG_TAGS)
+def test_train_matches_reference_flag_variants(cuda, tag):
+    """The device path through the public API against traces of the UNMODIFIED reference for every loss / return
+    option branch (oracle/gen_golden.py FLAG_VARIANTS): bit-exact actions, the six scalars within 1e-4."""
+    from openrl_b200.algorithms import A2CAlgorithm, PPOAlgorithm
+    from openrl_b200.utils.logger import Logger
+    from test_rollout_cuda import _product
+
+    d = np.load(os.path.join(GOLDEN, f"trace_flag_{tag}.npz"), allow_pickle=True)
+    iters, N = int(d["meta/iters"]), int(d["meta/env_num"])
+    a2c = str(d["meta/algo"]) == "a2c"
+    cfg, env, net, agent = _product("CartPole-v1", N, str(d["meta/flags"]).split(), golden=d)
+    logger = Logger(quiet=True)
+    agent.train(total_time_steps=cfg.episode_length * N * iters, logger=logger, train_algo_class=A2CAlgorithm if a2c else PPOAlgorithm)
+    train_logs = [h[1] for h in logger.history if "value_loss" in h[1]]
+    assert len(train_logs) == iters
+    names = ["value_loss", "critic_grad_norm", "policy_loss", "dist_entropy", "actor_grad_norm", "ratio"]
+    for it in range(iters):
+        want = d[f"it{it}/updates"].mean(axis=0)
+        for col, name in enumerate(names):
+            if a2c and name == "ratio":
+                continue   # A2C reports no ratio (a2c.py:142-145)
+            np.testing.assert_allclose(train_logs[it][name], want[col], rtol=1e-4, atol=2e-6, err_msg=f"it{it} {name}")
+    b = agent.driver.buffer.data
+    assert np.array_equal(b.actions.cpu().numpy(), d[f"it{iters - 1}/actions"])
+    np.testing.assert_allclose(b.returns.cpu().numpy()[:-1], d[f"it{iters - 1}/returns"][:-1], rtol=1e-5, atol=1e-5)
