@@ -93,7 +93,41 @@ class ClockSampler:
                 "samples": len(sm), "scope": scope, "reasons": sorted(reasons)}
 
 
-def build_agent(rank, world, parity=False):
+WORKLOADS = {
+    # BASELINE.json configs; "c2" is the configuration the metric is quoted on (the bench line), the rest are reported as extras
+    "c2": dict(env="CartPole-v1", envs=N_ENVS, T=T, flags=FLAGS),
+    "c1": dict(env="CartPole-v1", envs=8, T=T, flags=FLAGS),
+    "target128": dict(env="CartPole-v1", envs=128, T=T, flags=FLAGS),   # north_star's 128-env target point
+    "c3": dict(env="simple_spread", envs=2048, T=25,
+               flags=["--seed", "0", "--episode_length", "25", "--lr", "7e-4", "--critic_lr", "7e-4", "--use_recurrent_policy", "true",
+                      "--use_valuenorm", "true", "--use_adv_normalize", "true", "--log_interval", "1000000", "--log_each_episode", "false"]),
+}
+
+
+class SyntheticHostEnv:
+    """BASELINE configs[4] stand-in (mujoco is absent): host-stepped env with HalfCheetah's shapes —
+    obs ~ N(0,1) (N,1,17), reward ~ N(0,1), done ~ Bernoulli(1/1000), Box(6) actions — numpy on the host cores."""
+
+    def __init__(self, n, obs_dim=17, act_dim=6, seed=0):
+        import numpy as np
+
+        from openrl_b200 import spaces
+
+        self.parallel_env_num, self.agent_num = n, 1
+        self.observation_space = spaces.Box(-np.inf, np.inf, (obs_dim,), np.float32)
+        self.action_space = spaces.Box(-1, 1, (act_dim,), np.float32)
+        self.rng, self.obs_dim, self.np = np.random.default_rng(seed), obs_dim, np
+
+    def reset(self, seed=None):
+        return self.rng.standard_normal((self.parallel_env_num, 1, self.obs_dim)).astype(self.np.float32)
+
+    def step(self, actions):
+        n = self.parallel_env_num
+        return (self.rng.standard_normal((n, 1, self.obs_dim)).astype(self.np.float32), self.rng.standard_normal((n, 1, 1)),
+                self.rng.random((n, 1)) < 1e-3, [{} for _ in range(n)])
+
+
+def build_agent(rank, world, workload="c2", envs=None, extra_flags=()):
     import torch
 
     from openrl_b200.configs.config import create_config_parser
@@ -101,10 +135,12 @@ def build_agent(rank, world, parity=False):
     from openrl_b200.modules.common import PPONet
     from openrl_b200.runners.common import PPOAgent
 
-    cfg = create_config_parser().parse_args(FLAGS)
+    w = WORKLOADS[workload]
+    n = w["envs"] if envs is None else envs
+    cfg = create_config_parser().parse_args(list(w["flags"]) + list(extra_flags))
     cfg.quiet = True
     dev = f"cuda:{torch.cuda.current_device()}"
-    env = make("CartPole-v1", env_num=N_ENVS, device=dev, env_index_offset=rank * N_ENVS)
+    env = make(w["env"], env_num=n, device=dev, env_index_offset=rank * n)
     net = PPONet(env, cfg=cfg, device=dev)
     return cfg, env, net, PPOAgent(net, rank=rank, world_size=world)
 
@@ -114,9 +150,10 @@ def make_driver(cfg, env, net, agent, rank, world):
     from openrl_b200.buffers import NormalReplayBuffer
     from openrl_b200.drivers.onpolicy_driver import OnPolicyDriver
 
-    trainer = PPOAlgorithm(cfg, net.module, agent_num=1, device=net.device)
-    buf = NormalReplayBuffer(cfg, 1, env.observation_space, env.action_space, device=net.device)
-    drv = OnPolicyDriver({"cfg": cfg, "num_agents": 1, "run_dir": None, "envs": env, "device": net.device}, trainer, buf,
+    A = env.agent_num
+    trainer = PPOAlgorithm(cfg, net.module, agent_num=A, device=net.device)
+    buf = NormalReplayBuffer(cfg, A, env.observation_space, env.action_space, device=net.device)
+    drv = OnPolicyDriver({"cfg": cfg, "num_agents": A, "run_dir": None, "envs": env, "device": net.device}, trainer, buf,
                          agent, rank=rank, world_size=world, logger=None, callback=None)
     drv.reset_and_buffer_init()
     return drv
@@ -154,38 +191,26 @@ def gae_roofline(flush, steps=10):
     return out
 
 
-def run_ours(args):
+def time_iterations(drv, steps, warmup, flush, world):
+    """W untimed + K timed device iterations (collect + update), CUDA events per iteration on the launching stream,
+    256 MB L2 flush between timed iterations, max over ranks.  Returns (seconds, phases_ms, launches, wall window)."""
     import torch
     import torch.distributed as dist
-
-    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
-    local = int(os.environ.get("LOCAL_RANK", 0))
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-    from openrl_b200.utils.logger import Logger
-
-    cfg, env, net, agent = build_agent(rank, world)
-    drv = make_driver(cfg, env, net, agent, rank, world)
-    flush = torch.empty(256 * 1024 * 1024 // 4, device="cuda")  # 256 MB > 126 MB L2
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         drv.device_iteration()
     barrier()
     drv.phase_events = []
     l0 = drv.gpu_launches + drv.trainer.gpu_launches
     events = []
     barrier()
-    t_wall0 = time.time()
-    for _ in range(args.steps):
+    t0 = time.time()
+    for _ in range(steps):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -193,7 +218,7 @@ def run_ours(args):
         e1.record()
         events.append((e0, e1))
     barrier()
-    sampler.window = (t_wall0, time.time())
+    window = (t0, time.time())
     launches = drv.gpu_launches + drv.trainer.gpu_launches - l0
     total_s = sum(a.elapsed_time(b) for a, b in events) * 1e-3
     phases = {}
@@ -203,69 +228,211 @@ def run_ours(args):
     t = torch.tensor([total_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_s = float(t.item())
-    env_steps = N_ENVS * T * args.steps * world
-    value = env_steps / total_s
+    return float(t.item()), {k: statistics.mean(v) for k, v in phases.items()}, launches, window
 
-    # ---- e2e through the public API (PPOAgent.train): host logging + D2H metric reads inside ----
-    cfg2, env2, net2, agent2 = build_agent(rank, world)
-    cfg2.log_interval = 1
-    agent2.train(total_time_steps=N_ENVS * T * 3, logger=Logger(quiet=True))  # warm-up call
-    barrier()
-    h2d0 = agent2.driver.trainer.h2d_bytes
-    d2h0 = (agent2.driver.trainer.d2h_bytes, getattr(env2, "d2h_bytes", 0))
+
+def time_e2e(rank, world, steps, workload="c2", envs=None, extra_flags=()):
+    """The same metric through the public API: PPOAgent.train(total_time_steps), wall clock, host logging and the
+    per-iteration D2H metric reads inside; max over ranks.  Returns (seconds, h2d bytes/step, d2h bytes/step)."""
+    import torch
+    import torch.distributed as dist
+
+    from openrl_b200.utils.logger import Logger
+
+    cfg, env, net, agent = build_agent(rank, world, workload, envs, extra_flags)
+    cfg.log_interval = 1
+    n, Tn = env.parallel_env_num, cfg.episode_length
+    agent.train(total_time_steps=n * Tn * 3, logger=Logger(quiet=True))  # warm-up call
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    tr, dr = agent.driver.trainer, agent.driver
+    h0, d0 = tr.h2d_bytes + dr.h2d_bytes + getattr(env, "h2d_bytes", 0), tr.d2h_bytes + dr.d2h_bytes + getattr(env, "d2h_bytes", 0)
     t0 = time.perf_counter()
-    agent2.train(total_time_steps=N_ENVS * T * args.steps, logger=Logger(quiet=True))
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    agent.train(total_time_steps=n * Tn * steps, logger=Logger(quiet=True))
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
-    tr2, dr2 = agent2.driver.trainer, agent2.driver
-    h2d = (tr2.h2d_bytes - h2d0 + dr2.h2d_bytes) / args.steps
-    d2h = (tr2.d2h_bytes - d2h0[0] + dr2.d2h_bytes + getattr(env2, "d2h_bytes", 0) - d2h0[1]) / args.steps
+    tr, dr = agent.driver.trainer, agent.driver
+    h1, d1 = tr.h2d_bytes + dr.h2d_bytes + getattr(env, "h2d_bytes", 0), tr.d2h_bytes + dr.d2h_bytes + getattr(env, "d2h_bytes", 0)
+    return float(t.item()), (h1 - h0) / steps, (d1 - d0) / steps
 
+
+def side_result(rank, world, flush, workload, steps, envs=None, extra_flags=(), e2e=True):
+    """A compact measurement of another configuration / mode (same timing rules), for the `extras` block."""
+    cfg, env, net, agent = build_agent(rank, world, workload, envs, extra_flags)
+    drv = make_driver(cfg, env, net, agent, rank, world)
+    n, Tn = env.parallel_env_num, cfg.episode_length
+    sec, phases, launches, _ = time_iterations(drv, steps, 3, flush, world)
+    out = {"workload": f"{WORKLOADS[workload]['env']}, {n} envs/GPU x {env.agent_num} agent(s), T={Tn}, {cfg.ppo_epoch} epochs x {cfg.num_mini_batch} minibatch"
+                       + (" " + " ".join(extra_flags) if extra_flags else ""),
+           "value": n * Tn * steps * world / sec, "unit": "env-steps/s", "ms_per_step": sec / steps * 1e3,
+           "phases_ms": {k: round(v, 4) for k, v in phases.items()}, "gpu_launches": launches, "steps": steps,
+           "update_kernel": "tcgen05 split-fp16" if drv.trainer.use_tensor_cores else ("GRU warp kernels (fp32)" if drv.trainer.recurrent else "fp32 FFMA")}
+    del drv
+    if e2e:
+        es, h2d, d2h = time_e2e(rank, world, steps, workload, envs, extra_flags)
+        out["e2e"] = {"value": n * Tn * steps * world / es, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
+    return out
+
+
+def c5_result(steps=3):
+    """BASELINE configs[4] class: host env.step (numpy stand-in with HalfCheetah shapes), device act + buffer + GAE +
+    update, Gaussian head; measured through PPOAgent.train (there is no device-only form of this path)."""
+    import torch
+
+    from openrl_b200.configs.config import create_config_parser
+    from openrl_b200.envs.vec_env import HostVecEnv
+    from openrl_b200.modules.common import PPONet
+    from openrl_b200.runners.common import PPOAgent
+    from openrl_b200.utils.logger import Logger
+
+    n, Tn = 1024, T
+    cfg = create_config_parser().parse_args(FLAGS)
+    cfg.quiet = True
+    host = SyntheticHostEnv(n)
+    env = HostVecEnv(host)
+    agent = PPOAgent(PPONet(env, cfg=cfg, device=f"cuda:{torch.cuda.current_device()}"))
+    agent.train(total_time_steps=n * Tn * 1, logger=Logger(quiet=True))
+    torch.cuda.synchronize()
+    h0, d0 = env.h2d_bytes, env.d2h_bytes
+    t0 = time.perf_counter()
+    agent.train(total_time_steps=n * Tn * steps, logger=Logger(quiet=True))
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    # the host env alone (its numpy step is the floor of this path)
+    a = host.rng.standard_normal((n, 1, 6)).astype("float32")
+    t1 = time.perf_counter()
+    for _ in range(Tn):
+        host.step(a)
+    host_s = time.perf_counter() - t1
+    return {"workload": f"host-stepped synthetic HalfCheetah shapes (obs 17, Box(6)), {n} envs, T={Tn}, {EPOCHS} epochs, Gaussian head",
+            "e2e": {"value": n * Tn * steps / dt, "unit": "env-steps/s", "h2d_bytes_per_step": (env.h2d_bytes - h0) / steps,
+                    "d2h_bytes_per_step": (env.d2h_bytes - d0) / steps},
+            "ms_per_step": dt / steps * 1e3, "host_env_only_ms_per_step": host_s * 1e3, "steps": steps}
+
+
+def ncu_traffic():
+    """dram bytes per launch of the GAE kernel from the committed ncu capture summary (profiles/), or None."""
+    for name in ("r2_ncu_gae.json", "r1_ncu_gae.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            d = json.load(open(p))
+            return d.get("dram_bytes_per_launch"), f"ncu --set full, profiles/{name} (dram__bytes_read.sum + dram__bytes_write.sum)"
+    return None, "no ncu capture summary under profiles/"
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+
+    flush = torch.empty(256 * 1024 * 1024 // 4, device="cuda")  # 256 MB > 126 MB L2
+    cfg, env, net, agent = build_agent(rank, world, "c2")
+    drv = make_driver(cfg, env, net, agent, rank, world)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    total_s, phases, launches, window = time_iterations(drv, args.steps, args.warmup, flush, world)
+    sampler.window = window
     clocks = sampler.stop() if rank == 0 else None
+    env_steps = N_ENVS * T * args.steps * world
+    value = env_steps / total_s
+    tc_update = drv.trainer.use_tensor_cores
+    del drv
+
+    e2e_s, h2d, d2h = time_e2e(rank, world, args.steps, "c2")
+
+    strong = None
+    if world > 1:
+        # strong scaling (SURVEY.md §8d): the GLOBAL env count held at 4096, 4096 / N envs per GPU
+        per = N_ENVS // world
+        cs, es, ns, ags = build_agent(rank, world, "c2", envs=per)
+        ds = make_driver(cs, es, ns, ags, rank, world)
+        ss, sph, sl, _ = time_iterations(ds, args.steps, args.warmup, flush, world)
+        strong = {"scaling": "strong", "global_envs": N_ENVS, "envs_per_gpu": per, "value": N_ENVS * T * args.steps / ss, "unit": "env-steps/s",
+                  "ms_per_step": ss / args.steps * 1e3, "phases_ms": {k: round(v, 4) for k, v in sph.items()}, "gpu_launches": sl}
+        del ds
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     hbm_peak, how = peaks()
     gae = gae_roofline(flush)
-    gae_in_step = statistics.mean(phases.get("gae", [0.0])) * 1e-3
-    upd_s = statistics.mean(phases.get("update", [0.0])) * 1e-3
+    gae_in_step = phases.get("gae", 0.0) * 1e-3
+    upd_s = phases.get("update", 0.0) * 1e-3
     flops_update = 53e3 * N_ENVS * T * EPOCHS  # fwd+bwd of both nets, SURVEY.md §8d
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
     fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+    pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    tensor_peak = pk.get("bf16_tflops", 1668.8)   # fp16 and bf16 dense MMAs run at the same rate
+    traffic, traffic_src = ncu_traffic()
+
+    extras = {}
+    if world == 1 and not args.no_extras:
+        def guarded(name, fn):
+            try:
+                extras[name] = fn()
+            except Exception as e:  # noqa: BLE001
+                extras[name] = {"error": f"{type(e).__name__}: {str(e)[-300:]}"}
+        # the same C2 workload with the fp32 FFMA update kernel, and in parity mode (reference-order CPU noise + randperm)
+        guarded("c2_fp32_ffma_update", lambda: side_result(0, 1, flush, "c2", 5, extra_flags=["--use_tensor_cores", "false"], e2e=False))
+        guarded("c2_parity_mode", lambda: side_result(0, 1, flush, "c2", 3, extra_flags=["--parity_mode", "true"], e2e=False))
+        guarded("target_128_envs", lambda: side_result(0, 1, flush, "target128", 10))
+        guarded("c1_8_envs", lambda: side_result(0, 1, flush, "c1", 10))
+        guarded("c3_mpe_gru_2048x3", lambda: side_result(0, 1, flush, "c3", 3, e2e=False))
+        guarded("c5_host_env_1024", lambda: c5_result(3))
     cpu = None if args.no_cpu_baseline else cpu_baseline_sample(n_envs=256, iters=1)
     out = {
-        "metric": "env-steps/sec (collect+update), CartPole-v1 PPO", "value": value, "unit": "env-steps/s",
+        "metric": METRIC, "value": value, "unit": "env-steps/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_s / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (policy/critic/losses; fc3 GEMMs as split-fp16 tcgen05 MMAs with fp32 accumulate = fp32-class accuracy), f64 (CartPole state)",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 (nets, losses, Adam; the three 64x64 GEMM groups of the update run as split-fp16 tcgen05 MMAs with fp32 "
+                 "accumulation = fp32-class accuracy, the mode the 1e-4 parity tests run in), f64 (CartPole state)",
         "data": "synthetic: device-resident CartPole-v1, random-init nets, seed 0",
         "config": {"workload": WORKLOAD, "global_envs": N_ENVS * world, "rollout_T": T, "parallelism": f"env-shard dp{world}",
                    "l2": "256 MB L2 flush between timed iterations; inside an iteration the 25 MB buffer is re-read by design",
-                   "sampling": "device Philox (fast mode); parity mode is covered by tests/"},
+                   "sampling": "device Philox4x32 action sampling, whole-buffer minibatch without a permutation (chi-square / moment "
+                               "tested, tests/test_sampling_cuda.py); the reference-order CPU-noise mode is extras.c2_parity_mode"},
         "gpu_launches": launches,
-        "phases_ms": {k: statistics.mean(v) for k, v in phases.items()},
+        "phases_ms": phases,
         "e2e": {"value": env_steps / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "api": "PPOAgent.train(total_time_steps) incl. construction, per-iteration logging reads"},
+                "api": "PPOAgent.train(total_time_steps) incl. per-iteration logging reads; the env is device-resident (north_star), "
+                       "so a step has no host inputs"},
         "roofline": {"bound": "hbm", "kernel": "gae_scan_kernel (orl_gae), >=1 GB shape, L2 flushed", "achieved": gae["1GB"]["GBps"],
                      "peak": hbm_peak, "peak_source": how, "unit": "GB/s", "frac": gae["1GB"]["GBps"] / hbm_peak,
                      "algorithmic_bytes_per_launch": 128 * (1 << 21) * 24,
-                     "traffic": 4.303432e9 + 2.126753e9, "traffic_source": "ncu --set full, profiles/r1_ncu_summary.md (dram read+write)",
+                     "traffic": traffic, "traffic_source": traffic_src,
                      "config_shape": {**gae["config"], "frac": gae["config"]["GBps"] / hbm_peak,
                                       "in_step_avg_s": gae_in_step,
                                       "in_step_GBps": N_ENVS * T * 24 / max(gae_in_step, 1e-12) / 1e9}},
-        "update_kernel": {"kernel": "ppo_fwdbwd_tc_kernel (tcgen05, split-fp16 operands, fp32 accumulate)" if drv.trainer.use_tensor_cores else "ppo_fwdbwd_kernel (fp32 FFMA)",
-                          "bound": "issue/latency (row-wise LayerNorm + loss work between three small MMAs per 128-row tile)",
-                          "avg_s_per_iteration": upd_s, "algorithmic_flop_per_row": 53e3,
-                          "achieved_tflops": flops_update / max(upd_s, 1e-12) / 1e12, "fp32_peak_tflops_at_clock": fp32_peak,
-                          "frac_of_fp32_pipe_peak": flops_update / max(upd_s, 1e-12) / 1e12 / fp32_peak},
+        "roofline_dominant": {"kernel": "ppo_fwdbwd_tc_kernel (tcgen05 kind::f16, split-fp16 operands, 2 CTAs/SM)" if tc_update else "ppo_fwdbwd_kernel (fp32 FFMA)",
+                              "share_of_step": upd_s / max(total_s / args.steps, 1e-12),
+                              "bound": "tensor" if tc_update else "fp32 pipe",
+                              "avg_s_per_iteration": upd_s, "launches_per_iteration": EPOCHS * MINIBATCH,
+                              "algorithmic_flop_per_row": 53e3, "achieved": flops_update / max(upd_s, 1e-12) / 1e12, "unit": "TFLOP/s",
+                              "peak": tensor_peak if tc_update else fp32_peak,
+                              "frac": flops_update / max(upd_s, 1e-12) / 1e12 / (tensor_peak if tc_update else fp32_peak),
+                              "frac_of_fp32_pipe_peak": flops_update / max(upd_s, 1e-12) / 1e12 / fp32_peak,
+                              "note": "algorithmic FLOPs (53 kFLOP/row, SURVEY.md 8d); the split issues 3 MMAs per product and M=128 "
+                                      "tiles with unused lanes, so tensor-pipe activity is higher than this fraction (ncu, profiles/)"},
         "cpu_baseline": cpu,
         "clocks": clocks,
     }
+    if strong is not None:
+        out["strong_scaling"] = strong
+    if extras:
+        out["extras"] = extras
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -399,6 +566,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="development: skip the cpu_baseline leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extras block (other configs / modes)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

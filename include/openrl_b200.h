@@ -171,7 +171,9 @@ typedef struct OrlRolloutArgs {
                                    action_log_probs are (T, B, n) (per-dimension log-probs), exp_noise holds
                                    N(0,1) draws (torch.normal == noise*std + mean) and the parameter vector ends
                                    with logstd[n].  Gaussian heads act on host-stepped envs (ORL_ENV_NONE). */
-    int32_t reserved1;
+    int32_t rng_row_offset;     /* added to the row index in the Philox counter: rank r of an env-sharded run passes its
+                                   first global row (r * B) with the SAME rng_seed on every rank, so that sharded rollouts
+                                   draw exactly the noise the unsharded run draws for those rows */
 } OrlRolloutArgs;
 int orl_rollout(const OrlRolloutArgs* args, void* stream);
 

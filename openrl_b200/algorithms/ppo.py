@@ -242,7 +242,11 @@ class PPOAlgorithm:
             # train_ppo from whatever the buffer holds; here that is the GAE launch with the bootstrap value of slot T
             buf.compute_returns(None, self.algo_module.get_critic_value_normalizer())
             self.gpu_launches += 1
-        parallel.allreduce_sum_(buf.gae_stats)  # global advantage / return moments (ppo.py:402-409 semantics)
+        if not getattr(buf, "stats_global", False):
+            # global advantage / return moments (ppo.py:402-409 semantics); once per compute_returns — a second train() on
+            # the same buffer must not sum the already-global moments again
+            parallel.allreduce_sum_(buf.gae_stats)
+            buf.stats_global = True
         if self.recurrent:
             return self._train_recurrent(buf)
         total = buf.episode_length * buf.n_rollout_threads * buf.num_agents

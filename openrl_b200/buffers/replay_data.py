@@ -145,6 +145,7 @@ class ReplayData:
                                           (adv * act).sum(), (adv * adv * act).sum(), ret.sum(), (ret * ret).sum(),
                                           self.active_masks[:-1].double().sum()]))
         self.returns_ready = True
+        self.stats_global = False   # gae_stats now hold this rank's moments only (PPOAlgorithm.train_async all-reduces them once)
 
     def init_buffer(self, raw_obs, action_masks=None):
         """replay_data.py:286-298 — slot 0 <- first observation (host array or device tensor)."""
@@ -183,3 +184,4 @@ class ReplayData:
                                     lib.ptr(self.returns), lib.ptr(self.advantages), lib.ptr(self.gae_stats), T, B,
                                     float(self.gamma), float(self.gae_lambda), flags, lib.current_stream()), "orl_gae")
         self.returns_ready = True
+        self.stats_global = False   # gae_stats now hold this rank's moments only (PPOAlgorithm.train_async all-reduces them once)

@@ -95,7 +95,8 @@ __device__ __forceinline__ bool cartpole_dynamics(double (&s)[4], int action) {
 // cell is drawn uniformly over the 99 non-goal cells from Philox keyed by (seed, env, #reset), or
 // read from a host table reset_table[(env*max_resets + k)*2] when one is supplied (parity runs).
 __device__ __forceinline__ void gridworld_reset(int& x, int& y, int env, int nreset, uint64_t seed,
-                                                const int* __restrict__ table, int max_resets, int nrow, int ncol) {
+                                                const int* __restrict__ table, int max_resets, int nrow, int ncol,
+                                                int env_key = -1) {   // env_key: GLOBAL env index for the Philox counter (default: env)
     if (table) {
         const int k = min(nreset, max_resets - 1);
         x = table[(env * max_resets + k) * 2 + 0];
@@ -103,7 +104,7 @@ __device__ __forceinline__ void gridworld_reset(int& x, int& y, int env, int nre
         return;
     }
     // rejection sampling like the reference, bounded
-    uint4 c = make_uint4((uint32_t)env, (uint32_t)nreset, 0x47726964u, 0u);
+    uint4 c = make_uint4((uint32_t)(env_key >= 0 ? env_key : env), (uint32_t)nreset, 0x47726964u, 0u);
     const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
     for (int it = 0; it < 16; ++it) {
         c.w = it;

@@ -9,6 +9,7 @@ namespace orl {
 struct EnvPtrs {
     double* f64; uint64_t* u64; int32_t* i32; const int32_t* table; int table_len; uint64_t seed;
     float* ep_return; int32_t* ep_length; double* episode_stats;
+    int env_offset = 0;   // first GLOBAL env index of this shard: Philox-keyed env randomness is drawn per global env
 };
 
 // One env.step of a single-agent, 4-wide-observation env (CartPole-v1 / GridWorldEnv) with the
@@ -56,7 +57,7 @@ __device__ __forceinline__ void env_step_single(const EnvPtrs& E, int kind, int 
         int len = E.ep_length[e] + 1;
         fin[0] = (float)x; fin[1] = (float)y; fin[2] = 1.f; fin[3] = 1.f;
         if (done) {
-            gridworld_reset(x, y, e, nreset, E.seed, E.table, E.table_len, nrow, ncol);
+            gridworld_reset(x, y, e, nreset, E.seed, E.table, E.table_len, nrow, ncol, e + E.env_offset);
             nreset += 1; steps = 0;
             atomicAdd(E.episode_stats + 0, (double)ret);
             atomicAdd(E.episode_stats + 1, (double)len);

@@ -24,8 +24,10 @@
 //   GEMM3b Gb [128x16] += dZ1^T . [CST | X]          both MN-major: db1 (col 0), G1 = dZ1^T X (cols 8..15)
 // Ga / Gb stay in TMEM for the whole kernel.  GH = dL^T n3 needs no n3 tile: with n3 = (Z3 + b3f - mu3) rstd3
 // and Z3 = n1 W3f^T,   GH[j][k] = sum_i Q[j][i] W3f[k][i] + b3f[k] su[j] - smu[j]   (evaluated once at the end).
-// Backward operands are scaled by S = 2^e (~ minibatch rows / 16) so that 1/rows-weighted gradients sit in
-// the fp16 range; the accumulators are multiplied by 1/S (exact) when flushed.
+// fp16 carries 22 significand bits as hi + lo only while hi >= 2^-3 (below, lo is subnormal), so every backward
+// operand is scaled by a power of two chosen per minibatch to put its TYPICAL magnitude near 2^4: dZ3 / dZ1 by
+// S_z ~ 8 rows / max|Whf| (head weights are tiny: gain 0.01), U by S_u ~ 8 rows, observations by 16; the accumulators
+// are multiplied by the exact inverse when flushed, conversions saturate instead of overflowing.
 //
 // Minibatch tiles are staged in shared memory one tile ahead: TMA (cp.async.bulk.tensor: the 128 x d
 // observation tile and the scalar columns, zero-filled past the end) when the minibatch is a contiguous
@@ -33,6 +35,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -88,7 +91,14 @@ constexpr uint32_t SMALL_FLOATS = 8 * H + H + H + MAX_OUT * H + 2 * MAX_OUT;
 constexpr uint32_t XCH_FLOATS = 2 * T_M * 2 + 2 * T_M * 8;
 __host__ __device__ inline uint32_t tc_smem_bytes(int d) { return tc_small_off(d) + 4 * (SMALL_FLOATS + XCH_FLOATS) + 5 * 8 + 16; }
 
-template <bool POLICY, int NOUT, bool TMA>
+// ACT == 1: ReLU (the reference's default activation_id) compiled in; ACT == -1: runtime activation_id (tanh / leaky / elu
+// expand to ~60 instructions per element, which the fully unrolled row code cannot afford in the instruction cache)
+template <int ACT>
+__device__ __forceinline__ float act_fwd_t(float z, int activation_id) { return ACT == 1 ? fmaxf(z, 0.f) : act_fwd(z, activation_id); }
+template <int ACT>
+__device__ __forceinline__ float act_bwd_t(float a, bool pos, int activation_id) { return ACT == 1 ? (pos ? 1.f : 0.f) : act_bwd(a, pos, activation_id); }
+
+template <bool POLICY, int NOUT, int ACT, bool TMA>
 __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, const TcMaps& maps, uint8_t* smem, int cta, int G, int stride) {
     const int d = POLICY ? a.obs_dim : a.critic_obs_dim;
     const int n = POLICY ? (NOUT == 8 ? a.n_actions : NOUT) : 1;
@@ -165,10 +175,15 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, const TcMaps& m
     const double rows_d = (double)(a.norm_rows > 0 ? a.norm_rows : a.batch_rows);
     const float inv_rows = (float)(1.0 / rows_d), inv_act = (float)(1.0 / a.mb_stats[2]);
     // operand scale of the backward GEMMs: 2^e ~ rows / 16 (row weights are ~ 1/rows)
-    int sexp = 0;
-    while (sexp < 40 && (double)(1ll << sexp) < rows_d) ++sexp;
-    sexp = max(sexp - 4, 0);
-    const float S = exp2f((float)sexp), invS = exp2f(-(float)sexp);
+    // operand scales of the backward GEMMs (powers of two; see the header comment)
+    float wmax = 0.f;
+    for (int i = 0; i < MAX_OUT * H; ++i) wmax = fmaxf(wmax, fabsf(whf[i]));   // smem broadcast reads, once per kernel
+    const int e_rows = (int)ceil(log2(fmax(rows_d, 1.0)));
+    const int e_u = min(e_rows + 3, 60);
+    const int e_z = min(max(e_rows + 3 - (int)floorf(log2f(fmaxf(wmax, 1e-12f))), 0), 60);
+    const float Sz = exp2f((float)e_z), Su = exp2f((float)e_u);
+    constexpr float SX = 16.f, K1 = 0.25f;          // observations x 16; dZ1 is stored as S_z / 4
+    const float invSz = exp2f(-(float)e_z), invSu = exp2f(-(float)e_u), invS1 = invSz * (1.f / K1);
     AdvNormTc an = {0.f, 1.f, 0.f, 1.f, false};
     float vn_mean = 0.f, vn_std = 1.f;
     if (POLICY) {  // ppo.py:402-409
@@ -286,7 +301,7 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, const TcMaps& m
 #pragma unroll
         for (int i = 0; i < CW; ++i) {
             if (n1[i] > 0.f) posmask |= 1u << i;
-            n1[i] = act_fwd(n1[i], a.activation_id);
+            n1[i] = act_fwd_t<ACT>(n1[i], a.activation_id);
             s += n1[i]; sq = fmaf(n1[i], n1[i], sq);
         }
         {   // exchange 1 (slot xs): LayerNorm-1 statistics
@@ -307,16 +322,16 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, const TcMaps& m
             const uint32_t off = (uint32_t)((cb + q8) >> 3) * PANEL + row * 16;
             split_store8(R1h + off, R1l + off, n1 + q8, 1.0f);
         }
-        if (half == 0) split_store8(R1h + P_X * PANEL + row * 16, R1l + P_X * PANEL + row * 16, x, 1.0f);
+        if (half == 0) split_store8(R1h + P_X * PANEL + row * 16, R1l + P_X * PANEL + row * 16, x, SX);
         fence_proxy_async();
         tcgen05_fence_before();
         __syncthreads();
         if (warp == 0 && elect_one()) {   // GEMM1: Z3 = n1 . W3f^T
             tcgen05_fence_after();
-#pragma unroll
+#pragma unroll 1
             for (int pass = 0; pass < 3; ++pass) {
                 const uint32_t aa = pass == 0 ? aR1l : aR1h, bb = pass == 1 ? aWl : aWh;
-#pragma unroll
+#pragma unroll 1
                 for (int kk = 0; kk < 4; ++kk)
                     mma_f16(tmem + TM_Z, desc_at(dK_A, aa + 2 * kk * PANEL), desc_at(dK_W, bb + 2 * kk * PANEL_W), id_g1, (pass | kk) > 0);
             }
@@ -429,7 +444,7 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, const TcMaps& m
         //      mean(dn3) = sum_j dL[j] rowsum(Whf[j]) / 64 and mean(dn3 n3) = sum_j dL[j] dot[j] / 64), scaled by S ----
         float m1 = 0.f, m2 = 0.f;
 #pragma unroll
-        for (int j = 0; j < MAX_OUT; ++j) dl[j] *= S;
+        for (int j = 0; j < MAX_OUT; ++j) dl[j] *= Sz;
         FOR_OUT(j) { m1 = fmaf(dl[j], swh[j], m1); m2 = fmaf(dl[j], dot[j], m2); }
         m1 *= (1.f / H); m2 *= (1.f / H);
 #pragma unroll
@@ -453,7 +468,7 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, const TcMaps& m
         if (half == 0) {
             float u8[8], c8[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { u8[j] = dl[j] * rstd3; c8[j] = 0.f; }
+            for (int j = 0; j < 8; ++j) { u8[j] = dl[j] * (rstd3 * (Su * invSz)); c8[j] = 0.f; }
             c8[0] = 1.0f; c8[1] = mu3; c8[2] = var3 * rstd3;   // std3 = var3 / sqrt(var3)
             split_store8(R2h + P_U * PANEL + row * 16, R2l + P_U * PANEL + row * 16, u8, 1.0f);
             split_store8(R1h + P_CST * PANEL + row * 16, R1l + P_CST * PANEL + row * 16, c8, 1.0f);
@@ -463,18 +478,18 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, const TcMaps& m
         __syncthreads();
         if (warp == 0 && elect_one()) {   // GEMM2: dN1 = dZ3 . W3f ; GEMM3a: Ga += R2^T . R1
             tcgen05_fence_after();
-#pragma unroll
+#pragma unroll 1
             for (int pass = 0; pass < 3; ++pass) {
                 const uint32_t aa = pass == 0 ? aR2l : aR2h, bb = pass == 1 ? aWl : aWh;
-#pragma unroll
+#pragma unroll 1
                 for (int kk = 0; kk < 4; ++kk)
                     mma_f16(tmem + TM_Z, desc_at(dK_A, aa + 2 * kk * PANEL), desc_at(dMN_W, bb + kk * 256), id_g2, (pass | kk) > 0);
             }
             mma_commit(&bars[1]);
-#pragma unroll
+#pragma unroll 1
             for (int pass = 0; pass < 3; ++pass) {
                 const uint32_t aa = pass == 0 ? aR2l : aR2h, bb = pass == 1 ? aR1l : aR1h;
-#pragma unroll
+#pragma unroll 1
                 for (int kk = 0; kk < 8; ++kk)
                     mma_f16(tmem + TM_GA, desc_at(dMN_A, aa + kk * 256), desc_at(dMN_A, bb + kk * 256), id_3a, (it | pass | kk) > 0);
             }
@@ -501,7 +516,7 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, const TcMaps& m
             for (int i = 0; i < CW; ++i) {
                 const float da = rstd1 * (g[i] - t1 - n1[i] * t2);
                 const float aval = fmaf(n1[i], std1, mu1);                          // activation output
-                g[i] = da * act_bwd(aval, (posmask >> i) & 1u, a.activation_id);
+                g[i] = da * (K1 * act_bwd_t<ACT>(aval, (posmask >> i) & 1u, a.activation_id));
             }
             mbar_wait(&bars[2], par);   // GEMM3a has finished reading n1 from R1
 #pragma unroll
@@ -515,10 +530,10 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, const TcMaps& m
         __syncthreads();
         if (warp == 0 && elect_one()) {   // GEMM3b: Gb += dZ1^T . [CST | X]
             tcgen05_fence_after();
-#pragma unroll
+#pragma unroll 1
             for (int pass = 0; pass < 3; ++pass) {
                 const uint32_t aa = pass == 0 ? aR1l : aR1h, bb = (pass == 1 ? aR1l : aR1h) + P_CST * PANEL;
-#pragma unroll
+#pragma unroll 1
                 for (int kk = 0; kk < 8; ++kk)
                     mma_f16(tmem + TM_GB, desc_at(dMN_A, aa + kk * 256), desc_at(dMN_A, bb + kk * 256), id_3b, (it | pass | kk) > 0);
             }
@@ -539,7 +554,7 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, const TcMaps& m
             tmem_ld_row32(tmem_row + TM_GA + 32 * half, v);
             if (row < H) {
 #pragma unroll
-                for (int c = 0; c < 32; ++c) part[fo.g3 + row * H + 32 * half + c] = v[c] * invS;
+                for (int c = 0; c < 32; ++c) part[fo.g3 + row * H + 32 * half + c] = v[c] * invSz;
             } else if (row < H + n) {
 #pragma unroll
                 for (int c = 0; c < 32; ++c) qs[(row - H) * H + 32 * half + c] = v[c];
@@ -548,14 +563,14 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, const TcMaps& m
         if (half == 0) {
             float c8[8];
             tmem_ld_row8(tmem_row + TM_GA + 64, c8);
-            if (row < H) part[fo.db3 + row] = c8[0] * invS;
+            if (row < H) part[fo.db3 + row] = c8[0] * invSz;
             else if (row < H + n) { qsu[row - H] = c8[0]; qsu[8 + row - H] = c8[1]; qsu[16 + row - H] = c8[2]; }
             float g16[16];
             tmem_ld_row16(tmem_row + TM_GB, g16);
             if (row < H) {
-                part[fo.db1 + row] = g16[0] * invS;
+                part[fo.db1 + row] = g16[0] * invS1;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) if (c < d) part[fo.g1 + row * d + c] = g16[8 + c] * invS;
+                for (int c = 0; c < 8; ++c) if (c < d) part[fo.g1 + row * d + c] = g16[8 + c] * (invS1 * (1.f / SX));
             }
         }
         __syncthreads();
@@ -565,8 +580,8 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, const TcMaps& m
             float acc = 0.f;
             for (int i = 0; i < H; ++i) acc = fmaf(qs[j * H + i], params[po.w3 + k * H + i] * params[po.g1 + i], acc);
             acc = fmaf(b3f[k], qsu[j], acc) - qsu[8 + j];
-            part[fo.gh + o] = acc * invS;
-            if (k == 0) { part[fo.dbh + j] = qsu[16 + j] * invS; part[fo.dls + j] = 0.f; }
+            part[fo.gh + o] = acc * invSu;
+            if (k == 0) { part[fo.dbh + j] = qsu[16 + j] * invSu; part[fo.dls + j] = 0.f; }
         }
     } else {
         for (int i = tid; i < fo.total; i += T_NT) part[i] = 0.f;   // an idle CTA
@@ -590,17 +605,28 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, const TcMaps& m
     if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
-template <bool TMA>
-__global__ void __launch_bounds__(T_NT, 2) ppo_fwdbwd_tc_kernel(const OrlPpoArgs a, const __grid_constant__ TcMaps maps, int stride) {
+// blockIdx -> (net, cta): with `pair_nets` the two CTAs that share an SM (blocks b and b + #SMs under round-robin
+// placement, #SMs even) run the SAME net, i.e. the same instruction stream (instruction-cache footprint halves);
+// otherwise CTAs [0, G) are the policy net and [G, 2G) the critic net.
+template <int NOUT, int ACT, bool TMA>
+__global__ void __launch_bounds__(T_NT, 2) ppo_fwdbwd_tc_kernel(const OrlPpoArgs a, const __grid_constant__ TcMaps maps, int stride, int pair_nets) {
     extern __shared__ __align__(1024) uint8_t smem_tc[];
     const int G = a.grid_per_net;
-    if ((int)blockIdx.x < G) {
-        if (a.n_actions == 2) tc_net_pass<true, 2, TMA>(a, maps, smem_tc, blockIdx.x, G, stride);
-        else if (a.n_actions == 5) tc_net_pass<true, 5, TMA>(a, maps, smem_tc, blockIdx.x, G, stride);
-        else tc_net_pass<true, 8, TMA>(a, maps, smem_tc, blockIdx.x, G, stride);
-    } else {
-        tc_net_pass<false, 1, TMA>(a, maps, smem_tc, blockIdx.x - G, G, stride);
-    }
+    const bool policy = pair_nets ? ((blockIdx.x & 1) == 0) : ((int)blockIdx.x < G);
+    const int cta = pair_nets ? (int)(blockIdx.x >> 1) : ((int)blockIdx.x < G ? (int)blockIdx.x : (int)blockIdx.x - G);
+    if (policy) tc_net_pass<true, NOUT, ACT, TMA>(a, maps, smem_tc, cta, G, stride);
+    else tc_net_pass<false, 1, ACT, TMA>(a, maps, smem_tc, cta, G, stride);
+}
+
+using TcKernel = void (*)(const OrlPpoArgs, const TcMaps, int, int);
+template <int NOUT, int ACT>
+TcKernel pick_staging(bool tma) { return tma ? ppo_fwdbwd_tc_kernel<NOUT, ACT, true> : ppo_fwdbwd_tc_kernel<NOUT, ACT, false>; }
+template <int NOUT>
+TcKernel pick_act(int activation_id, bool tma) { return activation_id == 1 ? pick_staging<NOUT, 1>(tma) : pick_staging<NOUT, -1>(tma); }
+TcKernel pick_kernel(int n_actions, int activation_id, bool tma) {
+    if (n_actions == 2) return pick_act<2>(activation_id, tma);
+    if (n_actions == 5) return pick_act<5>(activation_id, tma);
+    return pick_act<8>(activation_id, tma);
 }
 
 // ---- host: TMA descriptors of the flattened rollout buffers ----
@@ -673,16 +699,6 @@ int launch_ppo_fwdbwd_tc(const OrlPpoArgs& a, cudaStream_t st) {
     }
     const int dmax = std::max(a.obs_dim, a.critic_obs_dim);
     const size_t smem = tc_smem_bytes(dmax);
-    static bool attr_set = false;
-    if (!attr_set) {
-        int e = check_cuda(cudaFuncSetAttribute(ppo_fwdbwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 116 * 1024), "cudaFuncSetAttribute(ppo_fwdbwd_tc)");
-        if (e) return e;
-        e = check_cuda(cudaFuncSetAttribute(ppo_fwdbwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 116 * 1024), "cudaFuncSetAttribute(ppo_fwdbwd_tc)");
-        if (e) return e;
-        cudaFuncSetAttribute(ppo_fwdbwd_tc_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaFuncSetAttribute(ppo_fwdbwd_tc_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        attr_set = true;
-    }
     const int stride = ppo_stride_host(a.obs_dim, a.critic_obs_dim, a.n_actions);
     // TMA staging: contiguous row range, rows of 16-byte multiples (d % 4 == 0), 16-byte aligned bases
     const bool tma_ok = a.indices == nullptr && (a.obs_dim % 4 == 0) && (a.critic_obs_dim % 4 == 0) &&
@@ -691,13 +707,22 @@ int launch_ppo_fwdbwd_tc(const OrlPpoArgs& a, cudaStream_t st) {
                           reinterpret_cast<uintptr_t>(a.returns) | reinterpret_cast<uintptr_t>(a.active_masks)) & 15) == 0 &&
                         a.row_begin + (((a.batch_rows + T_M - 1) / T_M) * T_M) < (1ll << 31);
     const TcMaps* maps = tma_ok ? maps_for(a) : nullptr;
-    if (maps) {
-        ppo_fwdbwd_tc_kernel<true><<<2 * a.grid_per_net, T_NT, smem, st>>>(a, *maps, stride);
-    } else {
-        TcMaps none;
-        memset(&none, 0, sizeof(none));
-        ppo_fwdbwd_tc_kernel<false><<<2 * a.grid_per_net, T_NT, smem, st>>>(a, none, stride);
+    TcKernel kern = pick_kernel(a.n_actions, a.activation_id, maps != nullptr);
+    {
+        static std::mutex mu;
+        static std::map<TcKernel, bool> prepared;
+        std::lock_guard<std::mutex> lock(mu);
+        if (!prepared.count(kern)) {
+            int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 116 * 1024), "cudaFuncSetAttribute(ppo_fwdbwd_tc)");
+            if (e) return e;
+            cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            prepared[kern] = true;
+        }
     }
+    static const int pair_nets = [] { const char* v = getenv("ORL_TC_PAIR_NETS"); return v ? atoi(v) : 0; }();
+    TcMaps none;
+    if (!maps) memset(&none, 0, sizeof(none));
+    kern<<<2 * a.grid_per_net, T_NT, smem, st>>>(a, maps ? *maps : none, stride, pair_nets && (a.grid_per_net % 2 == 0));
     return check_cuda(cudaGetLastError(), "ppo_fwdbwd_tc_kernel");
 }
 }  // namespace orl

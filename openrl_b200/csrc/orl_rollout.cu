@@ -98,10 +98,10 @@ __global__ void __launch_bounds__(R_NT) rollout_kernel(const OrlRolloutArgs a) {
             if (!a.exp_noise && !a.deterministic) {
                 const uint64_t step = rng_base + (uint64_t)t;
                 const uint2 key = make_uint2((uint32_t)a.rng_seed, (uint32_t)(a.rng_seed >> 32));
-                const uint4 r0 = philox4x32_10(make_uint4((uint32_t)step, (uint32_t)(step >> 32), (uint32_t)(row0 + hrow), 2u), key);
-                const uint4 r1 = philox4x32_10(make_uint4((uint32_t)step, (uint32_t)(step >> 32), (uint32_t)(row0 + hrow), 3u), key);
-                const uint4 r2 = philox4x32_10(make_uint4((uint32_t)step, (uint32_t)(step >> 32), (uint32_t)(row0 + hrow), 4u), key);
-                const uint4 r3 = philox4x32_10(make_uint4((uint32_t)step, (uint32_t)(step >> 32), (uint32_t)(row0 + hrow), 5u), key);
+                const uint4 r0 = philox4x32_10(make_uint4((uint32_t)step, (uint32_t)(step >> 32), (uint32_t)(row0 + hrow + a.rng_row_offset), 2u), key);
+                const uint4 r1 = philox4x32_10(make_uint4((uint32_t)step, (uint32_t)(step >> 32), (uint32_t)(row0 + hrow + a.rng_row_offset), 3u), key);
+                const uint4 r2 = philox4x32_10(make_uint4((uint32_t)step, (uint32_t)(step >> 32), (uint32_t)(row0 + hrow + a.rng_row_offset), 4u), key);
+                const uint4 r3 = philox4x32_10(make_uint4((uint32_t)step, (uint32_t)(step >> 32), (uint32_t)(row0 + hrow + a.rng_row_offset), 5u), key);
                 // Box-Muller: 8 normals from 16 uniforms (pairs (r0,r1) and (r2,r3))
                 const uint32_t u1[8] = {r0.x, r0.y, r0.z, r0.w, r2.x, r2.y, r2.z, r2.w};
                 const uint32_t u2[8] = {r1.x, r1.y, r1.z, r1.w, r3.x, r3.y, r3.z, r3.w};
@@ -150,8 +150,8 @@ __global__ void __launch_bounds__(R_NT) rollout_kernel(const OrlRolloutArgs a) {
                 } else {
                     const uint64_t step = rng_base + (uint64_t)t;
                     const uint2 key = make_uint2((uint32_t)a.rng_seed, (uint32_t)(a.rng_seed >> 32));
-                    const uint4 r0 = philox4x32_10(make_uint4((uint32_t)step, (uint32_t)(step >> 32), (uint32_t)(row0 + hrow), 0u), key);
-                    const uint4 r1 = philox4x32_10(make_uint4((uint32_t)step, (uint32_t)(step >> 32), (uint32_t)(row0 + hrow), 1u), key);
+                    const uint4 r0 = philox4x32_10(make_uint4((uint32_t)step, (uint32_t)(step >> 32), (uint32_t)(row0 + hrow + a.rng_row_offset), 0u), key);
+                    const uint4 r1 = philox4x32_10(make_uint4((uint32_t)step, (uint32_t)(step >> 32), (uint32_t)(row0 + hrow + a.rng_row_offset), 1u), key);
                     const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
                     for (int j = 0; j < MAX_OUT; ++j) q[j] = -logf(u32_to_unit_open(rr[j]));
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(R_NT) rollout_kernel(const OrlRolloutArgs a) {
           if constexpr (ENV == ORL_ENV_CARTPOLE || ENV == ORL_ENV_GRIDWORLD) {
             const int e = env0 + tid;
             EnvPtrs E{a.env_f64, a.env_u64, a.env_i32, a.env_table, a.env_table_len, a.rng_seed,
-                      a.ep_return, a.ep_length, a.episode_stats};
+                      a.ep_return, a.ep_length, a.episode_stats, a.rng_row_offset / max(a.n_agents, 1)};
             float ob[4], fin[4], reward; bool done;
             env_step_single(E, ENV, e, N, act_s[tid], ob, reward, done, fin);
             const size_t o1 = ((size_t)(t + 1) * B + e);

@@ -132,7 +132,11 @@ class OnPolicyDriver:
         a.masks, a.active_masks = lib.ptr(d.masks), lib.ptr(d.active_masks)
         a.action_masks = None if d.action_masks_trivial else lib.ptr(d.action_masks)
         a.exp_noise = lib.ptr(noise)
-        a.rng_seed, a.rng_step_base, a.rng_counter = int(self.cfg.seed) + 0x9E3779B9 * (self.rank + 1), 0, lib.ptr(self.rng_counter)
+        # one noise key for all ranks; a rank's rows are offset by its first GLOBAL row, so an env-sharded rollout draws
+        # exactly the noise the unsharded rollout draws for the same envs
+        # the env's own seed (what reset()/step() of the vec-env API use), so fused and per-call stepping agree
+        a.rng_seed, a.rng_step_base, a.rng_counter = int(getattr(env, "rng_seed", self.cfg.seed)), 0, lib.ptr(self.rng_counter)
+        a.rng_row_offset = int(getattr(env, "env_index_offset", 0)) * env.agent_num
         a.env_f64, a.env_u64, a.env_i32 = lib.ptr(env.env_f64), lib.ptr(env.env_u64), lib.ptr(env.env_i32)
         a.env_table = lib.ptr(env.env_table)
         a.ep_return, a.ep_length, a.episode_stats = lib.ptr(env.ep_return), lib.ptr(env.ep_length), lib.ptr(env.episode_stats)

@@ -108,7 +108,7 @@ class OrlRolloutArgs(ctypes.Structure):
         ("rng_seed", _c.c_uint64), ("rng_step_base", _c.c_uint64), ("rng_counter", _P),
         ("env_f64", _P), ("env_u64", _P), ("env_i32", _P), ("env_table", _P),
         ("ep_return", _P), ("ep_length", _P), ("episode_stats", _P),
-        ("head_kind", _c.c_int32), ("reserved1", _c.c_int32),
+        ("head_kind", _c.c_int32), ("rng_row_offset", _c.c_int32),
     ]
 
 

@@ -16,16 +16,26 @@ design.  The same functions run on CPU tensors with the gloo backend (tests/test
 import torch.distributed as dist
 
 
+_FORCE_SINGLE = False
+
+
+def force_single_process(on=True):
+    """Make this process behave as an unsharded run even though a process group exists (used by the multi-GPU
+    equivalence check, which runs the global-batch reference on rank 0 next to the sharded run)."""
+    global _FORCE_SINGLE
+    _FORCE_SINGLE = bool(on)
+
+
 def is_distributed():
-    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    return (not _FORCE_SINGLE) and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
 
 
 def world_size():
-    return dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+    return dist.get_world_size() if is_distributed() else 1
 
 
 def rank():
-    return dist.get_rank() if (dist.is_available() and dist.is_initialized()) else 0
+    return dist.get_rank() if is_distributed() else 0
 
 
 def allreduce_sum_(t):

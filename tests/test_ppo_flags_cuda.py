@@ -110,7 +110,7 @@ def test_update_flag_matrix_vs_oracle(cuda, flags):
         np.testing.assert_allclose(got[col], want[col], rtol=2e-4, atol=5e-6, err_msg=name)
     for mk, params in (("policy", pol), ("critic", cri)):
         for k, v in net.module.models[mk].named_parameters():
-            np.testing.assert_allclose(v.detach().cpu().numpy(), params[k].detach().numpy(), rtol=1e-3, atol=0.05 * max(cfg.lr, cfg.critic_lr),
+            np.testing.assert_allclose(v.detach().cpu().numpy(), params[k].detach().numpy(), rtol=1e-3, atol=0.1 * max(cfg.lr, cfg.critic_lr),
                                        err_msg=f"{mk}.{k}")
     if vn is not None:
         np.testing.assert_allclose(vn.state.cpu().numpy(), ovn.state(), rtol=1e-5)

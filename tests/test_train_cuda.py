@@ -40,7 +40,7 @@ def test_train_matches_reference_trace(cuda, tag):
         for k, v in net.module.models[mk].state_dict().items():
             gk = f"it{last}/params/{mk}.{k}"
             if gk in d:
-                np.testing.assert_allclose(v.cpu().numpy(), d[gk], rtol=2e-3, atol=0.05 * cfg.lr, err_msg=gk)
+                np.testing.assert_allclose(v.cpu().numpy(), d[gk], rtol=2e-3, atol=0.1 * cfg.lr, err_msg=gk)
 
 
 @pytest.mark.parametrize("use_tf32", ["true", "false"])
