@@ -1,0 +1,370 @@
+// Forward-only passes of the 64-wide MLPs on the tensor cores (tcgen05, split-fp16 operands, fp32 accumulate —
+// the same building blocks and accuracy class as the update kernel, orl_ppo_tc.cu / orl_tc16.cuh):
+//
+//   critic_values_tc_kernel : ValueNetwork.forward over a flat batch of rows (value_network.py:113-136), the
+//                             (T+1)*B-row pass of OnPolicyDriver.compute_returns (onpolicy_driver.py:206-215).
+//   rollout_tc_kernel       : the fused rollout (policy forward + Categorical sampling + device env.step + in-place
+//                             buffer insert, onpolicy_driver.py:154-203,236-279) for single-agent device envs
+//                             (CartPole-v1, GridWorldEnv): a CTA owns 128 envs for all T steps, ONE launch.
+//
+// CTA = 256 threads = 128 rows x 2 column halves (warps w, w+4 share rows [32(w%4), +32) = their TMEM lane quadrant).
+// Per 128-row tile: fc1 (K = d <= 8, FFMA) + activation + LayerNorm-1 in registers -> n1 as fp16 hi/lo panels ->
+// Z3 = n1 . W3f^T as 12 MMAs (3 split passes x K/16) into TMEM -> LayerNorm-3 + head in registers.  The rollout's
+// per-step critical path is one row's work (no shared-memory GEMM, no cross-row shuffles): ~1/3 of the FFMA kernel's.
+#include <algorithm>
+#include <cstdlib>
+#include <map>
+#include <mutex>
+
+#include "orl_envstep.cuh"
+#include "orl_tc16.cuh"
+
+namespace {
+using namespace orl;
+using namespace orl::tc;
+
+constexpr int F_M = 128, F_NT = 256, FCW = 32;
+constexpr uint32_t FPANEL = F_M * 16, FPANEL_W = H * 16;
+constexpr uint32_t FOFF_R1H = 0, FOFF_R1L = 8 * FPANEL, FOFF_WH = 16 * FPANEL, FOFF_WL = FOFF_WH + 8 * FPANEL_W, FOFF_SMALL = FOFF_WL + 8 * FPANEL_W;
+// fp32: w1t[8][64] b1[64] b3f[64] whf[8][64] bhf[8] | xs[2][128][2] xh[2][128][8] xst[128][8] | mbarrier, tmem holder
+constexpr uint32_t F_SMALL_FLOATS = 8 * H + H + H + MAX_OUT * H + MAX_OUT;
+constexpr uint32_t F_XCH_FLOATS = 2 * F_M * 2 + 2 * F_M * 8 + F_M * 8;
+constexpr uint32_t F_SMEM = FOFF_SMALL + 4 * (F_SMALL_FLOATS + F_XCH_FLOATS) + 16 + 16;
+
+#define F_FOR_OUT(j) _Pragma("unroll") for (int j = 0; j < NOUT; ++j) if (NOUT != 8 || j < n)
+#define F_ROWGROUP_SYNC()                                                      \
+    do {                                                                       \
+        switch (warp & 3) {                                                    \
+            case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;       \
+            case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;       \
+            case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;       \
+            default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;      \
+        }                                                                      \
+    } while (0)
+
+template <int ACT>
+__device__ __forceinline__ float f_act(float z, int activation_id) { return ACT == 1 ? fmaxf(z, 0.f) : act_fwd(z, activation_id); }
+
+struct FwdCtx {
+    uint8_t *R1h, *R1l;
+    float *w1t, *b1s, *b3f, *whf, *bhf, *xs, *xh, *xst;
+    uint64_t* bar;
+    uint32_t tmem, aR1h, aR1l, aWh, aWl;
+};
+
+// carve shared memory, stage + fold the weights (fc3 matrix as split fp16), allocate 64 TMEM columns; ends with a CTA barrier
+__device__ __forceinline__ FwdCtx fwd_setup(uint8_t* smem, const float* __restrict__ params, int d, int n) {
+    const int tid = threadIdx.x, warp = tid >> 5;
+    FwdCtx c;
+    c.R1h = smem + FOFF_R1H; c.R1l = smem + FOFF_R1L;
+    uint8_t* Wh = smem + FOFF_WH; uint8_t* Wl = smem + FOFF_WL;
+    c.w1t = reinterpret_cast<float*>(smem + FOFF_SMALL);
+    c.b1s = c.w1t + 8 * H; c.b3f = c.b1s + H; c.whf = c.b3f + H; c.bhf = c.whf + MAX_OUT * H;
+    c.xs = c.bhf + MAX_OUT; c.xh = c.xs + 2 * F_M * 2; c.xst = c.xh + 2 * F_M * 8;
+    c.bar = reinterpret_cast<uint64_t*>(c.xst + F_M * 8);
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(c.bar + 2);
+    const NetOffsets po = net_offsets(d, n);
+    for (int i = tid; i < 8 * H; i += F_NT) { const int k = i / H, j = i % H; c.w1t[i] = (k < d) ? params[po.w1 + j * d + k] : 0.f; }
+    for (int i = tid; i < H; i += F_NT) c.b1s[i] = params[po.b1 + i];
+    for (int i = tid; i < H * H / 2; i += F_NT) {
+        const int j = (2 * i) / H, k = (2 * i) % H;
+        uint32_t hi, lo;
+        split2(params[po.w3 + 2 * i] * params[po.g1 + k], params[po.w3 + 2 * i + 1] * params[po.g1 + k + 1], hi, lo);
+        const uint32_t off = (uint32_t)(k >> 3) * FPANEL_W + j * 16 + (k & 7) * 2;
+        *reinterpret_cast<uint32_t*>(Wh + off) = hi;
+        *reinterpret_cast<uint32_t*>(Wl + off) = lo;
+    }
+    for (int i = tid; i < MAX_OUT * H; i += F_NT) { const int j = i / H, k = i % H; c.whf[i] = (j < n) ? params[po.wh + j * H + k] * params[po.g3 + k] : 0.f; }
+    for (int j = tid; j < H; j += F_NT) {
+        float s = params[po.b3 + j];
+        for (int k = 0; k < H; ++k) s = fmaf(params[po.w3 + j * H + k], params[po.be1 + k], s);
+        c.b3f[j] = s;
+    }
+    for (int j = tid; j < MAX_OUT; j += F_NT) {
+        float s = 0.f;
+        if (j < n) { s = params[po.bh + j]; for (int k = 0; k < H; ++k) s = fmaf(params[po.wh + j * H + k], params[po.be3 + k], s); }
+        c.bhf[j] = s;
+    }
+    if (tid == 0) mbar_init(c.bar, 1);
+    if (warp == 0) tmem_alloc(tmem_holder, 64);
+    fence_proxy_async();
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    c.tmem = *tmem_holder;
+    c.aR1h = smem_u32(c.R1h); c.aR1l = smem_u32(c.R1l); c.aWh = smem_u32(Wh); c.aWl = smem_u32(Wl);
+    return c;
+}
+
+// One 128-row tile forward: x (this thread's row, zero padded) -> out[j] = head(j) incl. the folded bias, valid in
+// BOTH column halves of the row.  `par` = parity of the tile counter (the MMA mbarrier completes once per tile).
+template <int NOUT, int ACT>
+__device__ __forceinline__ void fwd_tile(const FwdCtx& c, const float (&x)[8], int d, int n, int activation_id, uint32_t par,
+                                         float (&out)[MAX_OUT]) {
+    const int tid = threadIdx.x, warp = tid >> 5, row = tid & 127, half = tid >> 7, cb = FCW * half;
+    float n1[FCW];
+#pragma unroll
+    for (int q4 = 0; q4 < FCW; q4 += 4) {
+        const float4 b = *reinterpret_cast<const float4*>(c.b1s + cb + q4);
+        n1[q4] = b.x; n1[q4 + 1] = b.y; n1[q4 + 2] = b.z; n1[q4 + 3] = b.w;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        if (k < d) {
+#pragma unroll
+            for (int q4 = 0; q4 < FCW; q4 += 4) {
+                const float4 wv = *reinterpret_cast<const float4*>(c.w1t + k * H + cb + q4);
+                n1[q4] = fmaf(x[k], wv.x, n1[q4]); n1[q4 + 1] = fmaf(x[k], wv.y, n1[q4 + 1]);
+                n1[q4 + 2] = fmaf(x[k], wv.z, n1[q4 + 2]); n1[q4 + 3] = fmaf(x[k], wv.w, n1[q4 + 3]);
+            }
+        }
+    }
+    float s = 0.f, sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < FCW; ++i) { n1[i] = f_act<ACT>(n1[i], activation_id); s += n1[i]; sq = fmaf(n1[i], n1[i], sq); }
+    {
+        *reinterpret_cast<float2*>(c.xs + (half * F_M + row) * 2) = make_float2(s, sq);
+        F_ROWGROUP_SYNC();
+        const float2 o = *reinterpret_cast<const float2*>(c.xs + ((half ^ 1) * F_M + row) * 2);
+        s += o.x; sq += o.y;
+    }
+    const float mu1 = s * (1.f / H);
+    const float rstd1 = 1.0f / sqrtf(fmaxf(sq * (1.f / H) - mu1 * mu1, 0.f) + LN_EPS);
+#pragma unroll
+    for (int i = 0; i < FCW; ++i) n1[i] = (n1[i] - mu1) * rstd1;
+#pragma unroll
+    for (int q8 = 0; q8 < FCW; q8 += 8) {
+        const uint32_t off = (uint32_t)((cb + q8) >> 3) * FPANEL + row * 16;
+        split_store8(c.R1h + off, c.R1l + off, n1 + q8, 1.0f);
+    }
+    fence_proxy_async();
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 0 && elect_one()) {   // Z3 = n1 . W3f^T
+        tcgen05_fence_after();
+        const uint64_t dK_A = desc_const(FPANEL, 128), dK_W = desc_const(FPANEL_W, 128);
+        const uint32_t idesc = make_idesc_f16(128, 64, false, false);
+#pragma unroll 1
+        for (int pass = 0; pass < 3; ++pass) {
+            const uint32_t aa = pass == 0 ? c.aR1l : c.aR1h, bb = pass == 1 ? c.aWl : c.aWh;
+#pragma unroll 1
+            for (int kk = 0; kk < 4; ++kk)
+                mma_f16(c.tmem, desc_at(dK_A, aa + 2 * kk * FPANEL), desc_at(dK_W, bb + 2 * kk * FPANEL_W), idesc, (pass | kk) > 0);
+        }
+        mma_commit(c.bar);
+    }
+    mbar_wait(c.bar, par);
+    tcgen05_fence_after();
+    float n3[FCW];
+    tmem_ld_row32(c.tmem + ((uint32_t)((warp & 3) * 32) << 16) + cb, n3);
+    tcgen05_fence_before();   // the next tile's MMA (after the next CTA barrier) overwrites these columns
+    float s3 = 0.f, q3 = 0.f;
+#pragma unroll
+    for (int i = 0; i < FCW; ++i) { n3[i] += c.b3f[cb + i]; s3 += n3[i]; q3 = fmaf(n3[i], n3[i], q3); }
+    {
+        __syncwarp();
+        // slot xs is free again: every partner read of exchange 1 happened before the CTA barrier above
+        *reinterpret_cast<float2*>(c.xs + (half * F_M + row) * 2) = make_float2(s3, q3);
+        F_ROWGROUP_SYNC();
+        const float2 o = *reinterpret_cast<const float2*>(c.xs + ((half ^ 1) * F_M + row) * 2);
+        s3 += o.x; q3 += o.y;
+    }
+    const float mu3 = s3 * (1.f / H);
+    const float rstd3 = 1.0f / sqrtf(fmaxf(q3 * (1.f / H) - mu3 * mu3, 0.f) + LN_EPS);
+#pragma unroll
+    for (int j = 0; j < MAX_OUT; ++j) out[j] = 0.f;
+#pragma unroll
+    for (int q4 = 0; q4 < FCW; q4 += 4) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) n3[q4 + i] = (n3[q4 + i] - mu3) * rstd3;
+        F_FOR_OUT(j) {
+            const float4 wv = *reinterpret_cast<const float4*>(c.whf + j * H + cb + q4);
+            out[j] = fmaf(n3[q4], wv.x, fmaf(n3[q4 + 1], wv.y, fmaf(n3[q4 + 2], wv.z, fmaf(n3[q4 + 3], wv.w, out[j]))));
+        }
+    }
+    {
+        F_FOR_OUT(j) c.xh[(half * F_M + row) * 8 + j] = out[j];
+        F_ROWGROUP_SYNC();
+        // both halves add the two partial dots in the SAME order (half 0 first), so they hold identical logits
+        F_FOR_OUT(j) {
+            const float p0 = c.xh[(0 * F_M + row) * 8 + j], p1 = c.xh[(1 * F_M + row) * 8 + j];
+            out[j] = (p0 + p1) + c.bhf[j];
+        }
+    }
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(F_NT, 2) critic_values_tc_kernel(const float* __restrict__ params, int d, int activation_id,
+                                                                   const float* __restrict__ obs, float* __restrict__ values,
+                                                                   long long rows) {
+    extern __shared__ __align__(1024) uint8_t smem_f[];
+    const FwdCtx c = fwd_setup(smem_f, params, d, 1);
+    const int tid = threadIdx.x, warp = tid >> 5, row = tid & 127, half = tid >> 7;
+    const long long n_tiles = (rows + F_M - 1) / F_M;
+    uint32_t it = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const long long r = tile * F_M + row;
+        float x[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] = (r < rows && k < d) ? obs[r * d + k] : 0.f;
+        float out[MAX_OUT];
+        fwd_tile<1, ACT>(c, x, d, 1, activation_id, it & 1u, out);
+        if (half == 0 && r < rows) values[r] = out[0];
+        // the exchange slots are reused by the next tile: its first write follows this row group's last read only
+        // through the barriers inside fwd_tile of the NEXT tile -> order them here
+        F_ROWGROUP_SYNC();
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(c.tmem, 64);
+}
+
+// torch.multinomial(probs, 1) for one sample == argmax(probs / q), q ~ Exp(1) (same rule as the FFMA rollout kernel)
+__device__ __forceinline__ int f_sample_categorical(const float (&pr)[MAX_OUT], int n, const float (&q)[MAX_OUT]) {
+    int act = 0;
+    float best = pr[0] / q[0];
+#pragma unroll
+    for (int j = 1; j < MAX_OUT; ++j) {
+        if (j < n) { const float v = pr[j] / q[j]; if (v > best) { best = v; act = j; } }
+    }
+    return act;
+}
+
+template <int ENV, int NOUT, int ACT>
+__global__ void __launch_bounds__(F_NT, 1) rollout_tc_kernel(const OrlRolloutArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem_f[];
+    const int N = a.n_envs, B = N, d = a.obs_dim;
+    const int n = NOUT == 8 ? a.n_actions : NOUT;
+    const FwdCtx c = fwd_setup(smem_f, a.policy_params, d, n);
+    const int tid = threadIdx.x, warp = tid >> 5, row = tid & 127, half = tid >> 7;
+    const int e = blockIdx.x * F_M + row;          // env == buffer row (single-agent envs)
+    const bool valid = e < N;
+    const uint64_t rng_base = a.rng_step_base + (a.rng_counter ? *a.rng_counter : 0ull);
+    float x[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = (valid && k < d) ? a.policy_obs[((size_t)a.t_begin * B + e) * d + k] : 0.f;
+    uint32_t it = 0;
+    for (int t = a.t_begin; t < a.t_end; ++t, ++it) {
+        float logit[MAX_OUT];
+        fwd_tile<NOUT, ACT>(c, x, d, n, a.activation_id, it & 1u, logit);
+        if (half == 0 && valid) {
+            const size_t grow = (size_t)t * B + e;
+            if (a.action_masks) {
+#pragma unroll
+                for (int j = 0; j < MAX_OUT; ++j)
+                    if (j < n && a.action_masks[grow * n + j] == 0.f) logit[j] = -6e4f;
+            }
+#pragma unroll
+            for (int j = 0; j < MAX_OUT; ++j) if (j >= n) logit[j] = 0.f;
+            float nl[MAX_OUT], pr[MAX_OUT];
+            log_softmax_n(logit, n, nl, pr);
+            int act;
+            if (a.deterministic) {
+                act = 0;
+#pragma unroll
+                for (int j = 1; j < MAX_OUT; ++j) if (j < n && pr[j] > pr[act]) act = j;
+            } else {
+                float q[MAX_OUT];
+                if (a.exp_noise) {
+#pragma unroll
+                    for (int j = 0; j < MAX_OUT; ++j) q[j] = (j < n) ? a.exp_noise[grow * n + j] : 1.f;
+                } else {
+                    const uint64_t step = rng_base + (uint64_t)t;
+                    const uint2 key = make_uint2((uint32_t)a.rng_seed, (uint32_t)(a.rng_seed >> 32));
+                    const uint4 r0 = philox4x32_10(make_uint4((uint32_t)step, (uint32_t)(step >> 32), (uint32_t)(e + a.rng_row_offset), 0u), key);
+                    const uint4 r1 = philox4x32_10(make_uint4((uint32_t)step, (uint32_t)(step >> 32), (uint32_t)(e + a.rng_row_offset), 1u), key);
+                    const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+                    for (int j = 0; j < MAX_OUT; ++j) q[j] = -logf(u32_to_unit_open(rr[j]));
+                }
+                act = f_sample_categorical(pr, n, q);
+            }
+            float lp = nl[0];
+#pragma unroll
+            for (int j = 1; j < MAX_OUT; ++j) if (j == act) lp = nl[j];
+            a.actions[grow] = (float)act;
+            a.action_log_probs[grow] = lp;
+            // ---- env.step of this thread's env, in-place insert into slot t / t+1 ----
+            EnvPtrs E{a.env_f64, a.env_u64, a.env_i32, a.env_table, a.env_table_len, a.rng_seed,
+                      a.ep_return, a.ep_length, a.episode_stats, a.rng_row_offset};
+            float ob[4], fin[4], reward; bool done;
+            env_step_single(E, ENV, e, N, act, ob, reward, done, fin);
+            const size_t o1 = (size_t)(t + 1) * B + e;
+            *reinterpret_cast<float4*>(a.policy_obs + o1 * 4) = make_float4(ob[0], ob[1], ob[2], ob[3]);
+            a.rewards[grow] = reward;
+            a.masks[o1] = done ? 0.f : 1.f;
+            a.active_masks[o1] = 1.f;   // onpolicy_driver.py:118-124 with one agent
+            *reinterpret_cast<float4*>(c.xst + row * 8) = make_float4(ob[0], ob[1], ob[2], ob[3]);
+        }
+        F_ROWGROUP_SYNC();   // publishes the next observation to the row's other half; orders the exchange slots
+        if (valid) {
+            const float4 o = *reinterpret_cast<const float4*>(c.xst + row * 8);
+            x[0] = o.x; x[1] = o.y; x[2] = o.z; x[3] = o.w;
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(c.tmem, 64);
+}
+
+template <typename K>
+int prepare_kernel(K kern) {
+    static std::mutex mu;
+    static std::map<const void*, bool> done;
+    std::lock_guard<std::mutex> lock(mu);
+    const void* key = reinterpret_cast<const void*>(kern);
+    if (!done.count(key)) {
+        int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM), "cudaFuncSetAttribute(fwd_tc)");
+        if (e) return e;
+        done[key] = true;
+    }
+    return 0;
+}
+
+}  // namespace
+
+namespace orl {
+
+bool fwd_tc_enabled() {
+    static const bool on = [] { const char* v = getenv("ORL_FWD_FFMA"); return !(v && atoi(v) != 0); }();
+    return on;
+}
+
+// ValueNetwork.forward over `rows` rows on the tensor cores; obs widths <= 8
+int launch_critic_values_tc(const float* params, int d, int activation_id, const float* obs, float* values, long long rows, cudaStream_t st) {
+    const long long n_tiles = (rows + F_M - 1) / F_M;
+    const int grid = (int)std::min<long long>(n_tiles, 2LL * sm_count());
+    if (activation_id == 1) {
+        if (int e = prepare_kernel(critic_values_tc_kernel<1>)) return e;
+        critic_values_tc_kernel<1><<<grid, F_NT, F_SMEM, st>>>(params, d, activation_id, obs, values, rows);
+    } else {
+        if (int e = prepare_kernel(critic_values_tc_kernel<-1>)) return e;
+        critic_values_tc_kernel<-1><<<grid, F_NT, F_SMEM, st>>>(params, d, activation_id, obs, values, rows);
+    }
+    return check_cuda(cudaGetLastError(), "critic_values_tc_kernel");
+}
+
+bool rollout_tc_eligible(const OrlRolloutArgs& a) {
+    return fwd_tc_enabled() && (a.env_kind == ORL_ENV_CARTPOLE || a.env_kind == ORL_ENV_GRIDWORLD) && a.n_agents == 1 && a.obs_dim == 4 &&
+           a.head_kind == ORL_HEAD_CATEGORICAL && (reinterpret_cast<uintptr_t>(a.policy_obs) & 15) == 0;
+}
+
+int launch_rollout_tc(const OrlRolloutArgs& a, cudaStream_t st) {
+    const int grid = (a.n_envs + F_M - 1) / F_M;
+#define ORL_RTC(ENVK, NO)                                                                               \
+    do {                                                                                                \
+        if (a.activation_id == 1) {                                                                     \
+            if (int e_ = prepare_kernel(rollout_tc_kernel<ENVK, NO, 1>)) return e_;                     \
+            rollout_tc_kernel<ENVK, NO, 1><<<grid, F_NT, F_SMEM, st>>>(a);                              \
+        } else {                                                                                        \
+            if (int e_ = prepare_kernel(rollout_tc_kernel<ENVK, NO, -1>)) return e_;                    \
+            rollout_tc_kernel<ENVK, NO, -1><<<grid, F_NT, F_SMEM, st>>>(a);                             \
+        }                                                                                               \
+    } while (0)
+    if (a.env_kind == ORL_ENV_CARTPOLE) ORL_RTC(ORL_ENV_CARTPOLE, 2);
+    else ORL_RTC(ORL_ENV_GRIDWORLD, 5);
+#undef ORL_RTC
+    return check_cuda(cudaGetLastError(), "rollout_tc_kernel");
+}
+
+}  // namespace orl
