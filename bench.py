@@ -192,8 +192,11 @@ def gae_roofline(flush, steps=10):
 
 
 def time_iterations(drv, steps, warmup, flush, world):
-    """W untimed + K timed device iterations (collect + update), CUDA events per iteration on the launching stream,
-    256 MB L2 flush between timed iterations, max over ranks.  Returns (seconds, phases_ms, launches, wall window)."""
+    """W untimed + K timed device iterations (collect + update) through `OnPolicyDriver.device_iteration` — one captured
+    CUDA graph replay per iteration when eligible (the product's default), else ~25 launches — CUDA events per iteration
+    on the launching stream, 256 MB L2 flush between timed iterations, max over ranks.  The per-phase times come from a
+    separate short eager pass (events cannot be read inside a graph).
+    Returns (seconds, phases_ms, launches, wall window)."""
     import torch
     import torch.distributed as dist
 
@@ -205,7 +208,6 @@ def time_iterations(drv, steps, warmup, flush, world):
     for _ in range(max(warmup, 3)):
         drv.device_iteration()
     barrier()
-    drv.phase_events = []
     l0 = drv.gpu_launches + drv.trainer.gpu_launches
     events = []
     barrier()
@@ -221,6 +223,12 @@ def time_iterations(drv, steps, warmup, flush, world):
     window = (t0, time.time())
     launches = drv.gpu_launches + drv.trainer.gpu_launches - l0
     total_s = sum(a.elapsed_time(b) for a, b in events) * 1e-3
+    # phases: eager pass
+    drv.phase_events = []
+    for _ in range(3):
+        flush.zero_()
+        drv.device_iteration()
+    barrier()
     phases = {}
     for name, a, b in drv.phase_events:
         phases.setdefault(name, []).append(a.elapsed_time(b))
@@ -272,6 +280,7 @@ def side_result(rank, world, flush, workload, steps, envs=None, extra_flags=(), 
                        + (" " + " ".join(extra_flags) if extra_flags else ""),
            "value": n * Tn * steps * world / sec, "unit": "env-steps/s", "ms_per_step": sec / steps * 1e3,
            "phases_ms": {k: round(v, 4) for k, v in phases.items()}, "gpu_launches": launches, "steps": steps,
+           "cuda_graph": getattr(drv, "_graph", None) is not None,
            "update_kernel": "tcgen05 split-fp16" if drv.trainer.use_tensor_cores else ("GRU warp kernels (fp32)" if drv.trainer.recurrent else "fp32 FFMA")}
     del drv
     if e2e:
@@ -348,6 +357,7 @@ def run_ours(args):
     env_steps = N_ENVS * T * args.steps * world
     value = env_steps / total_s
     tc_update = drv.trainer.use_tensor_cores
+    graphed = getattr(drv, "_graph", None) is not None
     del drv
 
     e2e_s, h2d, d2h = time_e2e(rank, world, args.steps, "c2")
@@ -405,7 +415,9 @@ def run_ours(args):
                    "sampling": "device Philox4x32 action sampling, whole-buffer minibatch without a permutation (chi-square / moment "
                                "tested, tests/test_sampling_cuda.py); the reference-order CPU-noise mode is extras.c2_parity_mode"},
         "gpu_launches": launches,
-        "phases_ms": phases,
+        "launch_mode": ("one CUDA graph replay per iteration (the captured graph holds the kernel launches counted in gpu_launches)"
+                        if graphed else "eager launches"),
+        "phases_ms": phases, "phases_note": "per-phase CUDA-event times from a separate eager (non-graph) pass of 3 iterations",
         "e2e": {"value": env_steps / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "PPOAgent.train(total_time_steps) incl. per-iteration logging reads; the env is device-resident (north_star), "
                        "so a step has no host inputs"},

@@ -184,6 +184,15 @@ int orl_rollout(const OrlRolloutArgs* args, void* stream);
 int orl_critic_values(const float* critic_params, int obs_dim, int activation_id,
                       const float* obs, float* values, long long rows, void* stream);
 
+/* ---- policy evaluation of given actions over a flat batch of rows ------------------------
+ * Replaces PolicyNetwork.eval_actions (policy_network.py:164-203) -> ACTLayer.evaluate_actions (act.py:130-172), the
+ * policy half of PPOModule.evaluate_actions (ppo_module.py:147-193), outside the fused update: obs (rows, d), actions
+ * (rows) [Categorical: index as float32] or (rows, n) [DiagGaussian] -> log_probs and entropy with the shape of
+ * `actions` (per row / per dimension; the caller takes the active-mask mean, act.py:160-168). */
+int orl_policy_eval(const float* policy_params, int obs_dim, int n_actions, int activation_id, int head_kind,
+                    const float* obs, const float* actions, const float* action_masks, float* log_probs,
+                    float* entropy, long long rows, void* stream);
+
 
 /* ---- PPO minibatch update ---------------------------------------------------------------
  * Replaces PPOAlgorithm.ppo_update (openrl/algorithms/ppo.py:46-176): prepare_loss :238-361

@@ -226,15 +226,21 @@ class PPOAlgorithm:
         keys = ["value_loss", "critic_grad_norm", "policy_loss", "dist_entropy", "actor_grad_norm", "ratio"]
         return {k: float(v) for k, v in zip(keys, info)}
 
-    def train_async(self, buffer):
-        """All launches of one training phase, no host read-back."""
-        buf = buffer
+    def sync_lrs(self):
+        """Learning rates live in a device buffer (the kernels read them there, so a captured graph can be replayed while
+        a schedule changes them): one 8-byte H2D copy, only when the host values changed."""
         m = self.algo_module
         lrs = (m.optimizers["policy"].param_groups[0]["lr"], m.optimizers["critic"].param_groups[0]["lr"])
-        if lrs != self._lrs_host:  # H2D only when the schedule changed them
+        if lrs != self._lrs_host:
             self.lrs.copy_(torch.tensor(lrs, dtype=torch.float32), non_blocking=True)
             self._lrs_host = lrs
             self.h2d_bytes += 8
+
+    def train_async(self, buffer):
+        """All launches of one training phase, no host read-back."""
+        buf = buffer
+        if not torch.cuda.is_current_stream_capturing():
+            self.sync_lrs()
         self.train_info.zero_()
         if not getattr(buf, "returns_ready", True):
             # train() on a buffer whose returns were never computed (the reference's algorithm tests call it on a fresh

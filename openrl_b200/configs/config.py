@@ -57,6 +57,9 @@ FLAGS = [
     # fp32-class accuracy, so it is also the parity-mode update); Categorical heads, obs widths <= 8,
     # fp32 FFMA kernel otherwise.  `use_tf32` is the round-1 name of the same switch.
     ("use_tensor_cores", _bool, True),
+    # replay one captured CUDA graph per iteration (rollout + critic + GAE + all updates + slot shift) instead of ~25
+    # launches; used when no callback needs rollout hooks, outside parity_mode, on device-resident envs
+    ("use_cuda_graph", _bool, True),
     ("use_tf32", _bool, True),
 ]
 

@@ -219,17 +219,6 @@ __global__ void __launch_bounds__(F_NT, 2) critic_values_tc_kernel(const float* 
     if (warp == 0) tmem_dealloc(c.tmem, 64);
 }
 
-// torch.multinomial(probs, 1) for one sample == argmax(probs / q), q ~ Exp(1) (same rule as the FFMA rollout kernel)
-__device__ __forceinline__ int f_sample_categorical(const float (&pr)[MAX_OUT], int n, const float (&q)[MAX_OUT]) {
-    int act = 0;
-    float best = pr[0] / q[0];
-#pragma unroll
-    for (int j = 1; j < MAX_OUT; ++j) {
-        if (j < n) { const float v = pr[j] / q[j]; if (v > best) { best = v; act = j; } }
-    }
-    return act;
-}
-
 template <int ENV, int NOUT, int ACT>
 __global__ void __launch_bounds__(F_NT, 1) rollout_tc_kernel(const OrlRolloutArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_f[];
@@ -277,7 +266,7 @@ __global__ void __launch_bounds__(F_NT, 1) rollout_tc_kernel(const OrlRolloutArg
 #pragma unroll
                     for (int j = 0; j < MAX_OUT; ++j) q[j] = -logf(u32_to_unit_open(rr[j]));
                 }
-                act = f_sample_categorical(pr, n, q);
+                act = sample_categorical(pr, n, q);   // argmax(probs / q): torch.multinomial's rule, as in the FFMA kernel
             }
             float lp = nl[0];
 #pragma unroll

@@ -287,7 +287,74 @@ __global__ void __launch_bounds__(C_NT) critic_values_kernel(const float* __rest
     }
 }
 
+// ---- PolicyNetwork.eval_actions over a flat batch (policy_network.py:164-203, act.py:160-168 / 150-158) ----------------
+// log-prob of the given action and the entropy of the action distribution per row (the caller takes the masked mean).
+__global__ void __launch_bounds__(C_NT) policy_eval_kernel(const float* __restrict__ params, int d, int n, int activation_id, int head_kind,
+                                                           const float* __restrict__ obs, const float* __restrict__ actions,
+                                                           const float* __restrict__ action_masks, float* __restrict__ logp_out,
+                                                           float* __restrict__ entropy_out, long long rows) {
+    extern __shared__ __align__(16) float smem[];
+    const int ldx = pad4(d) + 4;
+    float* p = smem;
+    SmemWeights w = carve_weights(p, d, false);
+    float* Xs = p;  p += C_M * ldx;
+    float* N1s = p; p += C_M * LDA;
+    float* N3s = p; p += C_M * LDA;
+    const int tid = threadIdx.x;
+    load_weights_folded<C_NT>(w, params, d, n, false);
+    const bool gaussian = head_kind == ORL_HEAD_GAUSSIAN;
+    const float* logstd = params + net_offsets(d, n, 1).ls;
+    const long long n_tiles = (rows + C_M - 1) / C_M;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long r0 = tile * C_M;
+        const int rows_here = (int)min((long long)C_M, rows - r0);
+        for (int i = tid; i < C_M * ldx; i += C_NT) {
+            const int r = i / ldx, k = i % ldx;
+            Xs[i] = (r < rows_here && k < d) ? obs[(r0 + r) * d + k] : 0.f;
+        }
+        __syncthreads();
+        float mu1[C_M / (C_NT / 16)], rstd1[C_M / (C_NT / 16)], rstd3[C_M / (C_NT / 16)];
+        unsigned pm;
+        trunk_forward<C_M, C_NT, false>(w, Xs, ldx, d, activation_id, N1s, N3s, mu1, rstd1, rstd3, pm);
+        __syncthreads();
+        float out[MAX_OUT];
+        head_dots<C_M, C_NT>(w, N3s, n, out);
+        constexpr int PPR = C_NT / C_M;
+        if (tid % PPR == 0 && tid / PPR < rows_here) {
+            const long long g = r0 + tid / PPR;
+            if (gaussian) {   // per-dimension log-probs and entropies (distributions.py:34-47)
+                for (int j = 0; j < n; ++j) {
+                    const float ls = logstd[j], std = expf(ls), diff = actions[g * n + j] - out[j];
+                    logp_out[g * n + j] = -(diff * diff) / (2.0f * (std * std)) - ls - 0.9189385332046727f;
+                    entropy_out[g * n + j] = 1.4189385332046727f + ls;
+                }
+            } else {
+                if (action_masks) {
+#pragma unroll
+                    for (int j = 0; j < MAX_OUT; ++j) if (j < n && action_masks[g * n + j] == 0.f) out[j] = -6e4f;
+                }
+                float nl[MAX_OUT], pr[MAX_OUT];
+                log_softmax_n(out, n, nl, pr);
+                const int act = (int)actions[g];
+                float lp = nl[0], ent = 0.f;
+#pragma unroll
+                for (int j = 0; j < MAX_OUT; ++j) if (j < n) { if (j == act) lp = nl[j]; ent -= pr[j] * nl[j]; }
+                logp_out[g] = lp;
+                entropy_out[g] = ent;
+            }
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace
+
+namespace orl {
+bool fwd_tc_enabled();
+bool rollout_tc_eligible(const OrlRolloutArgs& a);
+int launch_rollout_tc(const OrlRolloutArgs& a, cudaStream_t st);
+int launch_critic_values_tc(const float* params, int d, int activation_id, const float* obs, float* values, long long rows, cudaStream_t st);
+}  // namespace orl
 
 extern "C" int orl_env_reset(int env_kind, int n_envs, int n_agents, double* env_f64, uint64_t* env_u64,
                              int32_t* env_i32, const int32_t* env_table, int env_table_len, uint64_t rng_seed,
@@ -361,6 +428,14 @@ extern "C" int orl_rollout(const OrlRolloutArgs* args, void* stream) {
         orl::set_last_error("orl_rollout: unsupported env_kind %d", a.env_kind);
         return ORL_ERR_UNSUPPORTED;
     }
+    if (orl::rollout_tc_eligible(a)) {   // single-agent device envs: the tensor-core rollout (orl_fwd_tc.cu), one CTA per 128 envs
+        if (int e = orl::launch_rollout_tc(a, reinterpret_cast<cudaStream_t>(stream))) return e;
+        if (a.rng_counter) {
+            bump_counter_kernel<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a.rng_counter, (uint64_t)(a.t_end - a.t_begin));
+            ORL_LAUNCH_CHECK("bump_counter_kernel");
+        }
+        return 0;
+    }
     // rows per CTA: the step chain is latency-bound, so prefer many small CTAs (>= ~4 per SM) and
     // only grow the tile when there are enough rows to keep that many CTAs anyway
     const long long B = (long long)a.n_envs * a.n_agents;
@@ -410,6 +485,8 @@ extern "C" int orl_critic_values(const float* critic_params, int obs_dim, int ac
     ORL_CHECK_ARG(obs_dim > 0 && obs_dim <= 64, "obs_dim must be in 1..64");
     ORL_CHECK_ARG(rows > 0, "rows");
     ORL_CHECK_ARG(activation_id >= 0 && activation_id <= 3, "activation_id");
+    if (orl::fwd_tc_enabled() && obs_dim <= 8)   // tensor-core forward (orl_fwd_tc.cu)
+        return orl::launch_critic_values_tc(critic_params, obs_dim, activation_id, obs, values, rows, reinterpret_cast<cudaStream_t>(stream));
     const int ldx = orl::pad4(obs_dim) + 4;
     const size_t smem = sizeof(float) * (orl::smem_weights_floats(obs_dim, false) + C_M * ldx + 2 * C_M * orl::LDA);
     static bool attr_set = false;
@@ -424,5 +501,29 @@ extern "C" int orl_critic_values(const float* critic_params, int obs_dim, int ac
     critic_values_kernel<<<grid, C_NT, smem, reinterpret_cast<cudaStream_t>(stream)>>>(critic_params, obs_dim, activation_id,
                                                                                       obs, values, rows);
     ORL_LAUNCH_CHECK("critic_values_kernel");
+    return 0;
+}
+
+extern "C" int orl_policy_eval(const float* policy_params, int obs_dim, int n_actions, int activation_id, int head_kind,
+                               const float* obs, const float* actions, const float* action_masks, float* log_probs,
+                               float* entropy, long long rows, void* stream) {
+    ORL_CHECK_ARG(policy_params && obs && actions && log_probs && entropy, "null buffer");
+    ORL_CHECK_ARG(obs_dim > 0 && obs_dim <= 64 && n_actions > 0 && n_actions <= orl::MAX_OUT, "shapes");
+    ORL_CHECK_ARG(rows > 0 && activation_id >= 0 && activation_id <= 3, "rows / activation_id");
+    ORL_CHECK_ARG(head_kind == ORL_HEAD_CATEGORICAL || head_kind == ORL_HEAD_GAUSSIAN, "head_kind");
+    const int ldx = orl::pad4(obs_dim) + 4;
+    const size_t smem = sizeof(float) * (orl::smem_weights_floats(obs_dim, false) + C_M * ldx + 2 * C_M * orl::LDA);
+    static bool attr_set = false;
+    if (!attr_set) {
+        int e = orl::check_cuda(cudaFuncSetAttribute(policy_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
+                                "cudaFuncSetAttribute(policy_eval)");
+        if (e) return e;
+        attr_set = true;
+    }
+    const long long n_tiles = (rows + C_M - 1) / C_M;
+    const int grid = (int)std::min<long long>(n_tiles, 2LL * orl::sm_count());
+    policy_eval_kernel<<<grid, C_NT, smem, reinterpret_cast<cudaStream_t>(stream)>>>(policy_params, obs_dim, n_actions, activation_id, head_kind,
+                                                                                    obs, actions, action_masks, log_probs, entropy, rows);
+    ORL_LAUNCH_CHECK("policy_eval_kernel");
     return 0;
 }

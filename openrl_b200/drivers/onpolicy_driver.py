@@ -66,7 +66,80 @@ class OnPolicyDriver:
         d.masks[0].fill_(1.0)
         d.active_masks[0].fill_(1.0)
 
+    # -- one captured CUDA graph per iteration -------------------------------------------------
+    def _graph_ok(self):
+        return (bool(getattr(self.cfg, "use_cuda_graph", True)) and not self.cfg.parity_mode and self.callback is None
+                and self.envs.kind != lib.ENV_NONE and self.phase_events is None and hasattr(self.envs, "statistics_device"))
+
+    def _iteration_body(self):
+        """Everything an iteration launches, in order, with no host read-back (capturable)."""
+        self._launch_steps(0, self.episode_length, None)
+        self.compute_returns()
+        self.trainer.train_async(self.buffer.data)
+        A = self.envs.agent_num
+        self._stats_dev[:6].copy_(self.trainer.train_info.double() / float(self.trainer.ppo_epoch * self.trainer.num_mini_batch))
+        self.envs.statistics_device(self.buffer, self._stats_dev[6:6 + A + 4])
+        self.buffer.after_update()
+
+    def graph_iteration(self):
+        """Replay (or, the first times, warm up / capture) the iteration graph.  The first two iterations run eagerly on a
+        side stream (they are real training iterations), the third is captured and every iteration from then on is one
+        graph launch."""
+        if getattr(self, "_graph", None) is None:
+            A = self.envs.agent_num
+            if getattr(self, "_stats_dev", None) is None:
+                self._stats_dev = torch.zeros(6 + A + 4, dtype=torch.float64, device=self.device)
+                self._stats_host = torch.zeros(6 + A + 4, dtype=torch.float64, pin_memory=True)
+                self._graph_warm = 0
+            self.trainer.sync_lrs()
+            if self._graph_warm < 2:
+                s = torch.cuda.Stream(device=self.device)
+                s.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s):
+                    self._iteration_body()
+                torch.cuda.current_stream().wait_stream(s)
+                self._graph_warm += 1
+                return
+            l0 = self.gpu_launches + self.trainer.gpu_launches
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._iteration_body()
+            self._graph_launches = self.gpu_launches + self.trainer.gpu_launches - l0
+            self.gpu_launches -= self._graph_launches     # capture launched nothing
+            self._graph = g
+        self.trainer.sync_lrs()
+        self._graph.replay()
+        self.gpu_launches += self._graph_launches
+
+    def _read_graph_stats(self):
+        self._stats_host.copy_(self._stats_dev, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        self.d2h_bytes += self._stats_host.numel() * 8
+        return self._stats_host.numpy().copy()
+
+    def _inner_loop_graph(self):
+        if self.use_linear_lr_decay:
+            self.trainer.algo_module.lr_decay(self.episode, self.episodes)
+        self.graph_iteration()
+        T, N = self.episode_length, self.envs.parallel_env_num
+        self.agent.num_time_steps += N * T
+        self.total_num_steps = (self.episode + 1) * T * self.n_rollout_threads
+        if self.episode % self.log_interval == 0 and self.logger is not None:
+            vals = self._read_graph_stats()        # the only device -> host read of the iteration
+            keys = ["value_loss", "critic_grad_norm", "policy_loss", "dist_entropy", "actor_grad_norm", "ratio"]
+            train_infos = {k: float(v) for k, v in zip(keys, vals[:6])}
+            if type(self.trainer).__name__ == "A2CAlgorithm":
+                train_infos.pop("ratio", None)
+            rollout_infos = self.envs.statistics_host(vals[6:], T * N) if self.envs.use_monitor else {}
+            self.logger.log_info(rollout_infos, step=self.total_num_steps)
+            self.logger.log_info(train_infos, step=self.total_num_steps)
+        elif self.envs.use_monitor:
+            self.envs._total_step += T * N
+        return True
+
     def _inner_loop(self):
+        if self._graph_ok():
+            return self._inner_loop_graph()
         rollout_infos, cont = self.actor_rollout()
         if not cont:
             return False
@@ -89,6 +162,10 @@ class OnPolicyDriver:
     def device_iteration(self):
         """One collect + update iteration as pure device work (no host read-back, no logging):
         what bench.py times as `value`."""
+        if self._graph_ok():
+            self.graph_iteration()
+            self.agent.num_time_steps += self.envs.parallel_env_num * self.episode_length
+            return
         self._rollout_launch()
         self.compute_returns()
         with self._phase("update"):

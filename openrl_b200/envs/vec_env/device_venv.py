@@ -149,6 +149,27 @@ class DeviceVecEnv:
     def batch_rewards(self, buffer):
         return {}
 
+    def statistics_device(self, buffer, out):
+        """Device half of `statistics` (graph-capturable): out[:A] = per-agent rollout reward, out[A:A+4] = episode_stats
+        (then zeroed).  `statistics_host` turns the copied-back vector into the reference's info dict."""
+        rewards = buffer.data.rewards
+        A = self.agent_num
+        out[:A].copy_(rewards.mean(dim=1).sum(dim=0).reshape(-1).to(out.dtype))
+        out[A:A + 4].copy_(self.episode_stats)
+        self.episode_stats.zero_()
+
+    def statistics_host(self, vals, steps):
+        A = self.agent_num
+        self._total_step += steps
+        info = {f"agent_{i}/rollout_episode_reward": float(v) for i, v in enumerate(vals[:A])}
+        info["FPS"] = int(self._total_step / max(time.time() - self._start_time, 1e-9))
+        info["rollout_episode_reward"] = float(np.mean(vals[:A]))
+        st = vals[A:A + 4]
+        if st[2] > 0:
+            info["episode_return_mean"] = float(st[0] / st[2])
+            info["episode_length_mean"] = float(st[1] / st[2])
+        return info
+
     def statistics(self, buffer):
         rewards = buffer.data.rewards  # (T, N, A, 1) device
         T, N = rewards.shape[0], rewards.shape[1]

@@ -125,6 +125,23 @@ class ValueNorm(nn.Module):
     def debiasing_term(self):
         return self.state[2]
 
+    # checkpoints carry the reference's three entries (valuenorm.py:27-35: running_mean (1,), running_mean_sq (1,),
+    # debiasing_term ()), so a critic state_dict saved by either implementation loads into the other
+    def _save_to_state_dict(self, destination, prefix, keep_vars):
+        destination[prefix + "running_mean"] = self.state[0:1].detach().clone()
+        destination[prefix + "running_mean_sq"] = self.state[1:2].detach().clone()
+        destination[prefix + "debiasing_term"] = self.state[2].detach().clone()
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        if prefix + "state" in state_dict:                       # round-1 checkpoints
+            self.state.copy_(state_dict[prefix + "state"].to(self.state.device).reshape(3))
+            return
+        for i, name in enumerate(("running_mean", "running_mean_sq", "debiasing_term")):
+            if prefix + name in state_dict:
+                self.state[i] = state_dict[prefix + name].to(self.state.device).reshape(-1)[0]
+            elif strict:
+                missing_keys.append(prefix + name)
+
     def running_mean_var(self):
         d = self.state[2].clamp(min=1e-5)
         m = self.state[0] / d

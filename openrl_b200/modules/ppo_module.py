@@ -57,6 +57,17 @@ class PPOModule:
         self._act_calls = 0   # Philox step of the next stochastic act() call
         self._lib = lib.load()
 
+    # `torch.save(module)` / `torch.load` (the reference's checkpoint format, rl_agent.py:187-213): everything is
+    # picklable except the ctypes library handle
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        st.pop("_lib", None)
+        return st
+
+    def __setstate__(self, st):
+        self.__dict__.update(st)
+        self._lib = lib.load()
+
     # -- reference surface -----------------------------------------------------------------
     def lr_decay(self, episode, episodes):
         """update_linear_schedule (openrl/modules/utils/util.py:13-17)."""
@@ -77,6 +88,42 @@ class PPOModule:
         lib.check(self._lib.orl_critic_values(lib.ptr(cri.flat_params), cri.obs_dim, cri.activation_id, lib.ptr(obs),
                                               lib.ptr(out), rows, lib.current_stream()), "orl_critic_values")
         return out
+
+    def get_actions(self, critic_obs, obs, rnn_states_actor=None, rnn_states_critic=None, masks=None, action_masks=None,
+                    deterministic=False):
+        """ppo_module.py:102-138: (values, actions, action_log_probs, rnn_states_actor, rnn_states_critic) for a batch of
+        rows — the policy "original" forward plus the critic forward (feed-forward nets: rnn states pass through)."""
+        if getattr(self.models["policy"], "recurrent", False):
+            raise NotImplementedError("get_actions for recurrent nets: the recurrent critic runs inside OnPolicyDriver (orl_rnn_critic)")
+        actions, logp = self.act(obs, rnn_states_actor, masks, action_masks, deterministic)
+        values = self.get_values(critic_obs, rnn_states_critic, masks)
+        return values, actions, logp, rnn_states_actor, rnn_states_critic
+
+    def evaluate_actions(self, critic_obs, obs, rnn_states_actor, rnn_states_critic, action, masks, action_masks=None,
+                         active_masks=None, critic_masks_batch=None):
+        """ppo_module.py:147-193: (values, action_log_probs, dist_entropy, policy_values=None) of given actions; the entropy
+        is the active-mask mean when cfg.use_policy_active_masks (act.py:160-168), else the plain mean."""
+        pol = self.models["policy"]
+        if getattr(pol, "recurrent", False):
+            raise NotImplementedError("evaluate_actions for recurrent nets runs inside the chunked update (orl_rnn_fwdbwd)")
+        o = torch.as_tensor(obs, dtype=torch.float32).to(self.device).contiguous().view(-1, pol.obs_dim)
+        rows = o.shape[0]
+        gauss = pol.head_kind == lib.HEAD_GAUSSIAN
+        w = pol.n_actions if gauss else 1
+        act = torch.as_tensor(action, dtype=torch.float32).to(self.device).contiguous().view(rows, w)
+        am = None if (action_masks is None or gauss) else torch.as_tensor(action_masks, dtype=torch.float32).to(self.device).contiguous()
+        logp = torch.empty(rows, w, dtype=torch.float32, device=self.device)
+        ent = torch.empty(rows, w, dtype=torch.float32, device=self.device)
+        lib.check(self._lib.orl_policy_eval(lib.ptr(pol.flat_params), pol.obs_dim, pol.n_actions, pol.activation_id, pol.head_kind,
+                                            lib.ptr(o), lib.ptr(act), lib.ptr(am), lib.ptr(logp), lib.ptr(ent), rows,
+                                            lib.current_stream()), "orl_policy_eval")
+        if active_masks is not None and getattr(self.cfg, "use_policy_active_masks", True):
+            m = torch.as_tensor(active_masks, dtype=torch.float32).to(self.device).view(rows, 1)
+            dist_entropy = (ent * m).sum() / m.sum() if not gauss else (ent * m).sum() / m.sum()
+        else:
+            dist_entropy = ent.mean()
+        values = self.get_values(critic_obs, rnn_states_critic, critic_masks_batch if critic_masks_batch is not None else masks)
+        return values, logp, dist_entropy, None
 
     def act(self, obs, rnn_states_actor=None, masks=None, action_masks=None, deterministic=False, exp_noise=None,
             rng_seed=None, rng_step=None):

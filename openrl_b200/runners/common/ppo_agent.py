@@ -126,25 +126,33 @@ class PPOAgent:
         self.agent_num = env.agent_num
 
     def save(self, path):
-        """rl_agent.py:187-191: torch.save(self.net.module, path/"module.pt")."""
+        """rl_agent.py:187-191: `torch.save(self.net.module, path / "module.pt")` — the pickled module (models with the
+        reference's state_dict names, optimiser state, Adam step counters)."""
         path = pathlib.Path(path)
         path.mkdir(parents=True, exist_ok=True)
-        m = self.net.module
-        state = {
-            "models": {k: v.state_dict() for k, v in m.models.items()},
-            "optimizers": {k: v.state_dict() for k, v in m.optimizers.items()},
-            "adam_steps": m.adam_steps.clone(),
-        }
-        torch.save(state, path / "module.pt")
+        torch.save(self.net.module, path / "module.pt")
 
     def load(self, path):
+        """rl_agent.py:193-213.  Accepts (i) a module pickled by `save`, (ii) a round-1 checkpoint (dict of
+        state_dicts), (iii) any pickled object with `.models[k].state_dict()` under the reference's key names (a
+        reference `PPOModule`, when its package is importable): (ii) and (iii) are copied into the live module."""
         path = pathlib.Path(path)
         f = path / "module.pt" if path.is_dir() else path
-        state = torch.load(f, map_location=self.net.device, weights_only=False)
+        assert f.exists(), f"{f} does not exist"
+        obj = torch.load(f, map_location=self.net.device, weights_only=False)
         m = self.net.module
-        for k, sd in state["models"].items():
-            m.models[k].load_state_dict(sd)
-        for k, sd in state["optimizers"].items():
-            m.optimizers[k].load_state_dict(sd)
-        m.adam_steps.copy_(state["adam_steps"])
+        if isinstance(obj, type(m)):
+            self.net.module = obj
+        elif isinstance(obj, dict) and "models" in obj:
+            for k, sd in obj["models"].items():
+                m.models[k].load_state_dict(sd)
+            for k, sd in obj.get("optimizers", {}).items():
+                m.optimizers[k].load_state_dict(sd)
+            if "adam_steps" in obj:
+                m.adam_steps.copy_(obj["adam_steps"])
+        elif hasattr(obj, "models"):
+            for k, model in obj.models.items():
+                m.models[k].load_state_dict({kk: vv.to(self.net.device) for kk, vv in model.state_dict().items()}, strict=False)
+        else:
+            raise TypeError(f"{f}: unrecognised checkpoint object {type(obj).__name__}")
         self.net.reset()

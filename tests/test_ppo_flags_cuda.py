@@ -215,3 +215,41 @@ def test_tensor_core_kernel_head_width_templates(cuda, n_actions):
     for net_i in range(2):
         g32, gtc = res[0][1][net_i], res[1][1][net_i]
         assert np.linalg.norm(gtc - g32) <= 1e-4 * np.linalg.norm(g32), (n_actions, net_i)
+
+
+def test_checkpoint_is_pickled_module_with_reference_key_names(cuda, tmp_path):
+    """module.pt == torch.save(net.module) (rl_agent.py:187-191); the critic's state_dict carries the reference's ValueNorm
+    entries (valuenorm.py:27-35) and loads from a dict spelled with them."""
+    import torch
+
+    from openrl_b200.configs.config import create_config_parser
+    from openrl_b200.envs.common import make
+    from openrl_b200.modules.common import PPONet
+    from openrl_b200.modules.ppo_module import PPOModule
+    from openrl_b200.runners.common import PPOAgent
+
+    cfg = create_config_parser().parse_args(["--episode_length", "16", "--ppo_epoch", "1"])
+    cfg.quiet = True
+    agent = PPOAgent(PPONet(make("CartPole-v1", env_num=8), cfg=cfg, device="cuda:0"))
+    agent.train(total_time_steps=16 * 8 * 2)
+    agent.save(tmp_path / "ck")
+    obj = torch.load(tmp_path / "ck" / "module.pt", weights_only=False)
+    assert isinstance(obj, PPOModule) and set(obj.models) == {"policy", "critic"}
+    sd = agent.net.module.models["critic"].state_dict()
+    for k in ("value_normalizer.running_mean", "value_normalizer.running_mean_sq", "value_normalizer.debiasing_term"):
+        assert k in sd
+    assert sd["value_normalizer.running_mean"].shape == (1,) and sd["value_normalizer.debiasing_term"].shape == ()
+    assert float(sd["value_normalizer.debiasing_term"]) > 0
+    # a reference-spelled critic state_dict loads
+    sd2 = {k: v.clone() for k, v in sd.items()}
+    sd2["value_normalizer.running_mean"] += 1.0
+    agent.net.module.models["critic"].load_state_dict(sd2)
+    assert abs(float(agent.net.module.get_critic_value_normalizer().state[0]) - float(sd2["value_normalizer.running_mean"])) < 1e-7
+    # the loaded module keeps training (library handle restored, flat parameter views intact)
+    agent2 = PPOAgent(PPONet(make("CartPole-v1", env_num=8), cfg=cfg, device="cuda:0"))
+    agent2.load(tmp_path / "ck")
+    p0 = agent2.net.module.models["policy"].flat_params.clone()
+    agent2.train(total_time_steps=16 * 8)
+    assert not torch.equal(p0, agent2.net.module.models["policy"].flat_params)
+    for k, v in agent2.net.module.models["policy"].state_dict().items():   # named parameters still alias the flat buffer
+        assert v.data_ptr() >= agent2.net.module.models["policy"].flat_params.data_ptr()

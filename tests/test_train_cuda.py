@@ -225,3 +225,37 @@ def test_train_matches_reference_flag_variants(cuda, tag):
     b = agent.driver.buffer.data
     assert np.array_equal(b.actions.cpu().numpy(), d[f"it{iters - 1}/actions"])
     np.testing.assert_allclose(b.returns.cpu().numpy()[:-1], d[f"it{iters - 1}/returns"][:-1], rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("env_id,extra", [("CartPole-v1", []), ("GridWorldEnv", ["--num_mini_batch", "2"])])
+def test_cuda_graph_iterations_equal_eager_iterations(cuda, env_id, extra):
+    """cfg.use_cuda_graph replays ONE captured graph per iteration (rollout + critic + GAE + updates + slot shift):
+    same launches, same device RNG counters -> bit-identical parameters, buffers and logged metrics."""
+    import torch
+
+    from openrl_b200.configs.config import create_config_parser
+    from openrl_b200.envs.common import make
+    from openrl_b200.modules.common import PPONet
+    from openrl_b200.runners.common import PPOAgent
+    from openrl_b200.utils.logger import Logger
+
+    out = []
+    for graph in ("true", "false"):
+        cfg = create_config_parser().parse_args(["--seed", "2", "--episode_length", "24", "--ppo_epoch", "2", "--log_interval", "1",
+                                                 "--use_cuda_graph", graph, "--use_linear_lr_decay", "true"] + extra)
+        cfg.quiet = True
+        env = make(env_id, env_num=40)
+        agent = PPOAgent(PPONet(env, cfg=cfg, device="cuda:0"))
+        logger = Logger(quiet=True)
+        agent.train(total_time_steps=24 * 40 * 6, logger=logger)
+        assert (getattr(agent.driver, "_graph", None) is not None) == (graph == "true")
+        m = agent.net.module
+        logs = [h[1] for h in logger.history if "value_loss" in h[1]]
+        out.append((torch.cat([m.models[k].flat_params for k in ("policy", "critic")]).cpu(), agent.driver.buffer.data.actions.cpu(),
+                    logs, agent.num_time_steps))
+    assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1])
+    assert out[0][3] == out[1][3] == 24 * 40 * 6
+    assert len(out[0][2]) == len(out[1][2]) == 6
+    for a, b in zip(out[0][2], out[1][2]):
+        for k in a:
+            np.testing.assert_allclose(a[k], b[k], rtol=1e-6, atol=1e-9, err_msg=k)
