@@ -55,7 +55,9 @@ class PPOAlgorithm:
             self.flags |= lib.PPO_TENSORCORE
         if getattr(cfg, "dual_clip_ppo", False):
             self.flags |= lib.PPO_DUAL_CLIP
-        for name in ("use_joint_action_loss", "use_policy_vhead", "use_share_model", "use_popart",
+        assert not (getattr(cfg, "use_popart", False) and cfg.use_valuenorm), \
+            "self._use_popart and self._use_valuenorm can not be set True simultaneously"   # ppo.py:40-44
+        for name in ("use_joint_action_loss", "use_policy_vhead", "use_share_model",
                      "use_amp", "use_deepspeed", "use_naive_recurrent_policy"):
             if getattr(cfg, name, False):
                 raise NotImplementedError(f"cfg.{name} is not built into the CUDA update yet (SURVEY.md §8f)")

@@ -26,7 +26,7 @@ using namespace orl::tc;
 constexpr int F_M = 128, F_NT = 256, FCW = 32;
 constexpr uint32_t FPANEL = F_M * 16, FPANEL_W = H * 16;
 constexpr uint32_t FOFF_R1H = 0, FOFF_R1L = 8 * FPANEL, FOFF_WH = 16 * FPANEL, FOFF_WL = FOFF_WH + 8 * FPANEL_W, FOFF_SMALL = FOFF_WL + 8 * FPANEL_W;
-// fp32: w1t[8][64] b1[64] b3f[64] whf[8][64] bhf[8] | xs[2][128][2] xh[2][128][8] xst[128][8] | mbarrier, tmem holder
+// fp32: w1t[8][64] b1[64] b3f[64] whf[8][64] bhf[8] | xs[2][128][2] xh[8][2][128] xst[128][8] | mbarrier, tmem holder
 constexpr uint32_t F_SMALL_FLOATS = 8 * H + H + H + MAX_OUT * H + MAX_OUT;
 constexpr uint32_t F_XCH_FLOATS = 2 * F_M * 2 + 2 * F_M * 8 + F_M * 8;
 constexpr uint32_t F_SMEM = FOFF_SMALL + 4 * (F_SMALL_FLOATS + F_XCH_FLOATS) + 16 + 16;
@@ -183,11 +183,11 @@ __device__ __forceinline__ void fwd_tile(const FwdCtx& c, const float (&x)[8], i
         }
     }
     {
-        F_FOR_OUT(j) c.xh[(half * F_M + row) * 8 + j] = out[j];
+        F_FOR_OUT(j) c.xh[(j * 2 + half) * F_M + row] = out[j];   // [j][half][row]: conflict-free
         F_ROWGROUP_SYNC();
         // both halves add the two partial dots in the SAME order (half 0 first), so they hold identical logits
         F_FOR_OUT(j) {
-            const float p0 = c.xh[(0 * F_M + row) * 8 + j], p1 = c.xh[(1 * F_M + row) * 8 + j];
+            const float p0 = c.xh[(j * 2 + 0) * F_M + row], p1 = c.xh[(j * 2 + 1) * F_M + row];
             out[j] = (p0 + p1) + c.bhf[j];
         }
     }

@@ -86,7 +86,7 @@ struct AdvNormTc { float m0, s0, m1, s1; bool two; };
 
 __host__ __device__ inline uint32_t tc_stage_bytes(int d) { return (uint32_t)((T_M * d * 4 + 127) & ~127) + N_SCAL * T_M * 4; }
 __host__ __device__ inline uint32_t tc_small_off(int d) { return OFF_STAGE + tc_stage_bytes(d); }
-// fp32 weights: w1t[8][64] b1[64] b3f[64] whf[8][64] bhf[8] swh[8]; exchange: xs[2][128][2] xh[2][128][8]; 5 mbarriers + tmem holder
+// fp32 weights: w1t[8][64] b1[64] b3f[64] whf[8][64] bhf[8] swh[8]; exchange: xs[2][128][2] xh[8][2][128]; 5 mbarriers + tmem holder
 constexpr uint32_t SMALL_FLOATS = 8 * H + H + H + MAX_OUT * H + 2 * MAX_OUT;
 constexpr uint32_t XCH_FLOATS = 2 * T_M * 2 + 2 * T_M * 8;
 __host__ __device__ inline uint32_t tc_smem_bytes(int d) { return tc_small_off(d) + 4 * (SMALL_FLOATS + XCH_FLOATS) + 5 * 8 + 16; }
@@ -274,7 +274,14 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, const TcMaps& m
         const bool valid = gi >= 0;
         float x[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) x[k] = (k < d) ? st_obs[row * d + k] : 0.f;
+        for (int k = 0; k < 8; ++k) x[k] = 0.f;
+        if (d == 4) {   // one 16-byte load per row (conflict-free); other widths: scalar loads
+            const float4 v = *reinterpret_cast<const float4*>(st_obs + row * 4);
+            x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) if (k < d) x[k] = st_obs[row * d + k];
+        }
         const float row_a = st_sc[0 * T_M + row], row_b = st_sc[1 * T_M + row];
         const float row_c = POLICY ? st_sc[2 * T_M + row] : 0.f, active = st_sc[3 * T_M + row];
 
@@ -378,9 +385,9 @@ __device__ __forceinline__ void tc_net_pass(const OrlPpoArgs& a, const TcMaps& m
             }
         }
         {   // exchange 3 (slot xh): partial head dots
-            FOR_OUT(j) xh[(half * T_M + row) * 8 + j] = out[j];
+            FOR_OUT(j) xh[(j * 2 + half) * T_M + row] = out[j];   // [j][half][row]: lanes are consecutive words (conflict-free)
             ROWGROUP_SYNC();
-            FOR_OUT(j) out[j] += xh[((half ^ 1) * T_M + row) * 8 + j];
+            FOR_OUT(j) out[j] += xh[(j * 2 + (half ^ 1)) * T_M + row];
         }
         // dot[j] = sum_k Whf[j][k] n3[k] (needed by the LayerNorm-3 backward); logits add the folded bias
         float dot[MAX_OUT];

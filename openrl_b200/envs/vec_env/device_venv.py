@@ -187,5 +187,32 @@ class DeviceVecEnv:
         self.episode_stats.zero_()
         return info
 
+    # call / get_attr / set_attr / exec_func (base_venv.py:231-302).  There are no per-env Python objects on the device:
+    # a property of the vec-env is reported once per env, setting broadcasts, exec_func sees lightweight per-env views.
+    def call(self, name, *args, **kwargs):
+        f = getattr(self, name)
+        v = f(*args, **kwargs) if callable(f) else f
+        return [v for _ in range(self.parallel_env_num)]
+
+    def get_attr(self, name):
+        return self.call(name)
+
+    def set_attr(self, name, values):
+        if isinstance(values, (list, tuple)):
+            if len(values) != self.parallel_env_num:
+                raise ValueError(f"Values must be a list or tuple with length equal to the number of environments. "
+                                 f"Got `{len(values)}` values for {self.parallel_env_num} environments.")
+            if any(v != values[0] for v in values[1:]):
+                raise NotImplementedError("per-env attribute values are not supported by the device vec-env (one batched state)")
+            values = values[0]
+        setattr(self, name, values)
+
+    def exec_func(self, func, indices=None, *args, **kwargs):
+        import types
+
+        idx = range(self.parallel_env_num) if indices is None else indices
+        return [func(types.SimpleNamespace(index=i, vec_env=self, observation_space=self.observation_space,
+                                           action_space=self.action_space, env_name=self.env_name), *args, **kwargs) for i in idx]
+
     def close(self):
         pass

@@ -68,6 +68,19 @@ class HostVecEnv:
     def random_action(self, infos=None):
         return np.array([[self.action_space.sample() for _ in range(self.agent_num)] for _ in range(self.parallel_env_num)])
 
+    # call / exec_func / set_attr (base_venv.py:231-302): forwarded to the wrapped host vec-env
+    def call(self, name, *args, **kwargs):
+        return self.env.call(name, *args, **kwargs)
+
+    def get_attr(self, name):
+        return self.env.call(name)
+
+    def set_attr(self, name, values):
+        return self.env.set_attr(name, values)
+
+    def exec_func(self, func, indices=None, *args, **kwargs):
+        return self.env.exec_func(func, indices, *args, **kwargs)
+
     def batch_rewards(self, buffer):
         return {}
 

@@ -89,6 +89,31 @@ class DiagGaussian(nn.Module):
         self.logstd = AddBias(torch.zeros(num_outputs))
 
 
+class PopArt(nn.Module):
+    """`v_out` under cfg.use_popart (popart.py:9-117).  In the reference's PPO path the PopArt statistics are never
+    driven: `value_normalizer` is the ValueNorm object (base_value_network.py:31-34) or None, so `PopArt.update /
+    normalize / denormalize` have no caller (ppo.py:190-217, replay_data.py:320-423) and the layer acts as
+    `F.linear(x, weight, bias)`.  What differs from nn.Linear is (i) the initialisation sequence — `reset_parameters`
+    draws kaiming-uniform weights and a uniform bias from the global generator BEFORE the orthogonal / zero init
+    overwrites them (value_network.py:106-109), shifting every later draw — and (ii) four extra checkpoint entries
+    (stddev, mean, mean_sq, debiasing_term; buffers here, requires_grad=False parameters there)."""
+
+    def __init__(self, input_shape, output_shape, beta=0.99999, epsilon=1e-5):
+        super().__init__()
+        import math
+
+        self.beta, self.epsilon = beta, epsilon
+        self.weight = nn.Parameter(torch.empty(output_shape, input_shape))
+        self.bias = nn.Parameter(torch.empty(output_shape))
+        self.register_buffer("stddev", torch.ones(output_shape))
+        self.register_buffer("mean", torch.zeros(output_shape))
+        self.register_buffer("mean_sq", torch.zeros(output_shape))
+        self.register_buffer("debiasing_term", torch.tensor(0.0))
+        nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))          # reset_parameters (popart.py:47-55)
+        bound = 1 / math.sqrt(input_shape)
+        nn.init.uniform_(self.bias, -bound, bound)
+
+
 class ACTLayer(nn.Module):
     def __init__(self, action_space, inputs_dim, use_orthogonal, gain):
         super().__init__()

@@ -3,7 +3,7 @@ with the `value_normalizer` attribute the algorithm looks up (ppo_module.py:212-
 import torch
 import torch.nn as nn
 
-from .base import FlatParams, MLPBase, RNNLayer, ValueNorm, _init
+from .base import FlatParams, MLPBase, PopArt, RNNLayer, ValueNorm, _init
 
 
 def _critic_shape(space):
@@ -17,8 +17,6 @@ class ValueNetwork(nn.Module):
             raise NotImplementedError("use_naive_recurrent_policy (whole-trajectory BPTT) is not built; "
                                       "use_recurrent_policy (chunked) is")
         self.recurrent = bool(cfg.use_recurrent_policy)
-        if cfg.use_popart:
-            raise NotImplementedError("PopArt is a 'next' row (SURVEY.md §8f)")
         shape = _critic_shape(input_space)
         if len(shape) != 1 or shape[0] > 64:
             raise NotImplementedError("vector observations of width <= 64 only")
@@ -27,7 +25,8 @@ class ValueNetwork(nn.Module):
         self.base = MLPBase(cfg, shape)
         if self.recurrent:
             self.rnn = RNNLayer(self.base.output_size, self.base.output_size, cfg.recurrent_N, cfg.use_orthogonal, cfg.rnn_type)
-        self.v_out = _init(nn.Linear(self.base.output_size, 1), 1.0, cfg.use_orthogonal)
+        head = PopArt(self.base.output_size, 1) if cfg.use_popart else nn.Linear(self.base.output_size, 1)
+        self.v_out = _init(head, 1.0, cfg.use_orthogonal)
         self.device = torch.device(device)
         self._flat = FlatParams(self, self.device)
         # registered after flattening: its state is a buffer, not an optimised parameter

@@ -267,6 +267,7 @@ FLAG_VARIANTS = {   # name: (canonical flags, the reference parser's spelling, a
     "no_valuenorm": (["--use_valuenorm", "false"], None, "ppo"),
     "adv_norm_no_masks": (["--use_adv_normalize", "true", "--use_value_active_masks", "false", "--use_policy_active_masks", "false"],
                           ["--use_adv_normalize", "true", "--use_value_active_masks", "false", "--use_policy_active_masks"], "ppo"),
+    "popart": (["--use_popart", "true", "--use_valuenorm", "false"], None, "ppo"),   # the reference asserts not (popart and valuenorm)
     "no_grad_clip_wd": (["--use_max_grad_norm", "false", "--weight_decay", "0.01", "--activation_id", "0"],
                         ["--use_max_grad_norm", "--weight_decay", "0.01", "--activation_id", "0"], "ppo"),
 }

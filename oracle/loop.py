@@ -67,7 +67,7 @@ class Trainer:
         self.pol = nets.init_policy(cfg, d, "Box" if self.box else "Discrete", n)
         self.cri = nets.init_critic(cfg, d)
         self.opt_p, self.opt_c = ppo.make_optimizers(cfg, self.pol, self.cri)
-        self.vn = ppo.ValueNormState() if (cfg.use_valuenorm or cfg.use_popart) else None
+        self.vn = ppo.ValueNormState() if cfg.use_valuenorm else None   # base_value_network.py:31-34 (use_popart adds no normaliser)
         T, N, A = cfg.episode_length, env_num, 1
         f = lambda *s: np.zeros(s, np.float32)
         self.buf = types.SimpleNamespace(

@@ -94,7 +94,19 @@ def init_critic(cfg, obs_dim):
                   cfg.use_feature_normalization)
     if cfg.use_recurrent_policy:
         init_rnn(p, "rnn", cfg.hidden_size, cfg.recurrent_N)
-    _linear(p, "v_out", cfg.hidden_size, 1, 1.0)
+    if getattr(cfg, "use_popart", False):
+        # v_out = init_(PopArt(H, 1)) (value_network.py:106-109): PopArt.reset_parameters draws kaiming-uniform weights
+        # and a uniform bias first (popart.py:47-55), then init_ overwrites them with orthogonal / zero
+        import math
+
+        w = torch.empty(1, cfg.hidden_size)
+        nn.init.kaiming_uniform_(w, a=math.sqrt(5))
+        b = torch.empty(1)
+        nn.init.uniform_(b, -1 / math.sqrt(cfg.hidden_size), 1 / math.sqrt(cfg.hidden_size))
+        (nn.init.orthogonal_ if cfg.use_orthogonal else nn.init.xavier_uniform_)(w, gain=1.0)
+        p["v_out.weight"], p["v_out.bias"] = w, torch.zeros(1)
+    else:
+        _linear(p, "v_out", cfg.hidden_size, 1, 1.0)
     return p
 
 

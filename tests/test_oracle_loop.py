@@ -85,7 +85,7 @@ def test_multi_agent_oracle_reproduces_reference_trace(tag, env_id):
 
 
 FLAG_TAGS = ["a2c", "dual_clip", "no_huber", "no_value_clip", "proper_time_limits", "no_gae", "no_valuenorm", "adv_norm_no_masks",
-             "no_grad_clip_wd"]
+             "no_grad_clip_wd", "popart"]
 
 
 @pytest.mark.parametrize("tag", FLAG_TAGS)

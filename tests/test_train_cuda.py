@@ -196,7 +196,7 @@ def test_algorithm_train_on_fresh_buffer(cuda):
 
 
 FLAG_TAGS = ["a2c", "dual_clip", "no_huber", "no_value_clip", "proper_time_limits", "no_gae", "no_valuenorm", "adv_norm_no_masks",
-             "no_grad_clip_wd"]
+             "no_grad_clip_wd", "popart"]
 
 
 @pytest.mark.parametrize("tag", FLAG_TAGS)
