@@ -122,7 +122,10 @@ class SyntheticHostEnv:
         return self.rng.standard_normal((self.parallel_env_num, 1, self.obs_dim)).astype(self.np.float32)
 
     def step(self, actions):
-        n = self.parallel_env_num
+        return self.step_range(0, self.parallel_env_num, actions)
+
+    def step_range(self, lo, hi, actions):
+        n = hi - lo
         return (self.rng.standard_normal((n, 1, self.obs_dim)).astype(self.np.float32), self.rng.standard_normal((n, 1, 1)),
                 self.rng.random((n, 1)) < 1e-3, [{} for _ in range(n)])
 
@@ -289,7 +292,7 @@ def side_result(rank, world, flush, workload, steps, envs=None, extra_flags=(), 
     return out
 
 
-def c5_result(steps=3):
+def c5_result(steps=3, grouped=True):
     """BASELINE configs[4] class: host env.step (numpy stand-in with HalfCheetah shapes), device act + buffer + GAE +
     update, Gaussian head; measured through PPOAgent.train (there is no device-only form of this path)."""
     import torch
@@ -301,7 +304,7 @@ def c5_result(steps=3):
     from openrl_b200.utils.logger import Logger
 
     n, Tn = 1024, T
-    cfg = create_config_parser().parse_args(FLAGS)
+    cfg = create_config_parser().parse_args(FLAGS + ["--host_env_groups", "true" if grouped else "false"])
     cfg.quiet = True
     host = SyntheticHostEnv(n)
     env = HostVecEnv(host)
@@ -322,7 +325,9 @@ def c5_result(steps=3):
     return {"workload": f"host-stepped synthetic HalfCheetah shapes (obs 17, Box(6)), {n} envs, T={Tn}, {EPOCHS} epochs, Gaussian head",
             "e2e": {"value": n * Tn * steps / dt, "unit": "env-steps/s", "h2d_bytes_per_step": (env.h2d_bytes - h0) / steps,
                     "d2h_bytes_per_step": (env.d2h_bytes - d0) / steps},
-            "ms_per_step": dt / steps * 1e3, "host_env_only_ms_per_step": host_s * 1e3, "steps": steps}
+            "ms_per_step": dt / steps * 1e3, "host_env_only_ms_per_step": host_s * 1e3, "steps": steps,
+            "ingest": "two env groups in ping-pong (device work of one group overlaps host stepping of the other)" if grouped
+                      else "one group, synchronous (act -> D2H -> env.step -> H2D per step)"}
 
 
 def ncu_traffic():
@@ -360,7 +365,9 @@ def run_ours(args):
     graphed = getattr(drv, "_graph", None) is not None
     del drv
 
+    print("[bench] main timed region done", file=sys.stderr, flush=True)
     e2e_s, h2d, d2h = time_e2e(rank, world, args.steps, "c2")
+    print("[bench] e2e done", file=sys.stderr, flush=True)
 
     strong = None
     if world > 1:
@@ -391,10 +398,15 @@ def run_ours(args):
     extras = {}
     if world == 1 and not args.no_extras:
         def guarded(name, fn):
+            if args.only_extra and name not in args.only_extra.split(","):
+                return
+            t_ = time.time()
+            print(f"[bench] extra {name} ...", file=sys.stderr, flush=True)
             try:
                 extras[name] = fn()
             except Exception as e:  # noqa: BLE001
                 extras[name] = {"error": f"{type(e).__name__}: {str(e)[-300:]}"}
+            print(f"[bench] extra {name} done in {time.time() - t_:.1f} s", file=sys.stderr, flush=True)
         # the same C2 workload with the fp32 FFMA update kernel, and in parity mode (reference-order CPU noise + randperm)
         guarded("c2_fp32_ffma_update", lambda: side_result(0, 1, flush, "c2", 5, extra_flags=["--use_tensor_cores", "false"], e2e=False))
         guarded("c2_parity_mode", lambda: side_result(0, 1, flush, "c2", 3, extra_flags=["--parity_mode", "true"], e2e=False))
@@ -402,6 +414,8 @@ def run_ours(args):
         guarded("c1_8_envs", lambda: side_result(0, 1, flush, "c1", 10))
         guarded("c3_mpe_gru_2048x3", lambda: side_result(0, 1, flush, "c3", 3, e2e=False))
         guarded("c5_host_env_1024", lambda: c5_result(3))
+        guarded("c5_host_env_1024_synchronous_ingest", lambda: c5_result(3, grouped=False))
+    print("[bench] cpu baseline ...", file=sys.stderr, flush=True)
     cpu = None if args.no_cpu_baseline else cpu_baseline_sample(n_envs=256, iters=1)
     out = {
         "metric": METRIC, "value": value, "unit": "env-steps/s",
@@ -500,7 +514,7 @@ def cpu_baseline_sample(n_envs=256, iters=1):
                       f"reference from baseline/_ref, SyncVectorEnv, {ref['host_cores']} host cores", "port": port}
 
 
-def reference_run(envs, iters, warmup, asynchronous=False, timeout=900):
+def reference_run(envs, iters, warmup, asynchronous=False, timeout=300):
     """One timed run of the UNMODIFIED reference (baseline/_ref, oracle/run_reference.py) in a fresh
     process: `PPOAgent.train` on the host cores, all of them (the child resets torchrun's OMP_NUM_THREADS=1)."""
     cmd = [sys.executable, os.path.join(ROOT, "oracle", "run_reference.py"), "--env", "CartPole-v1", "--envs", str(envs),
@@ -579,6 +593,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="development: skip the cpu_baseline leg")
     ap.add_argument("--no-extras", action="store_true", help="skip the extras block (other configs / modes)")
+    ap.add_argument("--only-extra", default="", help="development: comma-separated names of the extras to run")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -184,6 +184,15 @@ int orl_rollout(const OrlRolloutArgs* args, void* stream);
 int orl_critic_values(const float* critic_params, int obs_dim, int activation_id,
                       const float* obs, float* values, long long rows, void* stream);
 
+/* ---- insert of one HOST env.step into the device rollout buffer ---------------------------
+ * Replaces OnPolicyDriver.add2buffer -> ReplayData.insert (onpolicy_driver.py:80-152, replay_data.py:245-284) for
+ * host-stepped envs: `staged` is the step's result as ONE uploaded block [obs (B*d) | rewards (B) | dones (B)]
+ * (B = n_envs * n_agents rows); writes slot t+1 of policy_obs / masks / active_masks and slot t of rewards with the
+ * reference's mask rules (masks = 0 where all agents of the env are done, active_masks = 0 for a done agent of a
+ * running env).  Pointers address the given slot / row range (rows of a group are contiguous). */
+int orl_host_insert(const float* staged, int n_envs, int n_agents, int obs_dim, float* policy_obs_next, float* rewards,
+                    float* masks_next, float* active_masks_next, void* stream);
+
 /* ---- policy evaluation of given actions over a flat batch of rows ------------------------
  * Replaces PolicyNetwork.eval_actions (policy_network.py:164-203) -> ACTLayer.evaluate_actions (act.py:130-172), the
  * policy half of PPOModule.evaluate_actions (ppo_module.py:147-193), outside the fused update: obs (rows, d), actions

@@ -60,6 +60,8 @@ FLAGS = [
     # replay one captured CUDA graph per iteration (rollout + critic + GAE + all updates + slot shift) instead of ~25
     # launches; used when no callback needs rollout hooks, outside parity_mode, on device-resident envs
     ("use_cuda_graph", _bool, True),
+    # host-stepped envs: step two env groups in ping-pong so that device work of one overlaps host stepping of the other
+    ("host_env_groups", _bool, True),
     ("use_tf32", _bool, True),
 ]
 

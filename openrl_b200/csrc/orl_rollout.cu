@@ -287,6 +287,26 @@ __global__ void __launch_bounds__(C_NT) critic_values_kernel(const float* __rest
     }
 }
 
+// ---- insert of one host env.step into the rollout buffer (OnPolicyDriver.add2buffer, onpolicy_driver.py:80-152) -----------
+// staged = [obs (B*d) | rewards (B) | dones (B)] as uploaded from the host in ONE copy; one thread per row.
+__global__ void host_insert_kernel(const float* __restrict__ staged, int n_envs, int n_agents, int d, float* __restrict__ obs_next,
+                                   float* __restrict__ rewards, float* __restrict__ masks_next, float* __restrict__ active_next) {
+    const int B = n_envs * n_agents;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= B) return;
+    const float* so = staged;
+    const float* sr = staged + (size_t)B * d;
+    const float* sd = sr + B;
+    for (int k = 0; k < d; ++k) obs_next[(size_t)r * d + k] = so[(size_t)r * d + k];
+    rewards[r] = sr[r];
+    const int e = r / n_agents;
+    bool all_done = true;
+    for (int a = 0; a < n_agents; ++a) all_done = all_done && (sd[e * n_agents + a] != 0.f);
+    const bool done = sd[r] != 0.f;
+    masks_next[r] = all_done ? 0.f : 1.f;                    // masks[dones_env] = 0
+    active_next[r] = (done && !all_done) ? 0.f : 1.f;        // active[dones] = 0, active[dones_env] = 1
+}
+
 // ---- PolicyNetwork.eval_actions over a flat batch (policy_network.py:164-203, act.py:160-168 / 150-158) ----------------
 // log-prob of the given action and the entropy of the action distribution per row (the caller takes the masked mean).
 __global__ void __launch_bounds__(C_NT) policy_eval_kernel(const float* __restrict__ params, int d, int n, int activation_id, int head_kind,
@@ -525,5 +545,16 @@ extern "C" int orl_policy_eval(const float* policy_params, int obs_dim, int n_ac
     policy_eval_kernel<<<grid, C_NT, smem, reinterpret_cast<cudaStream_t>(stream)>>>(policy_params, obs_dim, n_actions, activation_id, head_kind,
                                                                                     obs, actions, action_masks, log_probs, entropy, rows);
     ORL_LAUNCH_CHECK("policy_eval_kernel");
+    return 0;
+}
+
+extern "C" int orl_host_insert(const float* staged, int n_envs, int n_agents, int obs_dim, float* policy_obs_next, float* rewards,
+                               float* masks_next, float* active_masks_next, void* stream) {
+    ORL_CHECK_ARG(staged && policy_obs_next && rewards && masks_next && active_masks_next, "null buffer");
+    ORL_CHECK_ARG(n_envs > 0 && n_agents > 0 && obs_dim > 0, "shapes");
+    const int B = n_envs * n_agents;
+    host_insert_kernel<<<(B + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(staged, n_envs, n_agents, obs_dim, policy_obs_next,
+                                                                                         rewards, masks_next, active_masks_next);
+    ORL_LAUNCH_CHECK("host_insert_kernel");
     return 0;
 }

@@ -84,32 +84,37 @@ class OnPolicyDriver:
     def graph_iteration(self):
         """Replay (or, the first times, warm up / capture) the iteration graph.  The first two iterations run eagerly on a
         side stream (they are real training iterations), the third is captured and every iteration from then on is one
-        graph launch."""
-        if getattr(self, "_graph", None) is None:
+        graph launch.  The captured graph lives on the trainer (which, like the buffer, survives across
+        `PPOAgent.train` calls), so a later call with the same trainer / buffer / env replays it without re-capturing."""
+        st = getattr(self.trainer, "_iter_graph", None)
+        if st is None or st["buffer"] is not self.buffer.data or st["envs"] is not self.envs:
             A = self.envs.agent_num
-            if getattr(self, "_stats_dev", None) is None:
-                self._stats_dev = torch.zeros(6 + A + 4, dtype=torch.float64, device=self.device)
-                self._stats_host = torch.zeros(6 + A + 4, dtype=torch.float64, pin_memory=True)
-                self._graph_warm = 0
-            self.trainer.sync_lrs()
-            if self._graph_warm < 2:
+            st = dict(buffer=self.buffer.data, envs=self.envs, graph=None, warm=0, launches=0, rng_counter=self.rng_counter,
+                      stats_dev=torch.zeros(6 + A + 4, dtype=torch.float64, device=self.device),
+                      stats_host=torch.zeros(6 + A + 4, dtype=torch.float64, pin_memory=True))
+            self.trainer._iter_graph = st
+        self._stats_dev, self._stats_host = st["stats_dev"], st["stats_host"]
+        self.rng_counter = st["rng_counter"]      # the captured launches read this device counter
+        self.trainer.sync_lrs()
+        if st["graph"] is None:
+            if st["warm"] < 2:
                 s = torch.cuda.Stream(device=self.device)
                 s.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(s):
                     self._iteration_body()
                 torch.cuda.current_stream().wait_stream(s)
-                self._graph_warm += 1
+                st["warm"] += 1
                 return
             l0 = self.gpu_launches + self.trainer.gpu_launches
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self._iteration_body()
-            self._graph_launches = self.gpu_launches + self.trainer.gpu_launches - l0
-            self.gpu_launches -= self._graph_launches     # capture launched nothing
-            self._graph = g
-        self.trainer.sync_lrs()
-        self._graph.replay()
-        self.gpu_launches += self._graph_launches
+            st["launches"] = self.gpu_launches + self.trainer.gpu_launches - l0
+            self.gpu_launches -= st["launches"]     # capture launched nothing
+            st["graph"] = g
+        self._graph = st["graph"]
+        st["graph"].replay()
+        self.gpu_launches += st["launches"]
 
     def _read_graph_stats(self):
         self._stats_host.copy_(self._stats_dev, non_blocking=True)
@@ -320,6 +325,8 @@ class OnPolicyDriver:
         B = N * A
         pol = self.trainer.algo_module.models["policy"]
         w = d.actions.shape[-1]
+        if getattr(env, "supports_groups", False) and cb is None and not self.cfg.parity_mode and bool(getattr(self.cfg, "host_env_groups", True)):
+            return self._host_rollout_grouped()
         for step in range(T):
             noise = None
             if self.cfg.parity_mode:
@@ -340,19 +347,67 @@ class OnPolicyDriver:
             with self._phase("rollout"):
                 lib.check(self._lib.orl_rollout(a, lib.current_stream()), "orl_rollout(act)")
             self.gpu_launches += 2
-            obs_d, rew_d, done_d, obs, rewards, dones, infos = env.step_staged(d.actions[step].view(B, w))
-            d.policy_obs[step + 1].view(B, d.obs_dim).copy_(obs_d)
-            d.rewards[step].view(B).copy_(rew_d)
-            dones_env = done_d.min(dim=1, keepdim=True).values           # all agents done
-            d.masks[step + 1].view(N, A).copy_((1.0 - dones_env).expand(N, A))
-            active = (1.0 - done_d) + dones_env * done_d                  # active[dones]=0, active[dones_env]=1
-            d.active_masks[step + 1].view(N, A).copy_(active)
+            staged, obs, rewards, dones, infos = env.step_staged(d.actions[step].view(B, w))
+            lib.check(self._lib.orl_host_insert(lib.ptr(staged), N, A, d.obs_dim, lib.ptr(d.policy_obs[step + 1]), lib.ptr(d.rewards[step]),
+                                                lib.ptr(d.masks[step + 1]), lib.ptr(d.active_masks[step + 1]), lib.current_stream()),
+                      "orl_host_insert")
+            self.gpu_launches += 1
             self.agent.num_time_steps += N
             if cb is not None:
                 actions = d.actions[step].cpu().numpy()  # noqa: F841
                 cb.update_locals(locals())
                 if cb.on_step() is False:
                     return False
+        return True
+
+    def _act_rows(self, step, lo, hi):
+        """Policy forward + sampling for buffer rows [lo, hi) of slot `step` (orl_rollout, ORL_ENV_NONE)."""
+        d = self.buffer.data
+        pol = self.trainer.algo_module.models["policy"]
+        A = self.envs.agent_num
+        r0, r1 = lo * A, hi * A
+        obs = d.policy_obs[step].view(-1, d.obs_dim)
+        w = d.actions.shape[-1]
+        acts, logp = d.actions[step].view(-1, w), d.action_log_probs[step].view(-1, w)
+        a = lib.OrlRolloutArgs()
+        a.env_kind, a.n_envs, a.n_agents, a.episode_length = lib.ENV_NONE, r1 - r0, 1, 1
+        a.t_begin, a.t_end = 0, 1
+        a.obs_dim, a.critic_obs_dim, a.n_actions = d.obs_dim, 0, d.n_actions
+        a.activation_id, a.deterministic, a.head_kind = pol.activation_id, 0, pol.head_kind
+        a.policy_params = lib.ptr(pol.flat_params)
+        a.policy_obs = lib.ptr(obs[r0:r1])
+        a.actions, a.action_log_probs = lib.ptr(acts[r0:r1]), lib.ptr(logp[r0:r1])
+        a.rng_seed, a.rng_step_base, a.rng_counter = int(self.cfg.seed) + 0x9E3779B9 * (self.rank + 1), self._host_steps_base + step, None
+        a.rng_row_offset = r0
+        lib.check(self._lib.orl_rollout(a, lib.current_stream()), "orl_rollout(act rows)")
+        self.gpu_launches += 1
+        return acts[r0:r1]
+
+    def _host_rollout_grouped(self):
+        """Host-stepped rollout with two env groups in ping-pong (double-buffered pinned staging): while the host steps
+        group g, the device inserts the other group's results and runs its policy forward for the next step; a group's
+        actions travel D2H asynchronously and are awaited (CUDA event) only when the host is ready to step that group.
+        Same per-step semantics as `_host_rollout` (add2buffer, onpolicy_driver.py:80-152)."""
+        d, env = self.buffer.data, self.envs
+        T, N, A = self.episode_length, env.parallel_env_num, env.agent_num
+        groups = env.group_bounds(2)
+        self._host_steps_base = getattr(self, "_host_steps_base", 0)   # Philox step of slot 0 of this rollout
+        with self._phase("rollout"):
+            for g, (lo, hi) in enumerate(groups):       # prime: actions of step 0 for both groups
+                env.group_fetch_actions(g, lo, hi, self._act_rows(0, lo, hi))
+            for step in range(T):
+                for g, (lo, hi) in enumerate(groups):
+                    staged, *_ = env.group_step(g, lo, hi)     # host env.step of this group (device busy with the other)
+                    r0, r1 = lo * A, hi * A
+                    lib.check(self._lib.orl_host_insert(
+                        lib.ptr(staged), hi - lo, A, d.obs_dim, lib.ptr(d.policy_obs[step + 1].view(-1, d.obs_dim)[r0:r1]),
+                        lib.ptr(d.rewards[step].view(-1)[r0:r1]), lib.ptr(d.masks[step + 1].view(-1)[r0:r1]),
+                        lib.ptr(d.active_masks[step + 1].view(-1)[r0:r1]), lib.current_stream()), "orl_host_insert")
+                    self.gpu_launches += 1
+                    if step + 1 < T:
+                        env.group_fetch_actions(g, lo, hi, self._act_rows(step + 1, lo, hi))
+                self.agent.num_time_steps += N
+        self._host_steps_base += T
         return True
 
     @torch.no_grad()

@@ -46,11 +46,16 @@ class SyncHostVecEnv:
         return self._obs(obs), infos
 
     def step(self, actions, extra_data=None):
-        N, A = self.parallel_env_num, self.agent_num
+        return self.step_range(0, self.parallel_env_num, actions)
+
+    def step_range(self, lo, hi, actions):
+        """Step envs [lo, hi) only (`actions` holds their hi - lo actions): lets `HostVecEnv` ping-pong two env groups so
+        that the device works on one group while the host steps the other."""
+        N, A = hi - lo, self.agent_num
         rewards = np.zeros((N, A, 1), np.float64)
         dones = np.zeros((N, A), bool)
         obs, infos = [], []
-        for i, env in enumerate(self.envs):
+        for i, env in enumerate(self.envs[lo:hi]):
             a = np.asarray(actions[i])
             if A == 1:
                 a = a.reshape(-1)
@@ -74,7 +79,8 @@ class SyncHostVecEnv:
                 info["final_info"] = old_info
             obs.append(o)
             infos.append(info)
-        return self._obs(obs), rewards, dones, infos
+        o = np.stack([np.asarray(x, dtype=np.float32) for x in obs]).reshape(N, A, -1)
+        return o, rewards, dones, infos
 
     def random_action(self, infos=None):
         return np.array([[self.action_space.sample() for _ in range(self.agent_num)] for _ in range(self.parallel_env_num)])

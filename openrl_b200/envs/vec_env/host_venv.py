@@ -49,7 +49,8 @@ class HostVecEnv:
         return self.env.step(actions)
 
     def step_staged(self, actions_dev):
-        """actions (B, w) device tensor -> (obs, rewards, dones) device tensors via pinned staging."""
+        """actions (B, w) device tensor -> host env.step -> the device block [obs | rewards | dones] (one pinned H2D copy,
+        the layout orl_host_insert reads) plus the host-side step outputs."""
         N, A, d = self.parallel_env_num, self.agent_num, self.obs_dim
         a = actions_dev.cpu().numpy().reshape(N, A, -1)          # D2H (synchronises the stream)
         self.d2h_bytes += a.nbytes
@@ -63,7 +64,63 @@ class HostVecEnv:
         st[B * d + B:] = np.asarray(dones, dtype=np.float32).reshape(-1)
         dev = self._stage.to(self.device, non_blocking=True)      # one H2D copy
         self.h2d_bytes += st.nbytes
-        return dev[:B * d].view(B, d), dev[B * d:B * d + B], dev[B * d + B:].view(N, A), obs, rewards, dones, infos
+        return dev, obs, rewards, dones, infos
+
+    # -- two-group ping-pong (double-buffered ingest) ---------------------------------------------
+    @property
+    def supports_groups(self):
+        """True when the wrapped vec-env can step a sub-range of its envs (`step_range(lo, hi, actions)`)."""
+        return hasattr(self.env, "step_range") and self.parallel_env_num >= 2
+
+    def group_bounds(self, n_groups=2):
+        N = self.parallel_env_num
+        cuts = [N * g // n_groups for g in range(n_groups + 1)]
+        return [(cuts[g], cuts[g + 1]) for g in range(n_groups)]
+
+    def _group_stage(self, g, lo, hi):
+        key = (g, lo, hi)
+        if getattr(self, "_gstages", None) is None:
+            self._gstages = {}
+        if key not in self._gstages:
+            n, A, d = hi - lo, self.agent_num, self.obs_dim
+            pin = torch.cuda.is_available()
+            self._gstages[key] = dict(
+                inp=torch.empty(n * A * (d + 2), dtype=torch.float32, pin_memory=pin),     # obs | rewards | dones
+                act=None, dev=torch.empty(n * A * (d + 2), dtype=torch.float32, device=self.device),
+                ev=torch.cuda.Event() if pin else None)
+        return self._gstages[key]
+
+    def group_fetch_actions(self, g, lo, hi, actions_dev):
+        """Enqueue the D2H copy of this group's actions into its pinned buffer and mark it with an event."""
+        st = self._group_stage(g, lo, hi)
+        if st["act"] is None or st["act"].shape != actions_dev.shape:
+            st["act"] = torch.empty(actions_dev.shape, dtype=torch.float32, pin_memory=torch.cuda.is_available())
+        st["act"].copy_(actions_dev, non_blocking=True)
+        if st["ev"] is not None:
+            st["ev"].record()
+        self.d2h_bytes += actions_dev.numel() * 4
+
+    def group_step(self, g, lo, hi):
+        """Wait for the group's actions, step its envs on the host, stage the results in pinned memory and enqueue ONE
+        H2D copy; returns the device block [obs | rewards | dones] (the layout orl_host_insert reads) plus the host-side
+        step outputs."""
+        st = self._group_stage(g, lo, hi)
+        if st["ev"] is not None:
+            st["ev"].synchronize()
+        n, A, d = hi - lo, self.agent_num, self.obs_dim
+        a = st["act"].numpy().reshape(n, A, -1)
+        if self._discrete:
+            a = a.astype(np.int64)
+        obs, rewards, dones, infos = self.env.step_range(lo, hi, a)
+        B = n * A
+        buf = st["inp"].numpy()
+        buf[:B * d] = np.asarray(obs, dtype=np.float32).reshape(-1)
+        buf[B * d:B * d + B] = np.asarray(rewards, dtype=np.float32).reshape(-1)
+        buf[B * d + B:] = np.asarray(dones, dtype=np.float32).reshape(-1)
+        st["dev"].copy_(st["inp"], non_blocking=True)
+        self.h2d_bytes += buf.nbytes
+        dev = st["dev"]
+        return dev, obs, rewards, dones, infos
 
     def random_action(self, infos=None):
         return np.array([[self.action_space.sample() for _ in range(self.agent_num)] for _ in range(self.parallel_env_num)])

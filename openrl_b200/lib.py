@@ -138,6 +138,7 @@ _SIGNATURES.update({
     "orl_rollout": [_c.POINTER(OrlRolloutArgs), _P],
     "orl_env_step": [_I, _I, _I, _P, _P, _P, _P, _I, _c.c_uint64, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "orl_critic_values": [_P, _I, _I, _P, _P, _L, _P],
+    "orl_host_insert": [_P, _I, _I, _I, _P, _P, _P, _P, _P],
     "orl_policy_eval": [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _L, _P],
     "orl_ppo_stride": [_I, _I, _I],
     "orl_ppo_grads_stride": [_I, _I, _I],

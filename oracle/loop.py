@@ -30,7 +30,7 @@ DEFAULTS = dict(
     max_grad_norm=10.0, use_gae=True, gamma=0.99, gae_lambda=0.95, use_proper_time_limits=False,
     use_huber_loss=True, huber_delta=10.0, use_value_active_masks=True, use_policy_active_masks=True,
     use_adv_normalize=False, use_valuenorm=True, use_popart=False, dual_clip_ppo=False, dual_clip_coeff=3.0,
-    a2c=False,
+    a2c=False, use_share_model=False,
 )
 
 
@@ -64,8 +64,11 @@ class Trainer:
         d = self.env.obs_dim
         self.box = hasattr(self.env, "act_dim")
         n = self.env.act_dim if self.box else self.env.n_actions
-        self.pol = nets.init_policy(cfg, d, "Box" if self.box else "Discrete", n)
-        self.cri = nets.init_critic(cfg, d)
+        if getattr(cfg, "use_share_model", False):
+            self.pol = self.cri = nets.init_policy_value(cfg, d, "Box" if self.box else "Discrete", n)
+        else:
+            self.pol = nets.init_policy(cfg, d, "Box" if self.box else "Discrete", n)
+            self.cri = nets.init_critic(cfg, d)
         self.opt_p, self.opt_c = ppo.make_optimizers(cfg, self.pol, self.cri)
         self.vn = ppo.ValueNormState() if cfg.use_valuenorm else None   # base_value_network.py:31-34 (use_popart adds no normaliser)
         T, N, A = cfg.episode_length, env_num, 1

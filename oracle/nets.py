@@ -110,6 +110,42 @@ def init_critic(cfg, obs_dim):
     return p
 
 
+def init_policy_value(cfg, obs_dim, act_kind, act_dim):
+    """PolicyValueNetwork.__init__ (policy_value_network.py:33-104), cfg.use_share_model: obs_prep MLPBase ->
+    common MLPLayer(H, H, layer_N=0) -> [rnn] -> v_out (gain 1) -> act; `critic_obs_prep` is the same module object as
+    `obs_prep` (its state_dict entries are aliases, not new parameters)."""
+    p = {}
+    H = cfg.hidden_size
+    init_mlp_base(p, "obs_prep", obs_dim, H, cfg.layer_N, cfg.activation_id, cfg.use_feature_normalization)
+    gain = nn.init.calculate_gain(ACT_NAMES[cfg.activation_id])
+    _linear(p, "common.fc1.0", H, H, gain, cfg.use_orthogonal)
+    _layernorm(p, "common.fc1.2", H)
+    _linear(p, "common.fc3.0", H, H, gain, cfg.use_orthogonal)
+    _layernorm(p, "common.fc3.1", H)
+    if cfg.use_recurrent_policy:
+        init_rnn(p, "rnn", H, cfg.recurrent_N)
+    _linear(p, "v_out", H, 1, 1.0, cfg.use_orthogonal)
+    if act_kind == "Discrete":
+        _linear(p, "act.action_out.linear", H, act_dim, cfg.gain, cfg.use_orthogonal)
+    else:
+        _linear(p, "act.action_out.fc_mean", H, act_dim, cfg.gain, cfg.use_orthogonal)
+        p["act.action_out.logstd._bias"] = torch.zeros(act_dim, 1)
+    return p
+
+
+def is_shared(p):
+    return "common.fc1.0.weight" in p
+
+
+def shared_trunk(p, cfg, obs):
+    """obs_prep -> common (policy_value_network.py:117-124,152-156,166-172): the feature both heads read."""
+    x = mlp_base(p, "obs_prep", obs, cfg.layer_N, cfg.activation_id)
+    h = activation(F.linear(x, p["common.fc1.0.weight"], p["common.fc1.0.bias"]), cfg.activation_id)
+    h = F.layer_norm(h, h.shape[-1:], p["common.fc1.2.weight"], p["common.fc1.2.bias"])
+    h = F.linear(h, p["common.fc3.0.weight"], p["common.fc3.0.bias"])
+    return F.layer_norm(h, h.shape[-1:], p["common.fc3.1.weight"], p["common.fc3.1.bias"])
+
+
 def mlp_base(p, prefix, x, layer_N, activation_id):
     if prefix + ".feature_norm.weight" in p:
         x = F.layer_norm(x, x.shape[-1:], p[prefix + ".feature_norm.weight"], p[prefix + ".feature_norm.bias"])
@@ -158,7 +194,7 @@ def rnn_layer(p, prefix, x, hxs, masks):
 
 
 def policy_features(p, cfg, obs, rnn_states=None, masks=None):
-    f = mlp_base(p, "base", obs, cfg.layer_N, cfg.activation_id)
+    f = shared_trunk(p, cfg, obs) if is_shared(p) else mlp_base(p, "base", obs, cfg.layer_N, cfg.activation_id)
     if cfg.use_recurrent_policy:
         f, rnn_states = rnn_layer(p, "rnn", f, rnn_states, masks)
     return f, rnn_states
@@ -247,8 +283,8 @@ def policy_eval_gaussian(p, cfg, obs, actions, active_masks=None):
 
 
 def critic_forward(p, cfg, obs, rnn_states=None, masks=None):
-    """ValueNetwork.forward (value_network.py:113-136)."""
-    f = mlp_base(p, "base", obs, cfg.layer_N, cfg.activation_id)
+    """ValueNetwork.forward (value_network.py:113-136); PolicyValueNetwork.get_values for a shared model."""
+    f = shared_trunk(p, cfg, obs) if is_shared(p) else mlp_base(p, "base", obs, cfg.layer_N, cfg.activation_id)
     if cfg.use_recurrent_policy:
         f, rnn_states = rnn_layer(p, "rnn", f, rnn_states, masks)
     return F.linear(f, p["v_out.weight"], p["v_out.bias"]), rnn_states

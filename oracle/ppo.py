@@ -53,6 +53,11 @@ def huber_loss(e, d):
 
 
 def make_optimizers(cfg, policy_params, critic_params):
+    if policy_params is critic_params:   # cfg.use_share_model: ONE Adam over the shared model, lr = cfg.lr (ppo_module.py:60-69)
+        for v in policy_params.values():
+            v.requires_grad_(True)
+        opt = torch.optim.Adam(list(policy_params.values()), lr=cfg.lr, eps=cfg.opti_eps, weight_decay=cfg.weight_decay)
+        return opt, opt
     for v in list(policy_params.values()) + list(critic_params.values()):
         v.requires_grad_(True)
     opt_p = torch.optim.Adam(list(policy_params.values()), lr=cfg.lr, eps=cfg.opti_eps, weight_decay=cfg.weight_decay)
@@ -109,7 +114,10 @@ def ppo_update(cfg, pol, cri, opt_p, opt_c, vn, batch):
     else:
         policy_loss = -torch.sum(surr, dim=-1, keepdim=True).mean()
     value_loss = value_loss_fn(cfg, vn, values, batch["value_preds"], batch["returns"], active)
-    (policy_loss - ent * cfg.entropy_coef).backward()
+    # construct_loss_list + `for loss in loss_list: loss.backward()` (ppo.py:226-236,117-118); with a shared model both
+    # losses accumulate into the same .grad, both clip_grad_norm_ calls see ALL parameters (base_value_policy_network.py:
+    # 58-62: the second one acts on the already clipped gradients) and the single optimiser steps once
+    (policy_loss - ent * cfg.entropy_coef).backward(retain_graph=pol is cri)
     (value_loss * cfg.value_loss_coef).backward()
     if cfg.use_max_grad_norm:
         agn = torch.nn.utils.clip_grad_norm_(list(pol.values()), cfg.max_grad_norm)
@@ -118,5 +126,6 @@ def ppo_update(cfg, pol, cri, opt_p, opt_c, vn, batch):
         agn = torch.sqrt(sum(p.grad.norm() ** 2 for p in pol.values()))
         cgn = torch.sqrt(sum(p.grad.norm() ** 2 for p in cri.values()))
     opt_p.step()
-    opt_c.step()
+    if opt_c is not opt_p:
+        opt_c.step()
     return (value_loss.item(), float(cgn), policy_loss.item(), ent.item(), float(agn), ratio.mean().item())

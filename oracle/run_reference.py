@@ -42,13 +42,16 @@ def main():
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--async", dest="asynchronous", action="store_true")
-    ap.add_argument("--threads", type=int, default=0, help="torch intra-op threads (0 = all host cores)")
+    ap.add_argument("--threads", type=int, default=0, help="torch intra-op threads (0 = calibrate: the fastest of 1 / 4 / 8 / 16 / 32, capped at the core count)")
     ap.add_argument("--extra", default="", help="extra reference flags, space separated")
     a = ap.parse_args()
 
     # torchrun exports OMP_NUM_THREADS=1; the reference arm uses every host core it can
     ncores = os.cpu_count() or 1
-    threads = a.threads or ncores
+    # "all the host threads it can use": on many-core hosts torch's default (every core) makes these tiny ops slower, so
+    # with --threads 0 the first iterations try several counts and the fastest is kept for the warm-up and the timed run
+    cands = sorted({c for c in (1, 4, 8, 16, 32, min(ncores, 32)) if c <= ncores}) if not a.threads else []   # > 32 threads only slows these tiny ops
+    threads = a.threads or min(ncores, 32)
     os.environ["OMP_NUM_THREADS"] = str(threads)
     os.environ["MKL_NUM_THREADS"] = str(threads)
     for p in reversed(ref_paths()):
@@ -78,9 +81,21 @@ def main():
     stamps = []
     orig_inner = OnPolicyDriver._inner_loop
 
+    cal = {"i": 0, "t": time.perf_counter(), "dur": {}}
+
     def inner(self):
+        if cal["i"] < len(cands):
+            torch.set_num_threads(cands[cal["i"]])
+            cal["t"] = time.perf_counter()
         r = orig_inner(self)
-        stamps.append(time.perf_counter())
+        now = time.perf_counter()
+        if cal["i"] < len(cands):
+            cal["dur"][cands[cal["i"]]] = now - cal["t"]
+            cal["i"] += 1
+            if cal["i"] == len(cands):
+                torch.set_num_threads(min(cal["dur"], key=cal["dur"].get))
+            return r
+        stamps.append(now)
         return r
 
     OnPolicyDriver._inner_loop = inner
@@ -96,22 +111,23 @@ def main():
             if "FPS" in infos:
                 fps_log.append(float(infos["FPS"]))
 
-    total = a.T * a.envs * (a.iters + a.warmup)
+    total = a.T * a.envs * (a.iters + a.warmup + len(cands))
     t_start = time.perf_counter()
     try:
         agent.train(total_time_steps=total, logger=FpsTap())
     finally:
         OnPolicyDriver._inner_loop = orig_inner
     env.close()
-    stamps = [t_start] + stamps
-    if len(stamps) < a.warmup + a.iters + 1:
-        raise SystemExit(f"reference ran {len(stamps) - 1} iterations, expected {a.warmup + a.iters}")
-    dt = stamps[a.warmup + a.iters] - stamps[a.warmup]
+    if len(stamps) < a.warmup + a.iters:
+        raise SystemExit(f"reference ran {len(stamps)} timed-phase iterations, expected {a.warmup + a.iters}")
+    # stamps[i] = end of post-calibration iteration i; the timed window is iterations [warmup, warmup + iters)
+    dt = stamps[a.warmup + a.iters - 1] - stamps[a.warmup - 1] if a.warmup > 0 else stamps[a.iters - 1] - t_start
     print(json.dumps({
         "env": a.env, "envs": a.envs, "T": a.T, "epochs": a.epochs, "asynchronous": a.asynchronous, "iters": a.iters,
         "warmup": a.warmup, "seconds": dt, "env_steps_per_s": a.T * a.envs * a.iters / dt,
         "reference_fps_log_last": fps_log[-1] if fps_log else None, "torch_threads": torch.get_num_threads(),
-        "host_cores": ncores, "processes": (a.envs + 1) if a.asynchronous else 1,
+        "host_cores": ncores, "thread_calibration_s_per_iteration": {str(k): round(v, 4) for k, v in cal["dur"].items()},
+        "processes": (a.envs + 1) if a.asynchronous else 1,
     }))
 
 

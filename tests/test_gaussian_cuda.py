@@ -121,3 +121,42 @@ def test_config5_shape_runs(cuda):
     assert 8.0 < logs[0]["dist_entropy"] < 9.0   # 6 * (0.5 + 0.5 log(2 pi)) = 8.51 at logstd = 0
     assert abs(logs[0]["ratio"] - 1.0) < 1e-3
     assert env.h2d_bytes > 0 and env.d2h_bytes > 0
+
+
+@pytest.mark.parametrize("grouped", ["true", "false"])
+def test_host_rollout_grouped_and_synchronous_fill_the_buffer_identically(cuda, grouped):
+    """Host-stepped rollout through make(make_custom_envs=...): the two-group ping-pong ingest (double-buffered pinned
+    staging, device work of one group overlapping host stepping of the other) and the synchronous loop must insert the
+    same things: next observations, rewards (= the action taken), masks 0 exactly at episode ends, for EVERY env."""
+    from openrl_b200.configs.config import create_config_parser
+    from openrl_b200.envs.common import make
+    from openrl_b200.modules.common import PPONet
+    from openrl_b200.runners.common import PPOAgent
+    from openrl_b200.utils.logger import Logger
+    from test_host_sync_env import CountEnv
+
+    T, N, H = 12, 10, 5
+    cfg = create_config_parser().parse_args(["--seed", "0", "--episode_length", str(T), "--ppo_epoch", "1", "--host_env_groups", grouped,
+                                             "--log_interval", "1"])
+    cfg.quiet = True
+    env = make("Count-v0", env_num=N, make_custom_envs=lambda id, env_num, render_mode=None, **kw: [(lambda i=i: CountEnv(i, horizon=H)) for i in range(env_num)])
+    agent = PPOAgent(PPONet(env, cfg=cfg, device="cuda:0"))
+    logger = Logger(quiet=True)
+    agent.train(total_time_steps=T * N, logger=logger)
+    b = agent.driver.buffer.data
+    # after_update moved slot T to slot 0; slots 1..T still hold the rollout
+    obs = b.policy_obs.cpu().numpy()[:, :, 0, :]          # (T+1, N, 2) = [t, id]
+    acts = b.actions.cpu().numpy()[:, :, 0, 0]
+    rew = b.rewards.cpu().numpy()[:, :, 0, 0]
+    masks = b.masks.cpu().numpy()[:, :, 0, 0]
+    for t in range(T):
+        step_in_ep = (t + 1) % H
+        assert (obs[t + 1, :, 1] == np.arange(N)).all()                          # every env (both groups) was inserted
+        assert (obs[t + 1, :, 0] == (0 if step_in_ep == 0 else step_in_ep)).all()  # auto-reset observation at episode ends
+        assert (masks[t + 1] == (0.0 if step_in_ep == 0 else 1.0)).all()
+        assert (rew[t] == acts[t]).all()                                         # CountEnv rewards the action index
+    assert set(np.unique(acts)) <= {0.0, 1.0, 2.0} and len(np.unique(acts)) > 1   # sampled integer actions reached the host envs
+    for e in env.env.envs:
+        assert len(e.actions) == T
+    logs = [h[1] for h in logger.history if "value_loss" in h[1]]
+    assert len(logs) == 1 and np.isfinite(list(logs[0].values())).all()

@@ -116,3 +116,27 @@ def test_oracle_reproduces_reference_flag_variants(tag):
         tr.after_update()
         for k, v in _params(tr).items():
             np.testing.assert_allclose(v, d[f"it{it}/params/{k}"], rtol=1e-4, atol=1e-6, err_msg=k)
+
+
+def test_oracle_reproduces_reference_share_model_trace():
+    """cfg.use_share_model: PolicyValueNetwork (obs_prep -> common -> {act, v_out}, policy_value_network.py:33-174), one
+    optimiser, both losses into the same gradients, two clip_grad_norm_ over all parameters (ppo.py:120-141)."""
+    d = np.load(os.path.join(GOLDEN, "trace_share_model.npz"), allow_pickle=True)
+    cfg = loop.cfg_from_flags(str(d["meta/flags"]))
+    assert cfg.use_share_model
+    tr = loop.Trainer(cfg, "CartPole-v1", int(d["meta/env_num"]))
+    for k, v in tr.pol.items():
+        assert np.array_equal(v.detach().numpy(), d[f"init/model.{k}"]), k
+    for it in range(int(d["meta/iters"])):
+        tr.rollout()
+        b = tr.buf
+        assert np.array_equal(b.actions, d[f"it{it}/actions"])
+        assert np.array_equal(b.obs, d[f"it{it}/policy_obs"])
+        tr.compute_returns()
+        np.testing.assert_allclose(b.value_preds, d[f"it{it}/value_preds"], rtol=0, atol=1e-5)
+        updates, perms = tr.train()
+        assert np.array_equal(perms, d[f"it{it}/perms"])
+        np.testing.assert_allclose(updates, d[f"it{it}/updates"], rtol=1e-4, atol=1e-6)
+        tr.after_update()
+        for k, v in tr.pol.items():
+            np.testing.assert_allclose(v.detach().numpy(), d[f"it{it}/params/model.{k}"], rtol=1e-4, atol=1e-6, err_msg=k)
