@@ -355,6 +355,28 @@ int orl_rnn_fwdbwd(const OrlRnnArgs* args, void* stream);
 /* per-net global-norm clip + Adam on `grads`; ValueNorm commit; train_info accumulation */
 int orl_rnn_apply(const OrlRnnArgs* args, void* stream);
 
+
+/* ---- shared policy-value network (cfg.use_share_model) -----------------------------------
+ * Replace, for cfg.use_share_model, PolicyValueNetwork (openrl/modules/networks/policy_value_network.py:33-174:
+ * obs_prep MLPBase -> common MLPLayer(64, 64, layer_N=0) -> {v_out, act}) in the rollout (get_actions), the value pass
+ * (get_values) and PPOAlgorithm.ppo_update with `_use_share_model` (ppo.py:46-176: both losses into one set of
+ * gradients, clip_grad_norm_ over all parameters twice, ONE Adam step with lr = cfg.lr).
+ * Parameter layout (named_parameters order of the reference):
+ *   W1[64][d] b1 g1 be1 | W3[64][64] b3 g3 be3 | W5[64][64] b5 g5 be5 | W7[64][64] b7 g7 be7 | Wv[1][64] bv | Wa[n][64] ba
+ * Discrete heads, single-agent device envs (or ORL_ENV_NONE).  OrlRolloutArgs.policy_params = the shared model.
+ * OrlPpoArgs for the shared model: policy_params / policy_adam_* / lrs[0] / adam_steps[0] = the shared model and its
+ * optimiser, partials = workspace of orl_share_workspace_floats() floats, grads = true gradients (>= parameter count),
+ * folded = 8 floats of loss sums; critic_* fields are ignored.  With > 1 GPU the caller SUM-all-reduces `grads` and
+ * `folded[0..3]` between orl_share_fwdbwd and orl_share_apply. */
+int orl_share_param_count(int obs_dim, int n_actions);
+int orl_share_tape_width(void);
+long long orl_share_workspace_floats(long long rows, int obs_dim, int n_actions);
+int orl_share_rollout(const OrlRolloutArgs* args, void* stream);
+int orl_share_values(const float* params, int obs_dim, int n_actions, int activation_id, const float* obs, float* values,
+                     long long rows, void* stream);
+int orl_share_fwdbwd(const OrlPpoArgs* args, void* stream);
+int orl_share_apply(const OrlPpoArgs* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

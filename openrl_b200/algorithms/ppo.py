@@ -57,7 +57,19 @@ class PPOAlgorithm:
             self.flags |= lib.PPO_DUAL_CLIP
         assert not (getattr(cfg, "use_popart", False) and cfg.use_valuenorm), \
             "self._use_popart and self._use_valuenorm can not be set True simultaneously"   # ppo.py:40-44
-        for name in ("use_joint_action_loss", "use_policy_vhead", "use_share_model",
+        self.share = bool(getattr(init_module, "share_model", False))
+        if self.share:
+            # one network, one optimiser: true-layout gradients + 8 loss-sum slots in ONE bucket (a single all-reduce per update)
+            if self.recurrent:
+                raise NotImplementedError("use_share_model with recurrent policies is not built")
+            self.use_tensor_cores = False
+            self.flags &= ~lib.PPO_TENSORCORE
+            self.share_total = int(self._lib.orl_share_param_count(self.d, self.n))
+            self.share_bucket = torch.zeros(((self.share_total + 3) & ~3) + 8, dtype=torch.float32, device=dev)
+            self.share_grads = self.share_bucket[:(self.share_total + 3) & ~3]
+            self.share_loss = self.share_bucket[(self.share_total + 3) & ~3:]
+            self.share_ws = None
+        for name in ("use_joint_action_loss", "use_policy_vhead",
                      "use_amp", "use_deepspeed", "use_naive_recurrent_policy"):
             if getattr(cfg, name, False):
                 raise NotImplementedError(f"cfg.{name} is not built into the CUDA update yet (SURVEY.md §8f)")
@@ -119,6 +131,20 @@ class PPOAlgorithm:
                                                         lib.ptr(self.grads), lib.ptr(self.train_info))
         return a
 
+    def _share_update(self, buf, batch_rows, indices, row_begin, mb_stats):
+        """One minibatch update of the shared policy-value network (ppo.py:46-176 with `_use_share_model`)."""
+        L, s = self._lib, lib.current_stream()
+        need = int(L.orl_share_workspace_floats(int(batch_rows), self.d, self.n))
+        if self.share_ws is None or self.share_ws.numel() < need:
+            self.share_ws = torch.empty(need, dtype=torch.float32, device=self.device)
+        a = self._args(buf, batch_rows, indices, row_begin)
+        a.mb_stats = lib.ptr(mb_stats)
+        a.partials, a.grads, a.folded = lib.ptr(self.share_ws), lib.ptr(self.share_grads), lib.ptr(self.share_loss)
+        lib.check(L.orl_share_fwdbwd(a, s), "orl_share_fwdbwd")
+        parallel.allreduce_sum_(self.share_bucket)   # gradients + loss sums (no-op on one GPU)
+        lib.check(L.orl_share_apply(a, s), "orl_share_apply")
+        self.gpu_launches += 5
+
     def ppo_update(self, buf, batch_rows, indices=None, row_begin=0, mb_stats=None):
         """One minibatch update (ppo.py:46-176) — asynchronous."""
         L, s = self._lib, lib.current_stream()
@@ -128,6 +154,8 @@ class PPOAlgorithm:
             mb_stats = self.mb_stats
             self.gpu_launches += 1
             parallel.allreduce_sum_(mb_stats)
+        if self.share:
+            return self._share_update(buf, batch_rows, indices, row_begin, mb_stats)
         a = self._args(buf, batch_rows, indices, row_begin)
         a.mb_stats = lib.ptr(mb_stats)
         lib.check(L.orl_ppo_fwdbwd(a, s), "orl_ppo_fwdbwd")

@@ -60,8 +60,10 @@ FLAGS = [
     # replay one captured CUDA graph per iteration (rollout + critic + GAE + all updates + slot shift) instead of ~25
     # launches; used when no callback needs rollout hooks, outside parity_mode, on device-resident envs
     ("use_cuda_graph", _bool, True),
-    # host-stepped envs: step two env groups in ping-pong so that device work of one overlaps host stepping of the other
-    ("host_env_groups", _bool, True),
+    # host-stepped envs: step two env groups in ping-pong so that the device work of one overlaps the host stepping of the
+    # other.  Pays off when env.step is slow relative to the per-step launch cost (MuJoCo-class); for cheap host envs the
+    # doubled launch count costs more than the overlap hides (bench extras, c5: 54 ms vs 44 ms per iteration), so off by default
+    ("host_env_groups", _bool, False),
     ("use_tf32", _bool, True),
 ]
 

@@ -252,6 +252,9 @@ class OnPolicyDriver:
         if self.recurrent:
             lib.check(self._lib.orl_rnn_rollout(self._rnn_args(t_begin, t_end, noise), s), "orl_rnn_rollout")
             self.gpu_launches += 2
+        elif getattr(self.trainer, "share", False):
+            lib.check(self._lib.orl_share_rollout(self._rollout_args(t_begin, t_end, noise), s), "orl_share_rollout")
+            self.gpu_launches += 2
         else:
             lib.check(self._lib.orl_rollout(self._rollout_args(t_begin, t_end, noise), s), "orl_rollout")
             self.gpu_launches += 2
@@ -345,7 +348,8 @@ class OnPolicyDriver:
             a.exp_noise = lib.ptr(noise)
             a.rng_seed, a.rng_step_base, a.rng_counter = int(self.cfg.seed) + 0x9E3779B9 * (self.rank + 1), 0, lib.ptr(self.rng_counter)
             with self._phase("rollout"):
-                lib.check(self._lib.orl_rollout(a, lib.current_stream()), "orl_rollout(act)")
+                act_fn = self._lib.orl_share_rollout if getattr(self.trainer, "share", False) else self._lib.orl_rollout
+                lib.check(act_fn(a, lib.current_stream()), "orl_rollout(act)")
             self.gpu_launches += 2
             staged, obs, rewards, dones, infos = env.step_staged(d.actions[step].view(B, w))
             lib.check(self._lib.orl_host_insert(lib.ptr(staged), N, A, d.obs_dim, lib.ptr(d.policy_obs[step + 1]), lib.ptr(d.rewards[step]),
@@ -379,7 +383,8 @@ class OnPolicyDriver:
         a.actions, a.action_log_probs = lib.ptr(acts[r0:r1]), lib.ptr(logp[r0:r1])
         a.rng_seed, a.rng_step_base, a.rng_counter = int(self.cfg.seed) + 0x9E3779B9 * (self.rank + 1), self._host_steps_base + step, None
         a.rng_row_offset = r0
-        lib.check(self._lib.orl_rollout(a, lib.current_stream()), "orl_rollout(act rows)")
+        act_fn = self._lib.orl_share_rollout if getattr(self.trainer, "share", False) else self._lib.orl_rollout
+        lib.check(act_fn(a, lib.current_stream()), "orl_rollout(act rows)")
         self.gpu_launches += 1
         return acts[r0:r1]
 
@@ -427,9 +432,14 @@ class OnPolicyDriver:
             self.gpu_launches += 2
             return
         with self._phase("critic"):
-            lib.check(self._lib.orl_critic_values(lib.ptr(cri.flat_params), cri.obs_dim, cri.activation_id,
-                                                  lib.ptr(d.critic_obs), lib.ptr(d.value_preds), rows,
-                                                  lib.current_stream()), "orl_critic_values")
+            if getattr(self.trainer, "share", False):
+                lib.check(self._lib.orl_share_values(lib.ptr(cri.flat_params), cri.obs_dim, cri.n_actions, cri.activation_id,
+                                                     lib.ptr(d.critic_obs), lib.ptr(d.value_preds), rows, lib.current_stream()),
+                          "orl_share_values")
+            else:
+                lib.check(self._lib.orl_critic_values(lib.ptr(cri.flat_params), cri.obs_dim, cri.activation_id,
+                                                      lib.ptr(d.critic_obs), lib.ptr(d.value_preds), rows,
+                                                      lib.current_stream()), "orl_critic_values")
         with self._phase("gae"):
             self.buffer.compute_returns(None, self.trainer.algo_module.get_critic_value_normalizer())
         self.gpu_launches += 2

@@ -70,6 +70,7 @@ def load(path=None):
     lib.orl_last_error.restype = _c.c_char_p
     lib.orl_last_error.argtypes = []
     lib.orl_rnn_workspace_floats.restype = _c.c_int64
+    lib.orl_share_workspace_floats.restype = _c.c_int64
     if lib.orl_abi_version() != 1:
         raise OrlLibraryError("ABI version mismatch")
     if path is None:
@@ -138,6 +139,13 @@ _SIGNATURES.update({
     "orl_rollout": [_c.POINTER(OrlRolloutArgs), _P],
     "orl_env_step": [_I, _I, _I, _P, _P, _P, _P, _I, _c.c_uint64, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "orl_critic_values": [_P, _I, _I, _P, _P, _L, _P],
+    "orl_share_param_count": [_I, _I],
+    "orl_share_tape_width": [],
+    "orl_share_workspace_floats": [_L, _I, _I],
+    "orl_share_rollout": [_c.POINTER(OrlRolloutArgs), _P],
+    "orl_share_values": [_P, _I, _I, _I, _P, _P, _L, _P],
+    "orl_share_fwdbwd": [_c.POINTER(OrlPpoArgs), _P],
+    "orl_share_apply": [_c.POINTER(OrlPpoArgs), _P],
     "orl_host_insert": [_P, _I, _I, _I, _P, _P, _P, _P, _P],
     "orl_policy_eval": [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _L, _P],
     "orl_ppo_stride": [_I, _I, _I],

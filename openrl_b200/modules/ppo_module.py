@@ -7,7 +7,7 @@ import numpy as np
 import torch
 
 from .. import lib
-from .networks import PolicyNetwork, ValueNetwork
+from .networks import PolicyNetwork, PolicyValueNetwork, ValueNetwork
 
 
 class FusedAdamState:
@@ -30,19 +30,37 @@ class FusedAdamState:
         self.exp_avg_sq.copy_(sd["exp_avg_sq"])
 
 
+class _Roles(dict):
+    """{"model": shared net} that also answers the "policy" / "critic" roles with the shared object, so code written
+    against the two-net layout (models["policy"], optimizers["critic"], ...) reads the right parameters; iteration,
+    `in`, and checkpoints see only the real key, like the reference's dicts (ppo_module.py:60-69)."""
+
+    def __missing__(self, key):
+        if key in ("policy", "critic") and "model" in self:
+            return self["model"]
+        raise KeyError(key)
+
+
 class PPOModule:
     def __init__(self, cfg, policy_input_space, critic_input_space, act_space, share_model=False, device="cuda:0",
                  rank=0, world_size=1, model_dict=None):
-        if share_model:
-            raise NotImplementedError("use_share_model (PolicyValueNetwork) is a 'next' row (SURVEY.md §8f)")
         self.cfg = cfg
         self.device = torch.device(device)
         self.lr, self.critic_lr = cfg.lr, cfg.critic_lr
         self.opti_eps, self.weight_decay = cfg.opti_eps, cfg.weight_decay
         self.act_space = act_space
         self.rank, self.world_size = rank, world_size
-        self.share_model = False
-        self.models, self.optimizers = {}, {}
+        self.share_model = bool(share_model)
+        self.models, self.optimizers = _Roles(), _Roles()
+        self.adam_steps = torch.zeros(2, dtype=torch.int32, device=self.device)
+        self._act_calls = 0   # Philox step of the next stochastic act() call
+        self._lib = lib.load()
+        if self.share_model:   # ppo_module.py:60-69: one PolicyValueNetwork, one Adam with lr = cfg.lr
+            cls = (model_dict or {}).get("model", PolicyValueNetwork)
+            self.models["model"] = cls(cfg=cfg, input_space=policy_input_space, action_space=act_space, device=self.device,
+                                       use_half=False, extra_args=None)
+            self.optimizers["model"] = FusedAdamState(self.models["model"].flat_params, cfg.lr, cfg.opti_eps, cfg.weight_decay)
+            return
         # dict order as in the reference: policy first, then critic (ppo_module.py:71-88)
         pol_cls = (model_dict or {}).get("policy", PolicyNetwork)
         cri_cls = (model_dict or {}).get("critic", ValueNetwork)
@@ -53,9 +71,6 @@ class PPOModule:
                                         device=self.device, use_half=False, extra_args=None)
         self.optimizers["critic"] = FusedAdamState(self.models["critic"].flat_params, cfg.critic_lr, cfg.opti_eps,
                                                    cfg.weight_decay)
-        self.adam_steps = torch.zeros(2, dtype=torch.int32, device=self.device)
-        self._act_calls = 0   # Philox step of the next stochastic act() call
-        self._lib = lib.load()
 
     # `torch.save(module)` / `torch.load` (the reference's checkpoint format, rl_agent.py:187-213): everything is
     # picklable except the ctypes library handle
@@ -71,7 +86,7 @@ class PPOModule:
     # -- reference surface -----------------------------------------------------------------
     def lr_decay(self, episode, episodes):
         """update_linear_schedule (openrl/modules/utils/util.py:13-17)."""
-        for key, base in (("policy", self.lr), ("critic", self.critic_lr)):
+        for key, base in ((("model", self.lr),) if self.share_model else (("policy", self.lr), ("critic", self.critic_lr))):
             lr = base - (base * (episode / float(episodes)))
             for g in self.optimizers[key].param_groups:
                 g["lr"] = lr
@@ -85,6 +100,10 @@ class PPOModule:
         rows = obs.shape[0]
         out = torch.empty(rows, 1, dtype=torch.float32, device=self.device)
         cri = self.models["critic"]
+        if self.share_model:
+            lib.check(self._lib.orl_share_values(lib.ptr(cri.flat_params), cri.obs_dim, cri.n_actions, cri.activation_id, lib.ptr(obs),
+                                                 lib.ptr(out), rows, lib.current_stream()), "orl_share_values")
+            return out
         lib.check(self._lib.orl_critic_values(lib.ptr(cri.flat_params), cri.obs_dim, cri.activation_id, lib.ptr(obs),
                                               lib.ptr(out), rows, lib.current_stream()), "orl_critic_values")
         return out
@@ -104,8 +123,8 @@ class PPOModule:
         """ppo_module.py:147-193: (values, action_log_probs, dist_entropy, policy_values=None) of given actions; the entropy
         is the active-mask mean when cfg.use_policy_active_masks (act.py:160-168), else the plain mean."""
         pol = self.models["policy"]
-        if getattr(pol, "recurrent", False):
-            raise NotImplementedError("evaluate_actions for recurrent nets runs inside the chunked update (orl_rnn_fwdbwd)")
+        if getattr(pol, "recurrent", False) or self.share_model:
+            raise NotImplementedError("evaluate_actions for recurrent / shared nets runs inside the fused update kernels")
         o = torch.as_tensor(obs, dtype=torch.float32).to(self.device).contiguous().view(-1, pol.obs_dim)
         rows = o.shape[0]
         gauss = pol.head_kind == lib.HEAD_GAUSSIAN
@@ -156,7 +175,10 @@ class PPOModule:
         a.action_masks, a.exp_noise = lib.ptr(am), lib.ptr(noise)
         a.rng_seed, a.rng_step_base = int(rng_seed), int(rng_step)
         a.head_kind = pol.head_kind
-        lib.check(self._lib.orl_rollout(a, lib.current_stream()), "orl_rollout(act)")
+        if self.share_model:
+            lib.check(self._lib.orl_share_rollout(a, lib.current_stream()), "orl_share_rollout(act)")
+        else:
+            lib.check(self._lib.orl_rollout(a, lib.current_stream()), "orl_rollout(act)")
         return actions, logp
 
     def _act_recurrent(self, pol, obs, rnn_states_actor, masks, deterministic, exp_noise, rng_seed, rng_step):

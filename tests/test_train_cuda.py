@@ -259,3 +259,49 @@ def test_cuda_graph_iterations_equal_eager_iterations(cuda, env_id, extra):
     for a, b in zip(out[0][2], out[1][2]):
         for k in a:
             np.testing.assert_allclose(a[k], b[k], rtol=1e-6, atol=1e-9, err_msg=k)
+
+
+def test_share_model_matches_reference_trace(cuda):
+    """cfg.use_share_model through the public API against the reference's trace (PolicyValueNetwork, one optimiser, double
+    clip_grad_norm_ over all parameters): bit-exact actions, the six scalars within 1e-4, parameters close."""
+    import torch
+
+    from openrl_b200.configs.config import create_config_parser
+    from openrl_b200.envs.common import make
+    from openrl_b200.modules.common import PPONet
+    from openrl_b200.runners.common import PPOAgent
+    from openrl_b200.utils.logger import Logger
+
+    d = np.load(os.path.join(GOLDEN, "trace_share_model.npz"), allow_pickle=True)
+    iters, N = int(d["meta/iters"]), int(d["meta/env_num"])
+    cfg = create_config_parser().parse_args(str(d["meta/flags"]).split() + ["--parity_mode", "true", "--log_interval", "1"])
+    cfg.quiet = True
+    env = make("CartPole-v1", env_num=N)
+    net = PPONet(env, cfg=cfg, device="cuda:0")
+    assert set(net.module.models) == {"model"} and set(net.module.optimizers) == {"model"}
+    sd = net.module.models["model"].state_dict()
+    for k in sd:                                   # same parameter tree as the reference, incl. the critic_obs_prep aliases
+        assert f"init/model.{k}" in d, k
+    for k in [x[len("init/model."):] for x in d.keys() if x.startswith("init/model.")]:
+        assert k in sd, k
+        np.testing.assert_allclose(sd[k].cpu().numpy(), d[f"init/model.{k}"], rtol=0, atol=2e-7, err_msg=k)   # same init stream
+        sd[k].copy_(torch.from_numpy(d[f"init/model.{k}"]))
+    agent = PPOAgent(net)
+    logger = Logger(quiet=True)
+    agent.train(total_time_steps=cfg.episode_length * N * iters, logger=logger)
+    logs = [h[1] for h in logger.history if "value_loss" in h[1]]
+    assert len(logs) == iters
+    for it in range(iters):
+        want = d[f"it{it}/updates"].mean(axis=0)
+        for col, name in enumerate(["value_loss", "critic_grad_norm", "policy_loss", "dist_entropy", "actor_grad_norm", "ratio"]):
+            np.testing.assert_allclose(logs[it][name], want[col], rtol=1e-4, atol=2e-6, err_msg=f"it{it} {name}")
+    b = agent.driver.buffer.data
+    assert np.array_equal(b.actions.cpu().numpy(), d[f"it{iters - 1}/actions"])
+    for k, v in net.module.models["model"].state_dict().items():
+        gk = f"it{iters - 1}/params/model.{k}"
+        np.testing.assert_allclose(v.cpu().numpy(), d[gk], rtol=2e-3, atol=0.1 * cfg.lr, err_msg=gk)
+    # act / get_values of the module read the shared net
+    obs, _ = env.reset(seed=3)
+    a1, _ = agent.act(obs, deterministic=True)
+    assert a1.shape == (N, 1, 1)
+    assert net.module.get_values(obs.reshape(N, -1)).shape == (N, 1)
