@@ -68,7 +68,10 @@ class OnPolicyDriver:
 
     # -- one captured CUDA graph per iteration -------------------------------------------------
     def _graph_ok(self):
-        return (bool(getattr(self.cfg, "use_cuda_graph", True)) and not self.cfg.parity_mode and self.callback is None
+        import os
+
+        return (bool(getattr(self.cfg, "use_cuda_graph", True)) and not os.environ.get("ORL_NO_GRAPH") and not self.cfg.parity_mode
+                and self.callback is None
                 and self.envs.kind != lib.ENV_NONE and self.phase_events is None and hasattr(self.envs, "statistics_device"))
 
     def _iteration_body(self):
@@ -107,8 +110,18 @@ class OnPolicyDriver:
                 return
             l0 = self.gpu_launches + self.trainer.gpu_launches
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            try:
+                with torch.cuda.graph(g):
+                    self._iteration_body()
+            except Exception as e:  # noqa: BLE001  (e.g. a collective that cannot be captured): stay eager for good
+                import warnings
+
+                warnings.warn(f"openrl_b200: CUDA-graph capture of the iteration failed ({type(e).__name__}: {e}); running eagerly")
+                self.cfg.use_cuda_graph = False
+                self.trainer._iter_graph = None
+                torch.cuda.synchronize()
                 self._iteration_body()
+                return
             st["launches"] = self.gpu_launches + self.trainer.gpu_launches - l0
             self.gpu_launches -= st["launches"]     # capture launched nothing
             st["graph"] = g
