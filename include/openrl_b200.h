@@ -356,6 +356,32 @@ int orl_rnn_fwdbwd(const OrlRnnArgs* args, void* stream);
 int orl_rnn_apply(const OrlRnnArgs* args, void* stream);
 
 
+/* ---- self-play: two-player GridWorld against an opponent pool in HBM -----------------------
+ * Replaces, for BASELINE configs[3], the self-play control flow of the reference around the rollout:
+ * OpponentPoolWrapper.reset / get_opponent_action / on_episode_end (openrl/selfplay/wrappers/opponent_pool_wrapper.py:
+ * 30-120), RandomOpponent / LastOpponent.sample_opponent (selfplay/sample_strategy/random_opponent.py:25-28,
+ * last_opponent.py:24-27); the snapshot cadence of SelfplayCallback._on_step (selfplay/callbacks/selfplay_callback.py:
+ * 124-144) is the host's job (it copies the learner's parameters into the pool ring and bumps *pool_count).
+ * The env (rules in csrc/orl_selfplay.cu and oracle/selfplay.py; new env): the learner is player 0 of a
+ * 10x10 two-player GridWorld and sees (x0, y0, x1, y1); player 1 is driven by the snapshot pool_params[opponent index]
+ * (same policy architecture, d = 4, n = 5) drawn per episode, or acts uniformly at random while the pool is empty.
+ * rollout.env_kind = ORL_ENV_GRIDWORLD_2P, rollout.env_i32 = [8][N] (x0, y0, x1, y1, steps, #resets, opponent, -),
+ * rollout.env_table = optional [N][len][4] start cells, rollout.deterministic bits: 1 = greedy learner, 2 = learner
+ * actions scripted from exp_noise[(t*N+e)*2 + 0], 4 = opponent actions scripted from exp_noise[(t*N+e)*2 + 1]. */
+#define ORL_ENV_GRIDWORLD_2P 4
+#define ORL_SP_RANDOM 0   /* RandomOpponent: uniform over the snapshots in the ring */
+#define ORL_SP_LAST 1     /* LastOpponent: the newest snapshot */
+typedef struct OrlSelfPlayArgs {
+    OrlRolloutArgs rollout;
+    const float* pool_params;    /* (pool_capacity, pool_stride) policy snapshots, flat parameter layout */
+    const int32_t* pool_count;   /* (1) device: number of snapshots ever added; ring slot of snapshot k = k % pool_capacity */
+    int32_t* pool_stats;         /* (pool_capacity + 1, 3) += wins / losses / draws of the training agent against each ring
+                                    slot (last row: the random-action opponent), opponent_pool_wrapper.py:91-120 */
+    int32_t pool_capacity, pool_stride, strategy, reserved;
+} OrlSelfPlayArgs;
+int orl_selfplay_reset(const OrlSelfPlayArgs* args, float* policy_obs_out, void* stream);
+int orl_selfplay_rollout(const OrlSelfPlayArgs* args, void* stream);
+
 /* ---- shared policy-value network (cfg.use_share_model) -----------------------------------
  * Replace, for cfg.use_share_model, PolicyValueNetwork (openrl/modules/networks/policy_value_network.py:33-174:
  * obs_prep MLPBase -> common MLPLayer(64, 64, layer_N=0) -> {v_out, act}) in the rollout (get_actions), the value pass

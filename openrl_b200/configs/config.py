@@ -60,6 +60,8 @@ FLAGS = [
     # replay one captured CUDA graph per iteration (rollout + critic + GAE + all updates + slot shift) instead of ~25
     # launches; used when no callback needs rollout hooks, outside parity_mode, on device-resident envs
     ("use_cuda_graph", _bool, True),
+    # self-play (GridWorldSelfPlay): every `selfplay_save_freq` iterations the policy is snapshotted into the opponent pool
+    ("selfplay_save_freq", int, 5),
     # host-stepped envs: step two env groups in ping-pong so that the device work of one overlaps the host stepping of the
     # other.  Pays off when env.step is slow relative to the per-step launch cost (MuJoCo-class); for cheap host envs the
     # doubled launch count costs more than the overlap hides (bench extras, c5: 54 ms vs 44 ms per iteration), so off by default

@@ -66,13 +66,13 @@ __device__ __forceinline__ FwdCtx fwd_setup(uint8_t* smem, const float* __restri
     const NetOffsets po = net_offsets(d, n);
     for (int i = tid; i < 8 * H; i += F_NT) { const int k = i / H, j = i % H; c.w1t[i] = (k < d) ? params[po.w1 + j * d + k] : 0.f; }
     for (int i = tid; i < H; i += F_NT) c.b1s[i] = params[po.b1 + i];
-    for (int i = tid; i < H * H / 2; i += F_NT) {
-        const int j = (2 * i) / H, k = (2 * i) % H;
-        uint32_t hi, lo;
-        split2(params[po.w3 + 2 * i] * params[po.g1 + k], params[po.w3 + 2 * i + 1] * params[po.g1 + k + 1], hi, lo);
-        const uint32_t off = (uint32_t)(k >> 3) * FPANEL_W + j * 16 + (k & 7) * 2;
-        *reinterpret_cast<uint32_t*>(Wh + off) = hi;
-        *reinterpret_cast<uint32_t*>(Wl + off) = lo;
+    for (int i = tid; i < H * 8; i += F_NT) {   // item = (panel p, row j): lanes own consecutive rows -> conflict-free 16-byte stores
+        const int pnl = i / H, j = i % H;
+        float w8[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) w8[c] = params[po.w3 + j * H + 8 * pnl + c] * params[po.g1 + 8 * pnl + c];
+        const uint32_t off = (uint32_t)pnl * FPANEL_W + j * 16;
+        split_store8(Wh + off, Wl + off, w8, 1.0f);
     }
     for (int i = tid; i < MAX_OUT * H; i += F_NT) { const int j = i / H, k = i % H; c.whf[i] = (j < n) ? params[po.wh + j * H + k] * params[po.g3 + k] : 0.f; }
     for (int j = tid; j < H; j += F_NT) {

@@ -66,6 +66,14 @@ class OnPolicyDriver:
         d.masks[0].fill_(1.0)
         d.active_masks[0].fill_(1.0)
 
+    def _selfplay_snapshot(self):
+        """SelfplayCallback._on_step cadence (selfplay_callback.py:124-144): every `selfplay_save_freq` iterations the learner's
+        current policy becomes the newest opponent of the pool (device copy; a captured graph sees it on its next replay)."""
+        pool = getattr(self.envs, "opponent_pool", None)
+        freq = int(getattr(self.cfg, "selfplay_save_freq", 5))
+        if pool is not None and freq > 0 and (self.episode + 1) % freq == 0:
+            pool.add(self.trainer.algo_module.models["policy"].flat_params, self.agent.num_time_steps)
+
     # -- one captured CUDA graph per iteration -------------------------------------------------
     def _graph_ok(self):
         import os
@@ -141,6 +149,7 @@ class OnPolicyDriver:
         self.graph_iteration()
         T, N = self.episode_length, self.envs.parallel_env_num
         self.agent.num_time_steps += N * T
+        self._selfplay_snapshot()
         self.total_num_steps = (self.episode + 1) * T * self.n_rollout_threads
         if self.episode % self.log_interval == 0 and self.logger is not None:
             vals = self._read_graph_stats()        # the only device -> host read of the iteration
@@ -163,6 +172,7 @@ class OnPolicyDriver:
             return False
         train_infos = self.learner_update()
         self.buffer.after_update()
+        self._selfplay_snapshot()
         self.total_num_steps = (self.episode + 1) * self.episode_length * self.n_rollout_threads
         if self.episode % self.log_interval == 0 and self.logger is not None:
             self.logger.log_info(rollout_infos, step=self.total_num_steps)
@@ -264,6 +274,12 @@ class OnPolicyDriver:
         s = lib.current_stream()
         if self.recurrent:
             lib.check(self._lib.orl_rnn_rollout(self._rnn_args(t_begin, t_end, noise), s), "orl_rnn_rollout")
+            self.gpu_launches += 2
+        elif self.envs.kind == lib.ENV_GRIDWORLD_2P:
+            if getattr(self.trainer, "share", False) or noise is not None:
+                raise NotImplementedError("the self-play rollout is built for the two-net MLP policy with device sampling")
+            sp = self.envs.selfplay_args(self._rollout_args(t_begin, t_end, None))
+            lib.check(self._lib.orl_selfplay_rollout(sp, s), "orl_selfplay_rollout")
             self.gpu_launches += 2
         elif getattr(self.trainer, "share", False):
             lib.check(self._lib.orl_share_rollout(self._rollout_args(t_begin, t_end, noise), s), "orl_share_rollout")

@@ -20,7 +20,13 @@ def _mpe_space():
                         "critic": spaces.Box(-np.inf, np.inf, (54,), np.float32)})
 
 
+def _gridworld2p_space():
+    # (x0, y0, x1, y1) of the two players on the 10x10 grid (csrc/orl_selfplay.cu)
+    return spaces.Box(low=np.array([0, 0, 0, 0]), high=np.array([9, 9, 9, 9]), dtype=np.int64)
+
+
 ENV_SPECS = {
+    "GridWorldSelfPlay": dict(kind=lib.ENV_GRIDWORLD_2P, agents=1, obs_dim=4, n_actions=5, i32_rows=8, observation_space=_gridworld2p_space),
     "simple_spread": dict(kind=lib.ENV_MPE_SPREAD, agents=3, obs_dim=18, critic_obs_dim=54, n_actions=5,
                           f64_rows=18, observation_space=_mpe_space),
     "CartPole-v1": dict(kind=lib.ENV_CARTPOLE, agents=1, obs_dim=4, n_actions=2, observation_space=_cartpole_space),

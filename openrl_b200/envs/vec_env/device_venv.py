@@ -36,7 +36,8 @@ def _pcg64_streams(seed, n, index_offset=0):
 
 
 class DeviceVecEnv:
-    def __init__(self, env_id, env_num, device="cuda:0", seed=None, reset_table=None, env_index_offset=0):
+    def __init__(self, env_id, env_num, device="cuda:0", seed=None, reset_table=None, env_index_offset=0, opponent_pool_size=8,
+                 opponent_strategy="RandomOpponent"):
         spec = _kinds.ENV_SPECS[env_id]
         self.env_name = env_id
         # global index of env 0 when a larger vec-env is sharded over ranks (multi-GPU): env i is seeded
@@ -57,14 +58,20 @@ class DeviceVecEnv:
         dev = self.device
         self.env_f64 = torch.zeros(spec.get("f64_rows", 4), N, dtype=torch.float64, device=dev)
         self.env_u64 = torch.zeros(4, N, dtype=torch.int64, device=dev)  # bit pattern of uint64
-        self.env_i32 = torch.zeros(4, N, dtype=torch.int32, device=dev)
+        self.env_i32 = torch.zeros(spec.get("i32_rows", 4), N, dtype=torch.int32, device=dev)
         self.ep_return = torch.zeros(N, dtype=torch.float32, device=dev)
         self.ep_length = torch.zeros(N, dtype=torch.int32, device=dev)
         self.episode_stats = torch.zeros(4, dtype=torch.float64, device=dev)
         self.rng_seed = 0
         self.env_table = None
         self.env_table_len = 0
-        if reset_table is not None:  # (N, K, 2) int start cells for GridWorld parity runs
+        self.opponent_pool = None
+        if self.kind == lib.ENV_GRIDWORLD_2P:
+            from ...selfplay import OpponentPool
+
+            n_params = int(self._lib.orl_net_param_count(self.obs_dim, self.n_actions))
+            self.opponent_pool = OpponentPool(opponent_pool_size, n_params, opponent_strategy, device=dev)
+        if reset_table is not None:  # (N, K, 2) int start cells for GridWorld parity runs ((N, K, 4) for the 2-player grid)
             t = torch.as_tensor(np.asarray(reset_table), dtype=torch.int32).contiguous()
             self.env_table = t.to(dev)
             self.env_table_len = int(t.shape[1])
@@ -101,6 +108,13 @@ class DeviceVecEnv:
         L = self._lib
         if self._critic_obs is not None and critic_obs_out is None:
             critic_obs_out = self._critic_obs
+        if self.kind == lib.ENV_GRIDWORLD_2P:
+            lib.check(L.orl_selfplay_reset(self.selfplay_args(), lib.ptr(obs_out), lib.current_stream()), "orl_selfplay_reset")
+            self.ep_return.zero_()
+            self.ep_length.zero_()
+            if obs_out.data_ptr() != self._obs.data_ptr():
+                self._obs.copy_(obs_out.view_as(self._obs))
+            return
         lib.check(L.orl_env_reset(self.kind, self.parallel_env_num, self.agent_num, lib.ptr(self.env_f64),
                                   lib.ptr(self.env_u64), lib.ptr(self.env_i32), lib.ptr(self.env_table),
                                   self.env_table_len, self.rng_seed, lib.ptr(obs_out), lib.ptr(critic_obs_out),
@@ -112,8 +126,56 @@ class DeviceVecEnv:
         if critic_obs_out is not None and critic_obs_out.data_ptr() != self._critic_obs.data_ptr():
             self._critic_obs.copy_(critic_obs_out.view_as(self._critic_obs))
 
+    # -- self-play (ENV_GRIDWORLD_2P) ----------------------------------------------------------
+    def selfplay_args(self, rollout=None):
+        """OrlSelfPlayArgs around `rollout` (an OrlRolloutArgs; a minimal one for reset when None)."""
+        s = lib.OrlSelfPlayArgs()
+        a = rollout if rollout is not None else lib.OrlRolloutArgs()
+        if rollout is None:
+            a.env_kind, a.n_envs, a.n_agents = self.kind, self.parallel_env_num, 1
+            a.obs_dim, a.n_actions = self.obs_dim, self.n_actions
+            a.env_i32, a.env_table, a.env_table_len = lib.ptr(self.env_i32), lib.ptr(self.env_table), self.env_table_len
+            a.rng_seed, a.rng_row_offset = self.rng_seed, self.env_index_offset
+        s.rollout = a
+        p = self.opponent_pool
+        s.pool_params, s.pool_count, s.pool_stats = lib.ptr(p.params), lib.ptr(p.count_dev), lib.ptr(p.stats)
+        s.pool_capacity, s.pool_stride, s.strategy = p.capacity, p.stride, p.strategy
+        return s
+
+    def _selfplay_step(self, actions):
+        """vec-env step API for the 2-player grid: the learner's actions are given, the opponent acts from the pool.  Runs the
+        rollout kernel for one step on a two-slot scratch buffer (policy parameters are not needed: actions are scripted)."""
+        N = self.parallel_env_num
+        dev = self.device
+        if getattr(self, "_sp_scratch", None) is None:
+            z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)   # noqa: E731
+            n_params = int(self._lib.orl_net_param_count(self.obs_dim, self.n_actions))
+            self._sp_scratch = dict(obs=z(2, N, 4), act=z(1, N), logp=z(1, N), rew=z(1, N), masks=z(2, N), active=z(2, N), scripted=z(1, N, 2),
+                                    params=z(n_params))
+        sc = self._sp_scratch
+        sc["obs"][0].copy_(self._obs.view(N, 4))
+        sc["scripted"][0, :, 0].copy_(torch.as_tensor(np.asarray(actions, dtype=np.float32).reshape(N)).to(dev))
+        a = lib.OrlRolloutArgs()
+        a.env_kind, a.n_envs, a.n_agents, a.episode_length = self.kind, N, 1, 1
+        a.t_begin, a.t_end, a.obs_dim, a.n_actions, a.activation_id, a.deterministic = 0, 1, 4, self.n_actions, 1, 2
+        a.policy_params, a.policy_obs = lib.ptr(sc["params"]), lib.ptr(sc["obs"])
+        a.actions, a.action_log_probs, a.rewards = lib.ptr(sc["act"]), lib.ptr(sc["logp"]), lib.ptr(sc["rew"])
+        a.masks, a.active_masks, a.exp_noise = lib.ptr(sc["masks"]), lib.ptr(sc["active"]), lib.ptr(sc["scripted"])
+        self._sp_steps = getattr(self, "_sp_steps", 0) + 1
+        a.rng_seed, a.rng_step_base, a.rng_row_offset = self.rng_seed, (1 << 40) + self._sp_steps, self.env_index_offset
+        a.env_i32, a.env_table, a.env_table_len = lib.ptr(self.env_i32), lib.ptr(self.env_table), self.env_table_len
+        a.ep_return, a.ep_length, a.episode_stats = lib.ptr(self.ep_return), lib.ptr(self.ep_length), lib.ptr(self.episode_stats)
+        lib.check(self._lib.orl_selfplay_rollout(self.selfplay_args(a), lib.current_stream()), "orl_selfplay_rollout(step)")
+        self._obs.view(N, 4).copy_(sc["obs"][1])
+        obs = self._host_obs()
+        dones = (sc["masks"][1].cpu().numpy() == 0).reshape(N, 1)
+        rewards = sc["rew"][0].cpu().numpy().astype(np.float64).reshape(N, 1, 1)
+        return obs, rewards, dones, [{} for _ in range(N)]
+
     # -- plain step API (evaluation loops; the training loop uses the fused rollout) ---------
     def step(self, actions, extra_data=None):
+        if self.kind == lib.ENV_GRIDWORLD_2P:
+            return self._selfplay_step(actions)
         N, A = self.parallel_env_num, self.agent_num
         act = torch.as_tensor(np.asarray(actions, dtype=np.float32).reshape(N * A)).to(self.device)
         rew = torch.empty(N * A, dtype=torch.float32, device=self.device)

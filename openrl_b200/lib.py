@@ -113,6 +113,14 @@ class OrlRolloutArgs(ctypes.Structure):
     ]
 
 
+class OrlSelfPlayArgs(ctypes.Structure):
+    _fields_ = [
+        ("rollout", OrlRolloutArgs),
+        ("pool_params", _P), ("pool_count", _P), ("pool_stats", _P),
+        ("pool_capacity", _c.c_int32), ("pool_stride", _c.c_int32), ("strategy", _c.c_int32), ("reserved", _c.c_int32),
+    ]
+
+
 class OrlPpoArgs(ctypes.Structure):
     _fields_ = [
         ("obs_dim", _c.c_int32), ("critic_obs_dim", _c.c_int32), ("n_actions", _c.c_int32),
@@ -139,6 +147,8 @@ _SIGNATURES.update({
     "orl_rollout": [_c.POINTER(OrlRolloutArgs), _P],
     "orl_env_step": [_I, _I, _I, _P, _P, _P, _P, _I, _c.c_uint64, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "orl_critic_values": [_P, _I, _I, _P, _P, _L, _P],
+    "orl_selfplay_reset": [_c.POINTER(OrlSelfPlayArgs), _P, _P],
+    "orl_selfplay_rollout": [_c.POINTER(OrlSelfPlayArgs), _P],
     "orl_share_param_count": [_I, _I],
     "orl_share_tape_width": [],
     "orl_share_workspace_floats": [_L, _I, _I],
@@ -197,7 +207,8 @@ _SIGNATURES.update({
     "orl_rnn_apply": [_c.POINTER(OrlRnnArgs), _P],
 })
 
-ENV_NONE, ENV_CARTPOLE, ENV_GRIDWORLD, ENV_MPE_SPREAD = 0, 1, 2, 3
+ENV_NONE, ENV_CARTPOLE, ENV_GRIDWORLD, ENV_MPE_SPREAD, ENV_GRIDWORLD_2P = 0, 1, 2, 3, 4
+SP_RANDOM, SP_LAST = 0, 1
 HEAD_CATEGORICAL, HEAD_GAUSSIAN = 0, 1
 GAE_USE_GAE, GAE_PROPER_TIME_LIMITS, GAE_DENORM = 1, 2, 4
 PPO_HUBER, PPO_CLIP_VALUE, PPO_VALUE_ACTIVE_MASKS, PPO_POLICY_ACTIVE_MASKS = 1, 2, 4, 8
