@@ -98,6 +98,7 @@ WORKLOADS = {
     "c2": dict(env="CartPole-v1", envs=N_ENVS, T=T, flags=FLAGS),
     "c1": dict(env="CartPole-v1", envs=8, T=T, flags=FLAGS),
     "target128": dict(env="CartPole-v1", envs=128, T=T, flags=FLAGS),   # north_star's 128-env target point
+    "c4": dict(env="GridWorldSelfPlay", envs=N_ENVS, T=T, flags=FLAGS + ["--selfplay_save_freq", "2"]),   # configs[3]: 2-player GridWorld vs opponent pool
     "c3": dict(env="simple_spread", envs=2048, T=25,
                flags=["--seed", "0", "--episode_length", "25", "--lr", "7e-4", "--critic_lr", "7e-4", "--use_recurrent_policy", "true",
                       "--use_valuenorm", "true", "--use_adv_normalize", "true", "--log_interval", "1000000", "--log_each_episode", "false"]),
@@ -413,6 +414,7 @@ def run_ours(args):
         guarded("target_128_envs", lambda: side_result(0, 1, flush, "target128", 10))
         guarded("c1_8_envs", lambda: side_result(0, 1, flush, "c1", 10))
         guarded("c3_mpe_gru_2048x3", lambda: side_result(0, 1, flush, "c3", 3, e2e=False))
+        guarded("c4_selfplay_gridworld_4096", lambda: side_result(0, 1, flush, "c4", 5, e2e=False))
         guarded("c5_host_env_1024", lambda: c5_result(3))
         guarded("c5_host_env_1024_synchronous_ingest", lambda: c5_result(3, grouped=False))
     print("[bench] cpu baseline ...", file=sys.stderr, flush=True)

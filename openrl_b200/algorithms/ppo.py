@@ -30,7 +30,10 @@ class PPOAlgorithm:
         self.d, self.dc, self.n = pol.obs_dim, cri.obs_dim, pol.n_actions
         self.stride = self._lib.orl_ppo_stride(self.d, self.dc, self.n)
         self.head_kind = pol.head_kind
-        self.recurrent = bool(cfg.use_recurrent_policy)
+        self.recurrent = bool(cfg.use_recurrent_policy or getattr(cfg, "use_naive_recurrent_policy", False))
+        # naive_recurrent_generator (replay_data.py:806-946) == chunks of the WHOLE trajectory: chunk length = episode_length,
+        # chunk c = buffer row c, one randperm over rows per epoch (ppo.py:363-381: taken only when use_recurrent_policy is off)
+        self.naive = bool(getattr(cfg, "use_naive_recurrent_policy", False)) and not cfg.use_recurrent_policy
         # tensor-core update (tcgen05, split fp16, fp32-class accuracy): Categorical heads, obs widths <= 8
         self.use_tensor_cores = (bool(getattr(cfg, "use_tensor_cores", True)) and bool(getattr(cfg, "use_tf32", True))
                                  and max(self.d, self.dc) <= 8 and self.head_kind == lib.HEAD_CATEGORICAL and not self.recurrent)
@@ -39,7 +42,8 @@ class PPOAlgorithm:
         self.grid_per_net = max(1, sm if self.use_tensor_cores else sm // 2)
         dev = self.device
         self.partials = torch.zeros(2 * self.grid_per_net, self.stride, dtype=torch.float32, device=dev)
-        self.folded = torch.zeros(2, self.stride, dtype=torch.float32, device=dev)
+        # the gradient bucket that is all-reduced once per update (symmetric memory over NVLink when > 1 GPU)
+        self.folded, self.folded_sum = parallel.symmetric_buffer((2, self.stride), torch.float32, dev)
         self.grads_stride = self._lib.orl_ppo_grads_stride(self.d, self.dc, self.n)
         self.grads = torch.zeros(2, self.grads_stride, dtype=torch.float32, device=dev)
         self.train_info = torch.zeros(6, dtype=torch.float32, device=dev)
@@ -70,14 +74,16 @@ class PPOAlgorithm:
             self.share_loss = self.share_bucket[(self.share_total + 3) & ~3:]
             self.share_ws = None
         for name in ("use_joint_action_loss", "use_policy_vhead",
-                     "use_amp", "use_deepspeed", "use_naive_recurrent_policy"):
+                     "use_amp", "use_deepspeed"):
             if getattr(cfg, name, False):
                 raise NotImplementedError(f"cfg.{name} is not built into the CUDA update yet (SURVEY.md §8f)")
         if self.recurrent:
             if self.head_kind != lib.HEAD_CATEGORICAL:
                 raise NotImplementedError("recurrent policies are built for Discrete action spaces")
-            if not 1 <= cfg.data_chunk_length <= 32:
-                raise NotImplementedError("data_chunk_length must be in [1, 32] for the recurrent kernels")
+            self.chunk_length = cfg.episode_length if self.naive else cfg.data_chunk_length
+            if not 1 <= self.chunk_length <= 32:
+                raise NotImplementedError("the recurrent kernels take chunks of 1..32 steps (data_chunk_length, or episode_length "
+                                          "with use_naive_recurrent_policy)")
             self.rnn_stride = (max(self._lib.orl_rnn_param_count(self.d, self.n), self._lib.orl_rnn_param_count(self.dc, 1)) + 3) & ~3
             # one bucket = gradients of both nets + the loss sums: a single all-reduce per update with >1 GPU
             self.rnn_bucket = torch.zeros(2 * self.rnn_stride + 8, dtype=torch.float32, device=dev)
@@ -160,7 +166,8 @@ class PPOAlgorithm:
         a.mb_stats = lib.ptr(mb_stats)
         lib.check(L.orl_ppo_fwdbwd(a, s), "orl_ppo_fwdbwd")
         lib.check(L.orl_ppo_reduce(a, s), "orl_ppo_reduce")
-        parallel.allreduce_sum_(self.folded)  # the single gradient-bucket all-reduce of the update
+        summed = parallel.allreduce_sum_into(self.folded)  # the single gradient-bucket all-reduce of the update
+        a.folded = lib.ptr(summed)
         lib.check(L.orl_ppo_apply(a, s), "orl_ppo_apply")
         self.gpu_launches += 3
 
@@ -172,7 +179,7 @@ class PPOAlgorithm:
         a = lib.OrlRnnArgs()
         a.n_envs, a.n_agents, a.episode_length = buf.n_rollout_threads, buf.num_agents, buf.episode_length
         a.obs_dim, a.critic_obs_dim, a.n_actions, a.activation_id = self.d, self.dc, self.n, pol.activation_id
-        a.chunk_length, a.flags = cfg.data_chunk_length, self.flags
+        a.chunk_length, a.flags = self.chunk_length, self.flags
         a.n_chunks, a.chunk_ids = int(chunk_ids.numel()), lib.ptr(chunk_ids)
         a.policy_params, a.critic_params = lib.ptr(pol.flat_params), lib.ptr(cri.flat_params)
         a.policy_obs, a.critic_obs = lib.ptr(buf.policy_obs), lib.ptr(buf.critic_obs)
@@ -194,7 +201,7 @@ class PPOAlgorithm:
         a.dual_clip_coeff = float(getattr(cfg, "dual_clip_coeff", 3.0))
         a.vn_beta = 0.99999 if vn is None else vn.beta
         a.train_info = lib.ptr(self.train_info)
-        rows = int(chunk_ids.numel()) * cfg.data_chunk_length
+        rows = int(chunk_ids.numel()) * self.chunk_length
         a.norm_rows = rows * self.world_size if self.world_size > 1 else 0
         return a
 
@@ -204,7 +211,7 @@ class PPOAlgorithm:
         a minibatch is a slice of chunk ids, gathered inside the kernels."""
         cfg = self.cfg
         T, B = buf.episode_length, buf.n_rollout_threads * buf.num_agents
-        total, L = T * B, cfg.data_chunk_length
+        total, L = T * B, (T if self.naive else cfg.data_chunk_length)
         if total < L:
             raise AssertionError(f"PPO requires the number of processes ({buf.n_rollout_threads}) * episode length ({T}) "
                                  f"* agents to be greater than or equal to the data chunk length ({L}).")

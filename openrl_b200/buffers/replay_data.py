@@ -66,7 +66,7 @@ class ReplayData:
         self.advantages = f(T, N, A, 1)  # raw returns - V, written by the GAE kernel (ppo.py:384-399)
         self.gae_stats = torch.zeros(8, dtype=torch.float64, device=self.device)
         # hidden states, one per (slot, row): replay_data.py:96-111.  (T+1, N, A, recurrent_N, H)
-        self.recurrent = bool(cfg.use_recurrent_policy)
+        self.recurrent = bool(cfg.use_recurrent_policy or getattr(cfg, "use_naive_recurrent_policy", False))
         if self.recurrent:
             self.rnn_states = f(T + 1, N, A, cfg.recurrent_N, cfg.hidden_size)
             self.rnn_states_critic = f(T + 1, N, A, cfg.recurrent_N, cfg.hidden_size)

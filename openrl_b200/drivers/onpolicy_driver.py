@@ -43,7 +43,7 @@ class OnPolicyDriver:
         self.h2d_bytes = 0
         self.d2h_bytes = 0
         self.phase_events = None  # set to a list by bench.py to collect (name, start, end) CUDA events
-        self.recurrent = bool(cfg.use_recurrent_policy)
+        self.recurrent = bool(cfg.use_recurrent_policy or getattr(cfg, "use_naive_recurrent_policy", False))
         if self.recurrent and self.envs.kind == lib.ENV_NONE:
             raise NotImplementedError("recurrent policies need a device env (CartPole-v1, GridWorldEnv, simple_spread)")
 
@@ -193,13 +193,15 @@ class OnPolicyDriver:
         if self._graph_ok():
             self.graph_iteration()
             self.agent.num_time_steps += self.envs.parallel_env_num * self.episode_length
-            return
-        self._rollout_launch()
-        self.compute_returns()
-        with self._phase("update"):
-            self.trainer.train_async(self.buffer.data)
-        with self._phase("after_update"):
-            self.buffer.after_update()
+        else:
+            self._rollout_launch()
+            self.compute_returns()
+            with self._phase("update"):
+                self.trainer.train_async(self.buffer.data)
+            with self._phase("after_update"):
+                self.buffer.after_update()
+        self._selfplay_snapshot()
+        self.episode += 1
 
     class _Phase:
         def __init__(self, drv, name):

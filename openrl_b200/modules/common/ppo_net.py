@@ -32,7 +32,7 @@ class PPONet:
         self.rnn_states_actor, self.masks = None, None
 
     def act(self, observation, action_masks=None, deterministic=False, episode_starts=None):
-        if self.cfg.use_recurrent_policy:
+        if self.cfg.use_recurrent_policy or self.cfg.use_naive_recurrent_policy:
             if episode_starts is not None and self.rnn_states_actor is not None:
                 # reset_rnn_states (ppo_net.py:33-47): zero the hidden state of every agent of a restarted env
                 keep = 1.0 - np.repeat(np.asarray(episode_starts, dtype=np.float32), self.env.agent_num)

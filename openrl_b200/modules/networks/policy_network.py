@@ -12,10 +12,8 @@ def _policy_shape(space):
 class PolicyNetwork(nn.Module):
     def __init__(self, cfg, input_space, action_space, device=torch.device("cpu"), use_half=False, extra_args=None):
         super().__init__()
-        if cfg.use_naive_recurrent_policy:
-            raise NotImplementedError("use_naive_recurrent_policy (whole-trajectory BPTT) is not built; "
-                                      "use_recurrent_policy (chunked) is")
-        self.recurrent = bool(cfg.use_recurrent_policy)
+        # `_use_naive_recurrent_policy or _use_recurrent_policy` (policy_network.py:88-97): same RNNLayer either way
+        self.recurrent = bool(cfg.use_recurrent_policy or cfg.use_naive_recurrent_policy)
         self.hidden_size = cfg.hidden_size
         shape = _policy_shape(input_space)
         if len(shape) != 1 or shape[0] > 64:

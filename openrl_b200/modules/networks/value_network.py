@@ -13,10 +13,7 @@ def _critic_shape(space):
 class ValueNetwork(nn.Module):
     def __init__(self, cfg, input_space, action_space=None, use_half=False, device=torch.device("cpu"), extra_args=None):
         super().__init__()
-        if cfg.use_naive_recurrent_policy:
-            raise NotImplementedError("use_naive_recurrent_policy (whole-trajectory BPTT) is not built; "
-                                      "use_recurrent_policy (chunked) is")
-        self.recurrent = bool(cfg.use_recurrent_policy)
+        self.recurrent = bool(cfg.use_recurrent_policy or cfg.use_naive_recurrent_policy)
         shape = _critic_shape(input_space)
         if len(shape) != 1 or shape[0] > 64:
             raise NotImplementedError("vector observations of width <= 64 only")

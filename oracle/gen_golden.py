@@ -122,6 +122,7 @@ def gen_trace(env_id, env_num, flags, iters, tag, algo="ppo", ref_flags=None):
     orig_ppo_update = PPOAlgorithm.ppo_update
     orig_ffg = ReplayData.feed_forward_generator
     orig_rg = ReplayData.recurrent_generator
+    orig_ng = ReplayData.naive_recurrent_generator
     updates = []
 
     def compute_returns(self):
@@ -138,7 +139,7 @@ def gen_trace(env_id, env_num, flags, iters, tag, algo="ppo", ref_flags=None):
         else:
             rec[f"it{it}/policy_obs"] = d.policy_obs["policy"].copy()
             rec[f"it{it}/critic_obs"] = d.critic_obs["critic"].copy()
-        if cfg.use_recurrent_policy:
+        if cfg.use_recurrent_policy or cfg.use_naive_recurrent_policy:
             rec[f"it{it}/rnn_states"] = d.rnn_states.copy()
             rec[f"it{it}/rnn_states_critic"] = d.rnn_states_critic.copy()
         vn = self.trainer.algo_module.get_critic_value_normalizer()
@@ -163,6 +164,10 @@ def gen_trace(env_id, env_num, flags, iters, tag, algo="ppo", ref_flags=None):
         rec.setdefault(f"it{state['it']}/advantages", advantages.copy())
         return orig_rg(self, advantages, *a, **k)
 
+    def ng(self, advantages, *a, **k):
+        rec.setdefault(f"it{state['it']}/advantages", advantages.copy())
+        return orig_ng(self, advantages, *a, **k)
+
     orig_inner = OnPolicyDriver._inner_loop
 
     def inner(self):
@@ -185,6 +190,7 @@ def gen_trace(env_id, env_num, flags, iters, tag, algo="ppo", ref_flags=None):
     PPOAlgorithm.ppo_update = ppo_update
     ReplayData.feed_forward_generator = ffg
     ReplayData.recurrent_generator = rg
+    ReplayData.naive_recurrent_generator = ng
     OnPolicyDriver._inner_loop = inner
     try:
         if algo == "a2c":   # the reference's A2CAgent.train == PPOAgent.train(train_algo_class=A2CAlgorithm) (a2c_agent.py:66-77)
@@ -198,6 +204,7 @@ def gen_trace(env_id, env_num, flags, iters, tag, algo="ppo", ref_flags=None):
         PPOAlgorithm.ppo_update = orig_ppo_update
         ReplayData.feed_forward_generator = orig_ffg
         ReplayData.recurrent_generator = orig_rg
+        ReplayData.naive_recurrent_generator = orig_ng
         OnPolicyDriver._inner_loop = orig_inner
         torch.randperm = orig_randperm
     env.close()
@@ -242,6 +249,12 @@ def main():
                   ["--seed", "0", "--episode_length", "32", "--ppo_epoch", "2", "--num_mini_batch", "2",
                    "--use_recurrent_policy", "true", "--data_chunk_length", "4", "--log_interval", "1000"],
                   2, "cartpole_gru")
+    if a.only in ("", "mpe_naive_gru"):
+        # whole-trajectory BPTT (naive_recurrent_generator, replay_data.py:806-946): minibatches of (env, agent) rows
+        gen_trace("simple_spread", 4,
+                  ["--seed", "0", "--episode_length", "25", "--ppo_epoch", "2", "--num_mini_batch", "2", "--lr", "7e-4", "--critic_lr", "7e-4",
+                   "--use_naive_recurrent_policy", "true", "--use_valuenorm", "true", "--use_adv_normalize", "true", "--log_interval", "1000"],
+                  2, "mpe_naive_gru")
     if a.only in ("", "gaussian"):
         gen_trace("IdentityEnvcontinuous", 4,
                   ["--seed", "0", "--episode_length", "16", "--ppo_epoch", "2", "--num_mini_batch", "2", "--log_interval", "1000"],

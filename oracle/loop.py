@@ -30,7 +30,7 @@ DEFAULTS = dict(
     max_grad_norm=10.0, use_gae=True, gamma=0.99, gae_lambda=0.95, use_proper_time_limits=False,
     use_huber_loss=True, huber_delta=10.0, use_value_active_masks=True, use_policy_active_masks=True,
     use_adv_normalize=False, use_valuenorm=True, use_popart=False, dual_clip_ppo=False, dual_clip_coeff=3.0,
-    a2c=False, use_share_model=False,
+    a2c=False, use_share_model=False, use_naive_recurrent_policy=False,
 )
 
 

@@ -61,7 +61,7 @@ class MATrainer:
 
     def rollout(self):
         cfg, b, N, A = self.cfg, self.buf, self.N, self.A
-        rec = cfg.use_recurrent_policy
+        rec = nets.is_recurrent(cfg)
         for step in range(cfg.episode_length):
             with torch.no_grad():
                 cat = lambda x: torch.from_numpy(np.concatenate(x))  # noqa: E731
@@ -95,7 +95,7 @@ class MATrainer:
     def compute_returns(self):
         cfg, b = self.cfg, self.buf
         with torch.no_grad():
-            hc = torch.from_numpy(np.concatenate(b.rnn_states_critic[-1])) if cfg.use_recurrent_policy else None
+            hc = torch.from_numpy(np.concatenate(b.rnn_states_critic[-1])) if nets.is_recurrent(cfg) else None
             nv, _ = nets.critic_forward(self.cri, cfg, torch.from_numpy(np.concatenate(b.critic_obs[-1])), hc,
                                         torch.from_numpy(np.concatenate(b.masks[-1])))
         nv = nv.numpy().reshape(self.N, self.A, 1)
@@ -127,6 +127,30 @@ class MATrainer:
             out["rnn_states_critic"] = torch.from_numpy(np.stack([hc[c * L] for c in idx]))
             yield rand, out
 
+    def _naive_batches(self, adv):
+        """naive_recurrent_generator (replay_data.py:806-946): a minibatch is a set of (env, agent) rows with their WHOLE
+        trajectories (T steps, time-major), initial hidden state = slot 0."""
+        cfg, b = self.cfg, self.buf
+        T, N, A = b.rewards.shape[:3]
+        B = N * A
+        per = B // cfg.num_mini_batch
+        perm = torch.randperm(B).numpy()
+        col = lambda x: x.reshape(x.shape[0], B, *x.shape[3:])   # noqa: E731
+        arrs = {k: col(getattr(b, k)) for k in ("policy_obs", "critic_obs", "actions", "action_log_probs", "value_preds", "returns",
+                                                 "masks", "active_masks", "action_masks", "rnn_states", "rnn_states_critic")}
+        arrs["adv"] = col(adv)
+        for start in range(0, B, per):
+            ids = perm[start:start + per]
+            if len(ids) < per:
+                break
+            out = {}
+            for k in ("policy_obs", "critic_obs", "actions", "action_log_probs", "value_preds", "returns", "masks", "active_masks", "action_masks", "adv"):
+                st = arrs[k][:T][:, ids]                       # (T, k, d): every step of the chosen rows
+                out[k] = torch.from_numpy(np.ascontiguousarray(st).reshape(T * len(ids), *st.shape[2:]))
+            out["rnn_states"] = torch.from_numpy(np.ascontiguousarray(arrs["rnn_states"][0][ids]))
+            out["rnn_states_critic"] = torch.from_numpy(np.ascontiguousarray(arrs["rnn_states_critic"][0][ids]))
+            yield perm, out
+
     def train(self):
         cfg, b = self.cfg, self.buf
         vn_state = self.vn.state() if self.vn is not None else None
@@ -135,8 +159,9 @@ class MATrainer:
         updates, perms = [], []
         T, N, A = b.rewards.shape[:3]
         for _ in range(cfg.ppo_epoch):
-            if cfg.use_recurrent_policy:
-                for rand, bt in self._recurrent_batches(adv):
+            if cfg.use_recurrent_policy or getattr(cfg, "use_naive_recurrent_policy", False):
+                gen = self._recurrent_batches(adv) if cfg.use_recurrent_policy else self._naive_batches(adv)   # ppo.py:363-381
+                for rand, bt in gen:
                     batch = dict(critic_obs=bt["critic_obs"], policy_obs=bt["policy_obs"], actions=bt["actions"],
                                  value_preds=bt["value_preds"], returns=bt["returns"], active_masks=bt["active_masks"],
                                  old_logp=bt["action_log_probs"], adv=bt["adv"], action_masks=bt["action_masks"],

@@ -77,7 +77,7 @@ def init_policy(cfg, obs_dim, act_kind, act_dim):
     p = {}
     init_mlp_base(p, "base", obs_dim, cfg.hidden_size, cfg.layer_N, cfg.activation_id,
                   cfg.use_feature_normalization)
-    if cfg.use_recurrent_policy:
+    if cfg.use_recurrent_policy or getattr(cfg, "use_naive_recurrent_policy", False):
         init_rnn(p, "rnn", cfg.hidden_size, cfg.recurrent_N)
     if act_kind == "Discrete":
         _linear(p, "act.action_out.linear", cfg.hidden_size, act_dim, cfg.gain)
@@ -92,7 +92,7 @@ def init_critic(cfg, obs_dim):
     p = {}
     init_mlp_base(p, "base", obs_dim, cfg.hidden_size, cfg.layer_N, cfg.activation_id,
                   cfg.use_feature_normalization)
-    if cfg.use_recurrent_policy:
+    if cfg.use_recurrent_policy or getattr(cfg, "use_naive_recurrent_policy", False):
         init_rnn(p, "rnn", cfg.hidden_size, cfg.recurrent_N)
     if getattr(cfg, "use_popart", False):
         # v_out = init_(PopArt(H, 1)) (value_network.py:106-109): PopArt.reset_parameters draws kaiming-uniform weights
@@ -193,9 +193,14 @@ def rnn_layer(p, prefix, x, hxs, masks):
     return out, h.unsqueeze(1)
 
 
+def is_recurrent(cfg):
+    """`_use_naive_recurrent_policy or _use_recurrent_policy` (policy_network.py:88-97, value_network.py:88-97)."""
+    return bool(cfg.use_recurrent_policy or getattr(cfg, "use_naive_recurrent_policy", False))
+
+
 def policy_features(p, cfg, obs, rnn_states=None, masks=None):
     f = shared_trunk(p, cfg, obs) if is_shared(p) else mlp_base(p, "base", obs, cfg.layer_N, cfg.activation_id)
-    if cfg.use_recurrent_policy:
+    if is_recurrent(cfg):
         f, rnn_states = rnn_layer(p, "rnn", f, rnn_states, masks)
     return f, rnn_states
 
@@ -285,6 +290,6 @@ def policy_eval_gaussian(p, cfg, obs, actions, active_masks=None):
 def critic_forward(p, cfg, obs, rnn_states=None, masks=None):
     """ValueNetwork.forward (value_network.py:113-136); PolicyValueNetwork.get_values for a shared model."""
     f = shared_trunk(p, cfg, obs) if is_shared(p) else mlp_base(p, "base", obs, cfg.layer_N, cfg.activation_id)
-    if cfg.use_recurrent_policy:
+    if is_recurrent(cfg):
         f, rnn_states = rnn_layer(p, "rnn", f, rnn_states, masks)
     return F.linear(f, p["v_out.weight"], p["v_out.bias"]), rnn_states

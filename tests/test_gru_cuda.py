@@ -91,6 +91,13 @@ def test_recurrent_mappo_matches_reference_trace(cuda):
     check_recurrent_trace("mpe_gru", "simple_spread")
 
 
+def test_naive_recurrent_mpe_matches_reference_trace(cuda):
+    """cfg.use_naive_recurrent_policy (whole-trajectory BPTT, naive_recurrent_generator replay_data.py:806-946: minibatches of
+    (env, agent) rows, initial hidden state of slot 0) == the chunked path with chunk length = episode_length; the reference's
+    simple_spread trace with two minibatches per epoch."""
+    check_recurrent_trace("mpe_naive_gru", "simple_spread")
+
+
 @pytest.mark.parametrize("env_id,chunk,mini", [("CartPole-v1", 4, 2), ("GridWorldEnv", 1, 1), ("simple_spread", 3, 4)])
 def test_recurrent_training_runs_and_acts(cuda, env_id, chunk, mini):
     """Fast mode (device Philox), ragged minibatches (chunks that do not divide the buffer, several minibatches):
@@ -199,6 +206,12 @@ def test_recurrent_limits_are_loud(cuda):
     agent = PPOAgent(PPONet(make("CartPole-v1", env_num=2), cfg=cfg, device="cuda:0"))
     with pytest.raises(NotImplementedError):
         agent.train(total_time_steps=400)
+    # whole-trajectory BPTT is the chunked path with chunk = episode_length: the default episode_length (200) is beyond the 32-step limit
     cfg2 = create_config_parser().parse_args(["--use_naive_recurrent_policy", "true"])
+    cfg2.quiet = True
+    agent2 = PPOAgent(PPONet(make("CartPole-v1", env_num=2), cfg=cfg2, device="cuda:0"))
     with pytest.raises(NotImplementedError):
-        PPONet(make("CartPole-v1", env_num=2), cfg=cfg2, device="cuda:0")
+        agent2.train(total_time_steps=400)
+    cfg3 = create_config_parser().parse_args(["--use_recurrent_policy", "true", "--rnn_type", "lstm"])
+    with pytest.raises(NotImplementedError):
+        PPONet(make("CartPole-v1", env_num=2), cfg=cfg3, device="cuda:0")

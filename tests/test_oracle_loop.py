@@ -48,7 +48,8 @@ def test_oracle_reproduces_reference_trace(tag, env_id):
         np.testing.assert_allclose(tr.vn.state(), d[f"it{it}/vn_after_update"], rtol=1e-6)
 
 
-@pytest.mark.parametrize("tag,env_id", [("mpe_mlp", "simple_spread"), ("mpe_gru", "simple_spread"), ("cartpole_gru", "CartPole-v1")])
+@pytest.mark.parametrize("tag,env_id", [("mpe_mlp", "simple_spread"), ("mpe_gru", "simple_spread"), ("cartpole_gru", "CartPole-v1"),
+                                        ("mpe_naive_gru", "simple_spread")])
 def test_multi_agent_oracle_reproduces_reference_trace(tag, env_id):
     """MAPPO on simple_spread (3 agents, shared nets; feed-forward and GRU + chunked BPTT with
     data_chunk_length 2) and single-agent recurrent PPO on CartPole-v1 (episodes ending inside chunks of 4,
@@ -69,7 +70,7 @@ def test_multi_agent_oracle_reproduces_reference_trace(tag, env_id):
         assert np.array_equal(b.policy_obs, d[f"it{it}/policy_obs"])
         assert np.array_equal(b.rewards, d[f"it{it}/rewards"])
         assert np.array_equal(b.masks, d[f"it{it}/masks"])
-        if cfg.use_recurrent_policy:
+        if cfg.use_recurrent_policy or cfg.use_naive_recurrent_policy:
             np.testing.assert_allclose(b.rnn_states, d[f"it{it}/rnn_states"], rtol=0, atol=1e-5)
             np.testing.assert_allclose(b.rnn_states_critic, d[f"it{it}/rnn_states_critic"], rtol=0, atol=1e-5)
         tr.compute_returns()

@@ -129,4 +129,5 @@ def test_selfplay_training_runs_and_snapshots(cuda):
     obs, _ = env.reset(seed=3)
     o2, r, d, info = env.step(np.zeros((N, 1, 1)))
     assert o2.shape == (N, 1, 4) and r.shape == (N, 1, 1) and d.shape == (N, 1)
-    assert (o2[:, 0, :2] == obs[:, 0, :2]).all()                      # action 0 = stay: the learner did not move
+    keep = ~d[:, 0]                                                    # envs whose episode did not end in this step
+    assert keep.any() and (o2[keep, 0, :2] == obs[keep, 0, :2]).all()  # action 0 = stay: the learner did not move
