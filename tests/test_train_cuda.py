@@ -305,3 +305,45 @@ def test_share_model_matches_reference_trace(cuda):
     a1, _ = agent.act(obs, deterministic=True)
     assert a1.shape == (N, 1, 1)
     assert net.module.get_values(obs.reshape(N, -1)).shape == (N, 1)
+
+
+def test_parity_mode_at_4096_envs_matches_oracle(cuda):
+    """Parity mode at the BASELINE configs[1] env count (4096 envs, short T): two full iterations through the public API vs
+    the oracle loop on the same seeds — bit-exact actions / observations over all 4096 envs, the six scalars at 1e-4.
+    (32 tiles per net in the tensor-core update, 32 CTAs in the tensor-core rollout: the multi-tile / multi-CTA paths the
+    8-env reference traces cannot reach.)"""
+    from openrl_b200.utils.logger import Logger
+    from oracle import loop as oloop
+    from test_rollout_cuda import _product
+
+    N, T, iters = 4096, 8, 2
+    flags = ["--seed", "0", "--episode_length", str(T), "--ppo_epoch", "2", "--num_mini_batch", "2"]
+    cfg, env, net, agent = _product("CartPole-v1", N, flags)
+    tr = oloop.Trainer(oloop.cfg_from_flags(" ".join(flags)), "CartPole-v1", N)
+    # same initial weights (the oracle consumes the generator like the reference; pin them anyway)
+    import torch
+
+    for mk, prm in (("policy", tr.pol), ("critic", tr.cri)):
+        sd = net.module.models[mk].state_dict()
+        for k, v in prm.items():
+            sd[k].copy_(v.detach())
+    rng_state = torch.get_rng_state()       # both sides draw noise / permutations from the global CPU generator, from here on
+    logger = Logger(quiet=True)
+    agent.train(total_time_steps=T * N * iters, logger=logger)
+    logs = [h[1] for h in logger.history if "value_loss" in h[1]]
+    assert agent.driver.trainer.use_tensor_cores and len(logs) == iters
+    names = ["value_loss", "critic_grad_norm", "policy_loss", "dist_entropy", "actor_grad_norm", "ratio"]
+    torch.set_rng_state(rng_state)
+    for it in range(iters):
+        tr.rollout()
+        tr.compute_returns()
+        if it == iters - 1:
+            b = agent.driver.buffer.data
+            assert np.array_equal(b.actions.cpu().numpy(), tr.buf.actions)
+            assert np.array_equal(b.policy_obs.cpu().numpy()[1:], tr.buf.obs[1:])
+            np.testing.assert_allclose(b.returns.cpu().numpy()[:-1], tr.buf.returns[:-1], rtol=1e-5, atol=1e-5)
+        updates, _ = tr.train()
+        tr.after_update()
+        want = updates.mean(axis=0)
+        for col, name in enumerate(names):
+            np.testing.assert_allclose(logs[it][name], want[col], rtol=1e-4, atol=2e-6, err_msg=f"it{it} {name}")
