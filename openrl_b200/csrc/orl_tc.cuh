@@ -1,22 +1,8 @@
-// Hand-written tcgen05 (5th-gen tensor core) primitives for sm_100a, TF32 operands / FP32
-// accumulate in TMEM: shared-memory matrix descriptors (K-major and MN-major), instruction
-// descriptor, TMEM allocation, MMA issue, commit -> mbarrier, TMEM -> register loads.
-// Bit layouts follow the PTX ISA tcgen05 matrix / instruction descriptors (cross-checked against the
-// CUTLASS headers cute/arch/mma_sm100_desc.hpp vendored in this image; no CUTLASS code is used).
-//
-// Shared-memory operand tile ("panel tile", the canonical no-swizzle / INTERLEAVE layout): a matrix
-// of R rows x C float columns (R % 8 == 0, C % 4 == 0) is stored as C/4 column panels; panel p holds
-// columns [4p, 4p+4) of every row as R consecutive 16-byte units.  Element (row, col) lives at byte
-//        (col/4) * R*16 + row*16 + (col%4)*4.
-// An 8-row x 16-byte block (128 contiguous bytes) is one "core matrix".  The SAME buffer can be
-// read by the tensor core in both majors, which the update kernel uses to avoid transposed copies:
-//   * K-major  (rows = M/N index, columns = K): LBO = R*16 (next core matrix along K),
-//     SBO = 128 (next 8-row group); the k-slice of one MMA (K = 8 floats) starts at panel k0/4.
-//   * MN-major (rows = K index, columns = M/N): SBO = R*16 (next 4 columns along M/N),
-//     LBO = 128 (next 8 rows along K); the k-slice of one MMA starts at row k0.
-// A thread that owns a row stores float4s; the 32 rows of a warp are 512 contiguous bytes per
-// panel (conflict-free).  (TF32 MN-major operands admit no 128B swizzle other than the
-// 32-byte-atomic one, so a swizzled buffer could not be shared between the two majors.)
+// Hand-written tcgen05 (5th-gen tensor core) primitives for sm_100a shared by the kernels of this library:
+// shared-memory matrix descriptors, TMEM allocation, commit -> mbarrier, mbarrier waits, TMEM -> register loads.
+// Bit layouts follow the PTX ISA tcgen05 matrix descriptors (cross-checked against the CUTLASS header
+// cute/arch/mma_sm100_desc.hpp vendored in this image; no CUTLASS code is used).  The MMA issue, instruction
+// descriptor and operand layouts of the split-fp16 GEMMs are in orl_tc16.cuh.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -26,26 +12,6 @@ namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ uint32_t panel_offset(int rows, int row, int col) {
-    return (uint32_t)((col >> 2) * rows * 16 + row * 16 + (col & 3) * 4);
-}
-// round-to-nearest TF32 (the tensor core truncates the low 13 mantissa bits of fp32 operands)
-__device__ __forceinline__ float to_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
-__device__ __forceinline__ void panel_store(float* tile, int rows, int row, int col, float v) {
-    *reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(tile) + panel_offset(rows, row, col)) = v;
-}
-// 16-byte store of columns [col, col+4), col % 4 == 0
-__device__ __forceinline__ void panel_store4(float* tile, int rows, int row, int col, float4 v) {
-    *reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(tile) + panel_offset(rows, row, col)) = v;
-}
-__device__ __forceinline__ float4 panel_load4(const float* tile, int rows, int row, int col) {
-    return *reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(tile) + panel_offset(rows, row, col));
-}
-
 __device__ __forceinline__ uint64_t desc_common(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     uint64_t d = 0;
     d |= (uint64_t)((addr >> 4) & 0x3FFF);             // start address, bits [0,14)
@@ -54,27 +20,6 @@ __device__ __forceinline__ uint64_t desc_common(uint32_t addr, uint32_t lbo_byte
     d |= (uint64_t)1 << 46;                            // descriptor version (Blackwell)
     return d;                                          // layout type bits [61,64) = 0: SWIZZLE_NONE
 }
-// K-major operand: MMA k-slice starting at float column k0 (k0 % 8 == 0); first M/N row r0 (r0 % 8 == 0)
-__device__ __forceinline__ uint64_t make_desc_kmajor(const float* tile, int rows, int k0, int r0 = 0) {
-    return desc_common(smem_u32(tile) + (uint32_t)((k0 >> 2) * rows * 16 + r0 * 16), (uint32_t)rows * 16, 128);
-}
-// MN-major operand: MMA k-slice = rows [k0, k0+8) (k0 % 8 == 0); first M/N index = column c0 (c0 % 4 == 0)
-__device__ __forceinline__ uint64_t make_desc_mnmajor(const float* tile, int rows, int k0, int c0 = 0) {
-    return desc_common(smem_u32(tile) + (uint32_t)(k0 * 16 + (c0 >> 2) * rows * 16), 128, (uint32_t)rows * 16);
-}
-// instruction descriptor, kind::tf32, FP32 accumulate
-__host__ __device__ __forceinline__ uint32_t make_idesc_tf32(int M, int N, bool a_mn_major, bool b_mn_major) {
-    uint32_t d = 0;
-    d |= 1u << 4;                        // c_format = F32
-    d |= 2u << 7;                        // a_format = TF32
-    d |= 2u << 10;                       // b_format = TF32
-    d |= (a_mn_major ? 1u : 0u) << 15;   // a_major
-    d |= (b_mn_major ? 1u : 0u) << 16;   // b_major
-    d |= (uint32_t)(N >> 3) << 17;       // n_dim
-    d |= (uint32_t)(M >> 4) << 24;       // m_dim
-    return d;
-}
-
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
@@ -107,15 +52,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "DONE:\n\t}" ::"r"(a), "r"(parity) : "memory");
 }
 
-// D[tmem] (+)= A[smem] . B[smem]; issued by ONE thread
-__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, bool accumulate) {
-    const uint32_t acc = accumulate ? 1u : 0u;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc)
-        : "memory");
-}
 // make the mbarrier track completion of all MMAs issued so far by this thread
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");

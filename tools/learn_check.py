@@ -6,8 +6,8 @@ from openrl_b200.configs.config import create_config_parser
 from openrl_b200.envs.common import make
 from openrl_b200.modules.common import PPONet
 from openrl_b200.runners.common import PPOAgent
-def run(seed, tf32, steps=20000):
-    cfg = create_config_parser().parse_args(["--seed", str(seed), "--use_tf32", str(tf32)])
+def run(seed, tc, steps=20000):
+    cfg = create_config_parser().parse_args(["--seed", str(seed), "--use_tensor_cores", str(tc)])
     cfg.quiet = True
     env = make("CartPole-v1", env_num=9)
     agent = PPOAgent(PPONet(env, cfg=cfg, device="cuda:0"))
@@ -21,5 +21,5 @@ def run(seed, tf32, steps=20000):
         totals += r[:, 0, 0] * (~fin); fin |= d[:, 0]
         if fin.all(): break
     return totals.mean()
-for tf32 in (False, True):
-    print("tf32", tf32, [round(run(s, tf32), 1) for s in range(6)], flush=True)
+for tc in (False, True):
+    print("tc", tc, [round(run(s, tc), 1) for s in range(6)], flush=True)
