@@ -364,6 +364,7 @@ def run_ours(args):
     value = env_steps / total_s
     tc_update = drv.trainer.use_tensor_cores
     graphed = getattr(drv, "_graph", None) is not None
+    peer_exchange = getattr(drv.trainer, "peer", None) is not None
     del drv
 
     print("[bench] main timed region done", file=sys.stderr, flush=True)
@@ -427,6 +428,9 @@ def run_ours(args):
                  "accumulation = fp32-class accuracy, the mode the 1e-4 parity tests run in), f64 (CartPole state)",
         "data": "synthetic: device-resident CartPole-v1, random-init nets, seed 0",
         "config": {"workload": WORKLOAD, "global_envs": N_ENVS * world, "rollout_T": T, "parallelism": f"env-shard dp{world}",
+                   "gradient_exchange": ("none (1 GPU)" if world == 1 else
+                                         "NVLink peer-memory sum fused into the optimiser kernel (orl_ppo_apply_peer)" if peer_exchange
+                                         else "all-reduce between orl_ppo_reduce and orl_ppo_apply (NCCL, or symmetric one-shot with ORL_SYMM_ALLREDUCE=1)"),
                    "l2": "256 MB L2 flush between timed iterations; inside an iteration the 25 MB buffer is re-read by design",
                    "sampling": "device Philox4x32 action sampling, whole-buffer minibatch without a permutation (chi-square / moment "
                                "tested, tests/test_sampling_cuda.py); the reference-order CPU-noise mode is extras.c2_parity_mode"},

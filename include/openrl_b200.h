@@ -293,6 +293,35 @@ int orl_net_param_count(int obs_dim, int n_out);
 int orl_ppo_fwdbwd(const OrlPpoArgs* args, void* stream);
 int orl_ppo_reduce(const OrlPpoArgs* args, void* stream);
 int orl_ppo_apply(const OrlPpoArgs* args, void* stream);
+
+/* Multi-GPU (one process per GPU): the SUM all-reduce of the gradient bucket between orl_ppo_reduce and orl_ppo_apply
+ * (the north-star's "single allreduce on the gradient bucket per update"; the reference has no distributed update) fused
+ * into the two kernels over NVLink peer memory instead of a separate collective.  Every rank owns one symmetric
+ * allocation of orl_ppo_peer_bucket_bytes() bytes, zero-filled before first use, mapped into all peers (CUDA VMM /
+ * torch symmetric memory); peer_buffers is a DEVICE array of `world` addresses of these allocations as seen from this
+ * rank (entry `rank` = local_buffer).  orl_ppo_reduce_peer PUSHES this rank's bucket into slot [parity of epochs[net]]
+ * [rank] of every rank's allocation; orl_ppo_apply_peer signals the peers, waits for their buckets (error_flag := 1 + peer
+ * rank if one does not arrive within timeout_ms; the logged losses are then NaN), sums the `world` slots of its own copy
+ * in rank order into `summed` and applies the optimiser step exactly as orl_ppo_apply does on the sum; it increments
+ * epochs[net].  All ranks must issue the same sequence of reduce_peer / apply_peer pairs. */
+#define ORL_PEER_MAX_WORLD 16
+#define ORL_PEER_SMALL_MAX 16   /* doubles per orl_peer_sum_f64 call */
+typedef struct OrlPeerArgs {
+    const uint64_t* peer_buffers; /* device (world): addresses of every rank's symmetric bucket */
+    float* local_buffer;          /* this rank's symmetric bucket */
+    uint32_t* epochs;             /* device (3): completed exchanges {policy bucket, critic bucket, orl_peer_sum_f64}; start at 0 */
+    int32_t* error_flag;          /* device (1): 0, or 1 + rank of a peer that timed out */
+    float* summed;                /* device (2, stride): receives the all-rank sum (local scratch) */
+    int32_t world, rank;
+    int32_t timeout_ms;           /* bound on the wait for a peer's bucket */
+    int32_t reserved;
+} OrlPeerArgs;
+long long orl_ppo_peer_bucket_bytes(int obs_dim, int critic_obs_dim, int n_actions, int world);
+int orl_ppo_reduce_peer(const OrlPpoArgs* args, const OrlPeerArgs* peer, void* stream);
+int orl_ppo_apply_peer(const OrlPpoArgs* args, const OrlPeerArgs* peer, void* stream);
+/* In-place SUM over all ranks of n <= ORL_PEER_SMALL_MAX doubles (the 8 rollout moments of orl_gae, all-reduced once per
+ * iteration: parallel.py step 1) through the same symmetric allocation; `stride` = orl_ppo_stride() of the bucket. */
+int orl_peer_sum_f64(const OrlPeerArgs* peer, int stride, double* data, int n, void* stream);
 /* {sum returns, sum returns^2, sum active} over a minibatch given by `indices` (see mb_stats). */
 int orl_minibatch_stats(const int64_t* indices, int64_t batch_rows, const float* returns,
                         const float* active_masks, double* mb_stats_out, void* stream);

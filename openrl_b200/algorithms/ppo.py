@@ -44,6 +44,11 @@ class PPOAlgorithm:
         self.partials = torch.zeros(2 * self.grid_per_net, self.stride, dtype=torch.float32, device=dev)
         # the gradient bucket that is all-reduced once per update (symmetric memory over NVLink when > 1 GPU)
         self.folded, self.folded_sum = parallel.symmetric_buffer((2, self.stride), torch.float32, dev)
+        # > 1 GPU, feed-forward nets: the exchange is fused into the reduce / optimiser kernels over NVLink peer memory
+        self.peer = None
+        if self.world_size > 1 and not self.recurrent and not bool(getattr(cfg, "use_share_model", False)):
+            self.peer = parallel.PeerBucket.create(self._lib.orl_ppo_peer_bucket_bytes(self.d, self.dc, self.n, self.world_size),
+                                                    self.stride, dev)
         self.grads_stride = self._lib.orl_ppo_grads_stride(self.d, self.dc, self.n)
         self.grads = torch.zeros(2, self.grads_stride, dtype=torch.float32, device=dev)
         self.train_info = torch.zeros(6, dtype=torch.float32, device=dev)
@@ -165,6 +170,12 @@ class PPOAlgorithm:
         a = self._args(buf, batch_rows, indices, row_begin)
         a.mb_stats = lib.ptr(mb_stats)
         lib.check(L.orl_ppo_fwdbwd(a, s), "orl_ppo_fwdbwd")
+        if self.peer is not None:
+            # the single gradient-bucket exchange of the update, inside the optimiser kernel (peer loads over NVLink)
+            lib.check(L.orl_ppo_reduce_peer(a, self.peer.args, s), "orl_ppo_reduce_peer")
+            lib.check(L.orl_ppo_apply_peer(a, self.peer.args, s), "orl_ppo_apply_peer")
+            self.gpu_launches += 3
+            return
         lib.check(L.orl_ppo_reduce(a, s), "orl_ppo_reduce")
         summed = parallel.allreduce_sum_into(self.folded)  # the single gradient-bucket all-reduce of the update
         a.folded = lib.ptr(summed)
@@ -260,6 +271,8 @@ class PPOAlgorithm:
         num_updates = self.ppo_epoch * self.num_mini_batch
         info = (self.train_info / num_updates).cpu().numpy()
         self.d2h_bytes += info.nbytes
+        if self.peer is not None and not (info == info).all():
+            self.peer.check()
         keys = ["value_loss", "critic_grad_norm", "policy_loss", "dist_entropy", "actor_grad_norm", "ratio"]
         return {k: float(v) for k, v in zip(keys, info)}
 
@@ -288,7 +301,12 @@ class PPOAlgorithm:
         if not getattr(buf, "stats_global", False):
             # global advantage / return moments (ppo.py:402-409 semantics); once per compute_returns — a second train() on
             # the same buffer must not sum the already-global moments again
-            parallel.allreduce_sum_(buf.gae_stats)
+            if self.peer is not None and buf.gae_stats.numel() <= 16:
+                lib.check(self._lib.orl_peer_sum_f64(self.peer.args, self.stride, lib.ptr(buf.gae_stats), buf.gae_stats.numel(),
+                                                     lib.current_stream()), "orl_peer_sum_f64")
+                self.gpu_launches += 1
+            else:
+                parallel.allreduce_sum_(buf.gae_stats)
             buf.stats_global = True
         if self.recurrent:
             return self._train_recurrent(buf)

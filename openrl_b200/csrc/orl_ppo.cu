@@ -381,8 +381,119 @@ __global__ void ppo_reduce_kernel(const float* __restrict__ partials, float* __r
     folded[(size_t)net * stride + i] = s;
 }
 
-// one CTA per net: unfold, norm, clip, Adam (torch.optim.Adam single-tensor formulas)
-__global__ void __launch_bounds__(1024) ppo_apply_kernel(const OrlPpoArgs a) {
+// ---- gradient-bucket exchange over NVLink peer memory, fused into the reduce and optimiser kernels -------------------
+// Every rank owns a symmetric allocation mapped into all peers: floats [parity 2][source rank W][net 2][stride], then
+// uint32 arrival flags [3][ORL_PEER_MAX_WORLD], then doubles [parity 2][ORL_PEER_SMALL_MAX] (orl_peer_sum_f64).
+// Update number e of a net (1-based) uses half (e-1)&1.  PUSH: ppo_reduce_peer_kernel (76 CTAs) stores this rank's
+// bucket straight into slot [half][my rank] of EVERY rank's allocation - posted NVLink writes, no round trip.  The apply
+// CTA of that net then (a) publishes "my bucket for update e has been written everywhere" into every peer's flag word
+// [net][my rank] (fence.sys + st.release.sys; the pushes are ordered before it by the kernel boundary), (b) waits until
+// all W flag words of its own copy show >= e (ld.acquire.sys), (c) sums the W slots of its OWN copy in rank order - local
+// reads, the same order on every rank, so all ranks hold bit-identical sums - and continues as the single-GPU optimiser.
+// Two halves suffice: a rank pushes into half h again in update e+2, after its apply of e+1 saw every peer's flag e+1,
+// and a peer raises flag e+1 only after its apply of e (the last reader of its half h) has retired.
+__global__ void ppo_reduce_peer_kernel(const float* __restrict__ partials, const OrlPeerArgs pa, int G, int stride) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int net = blockIdx.y;
+    if (i >= stride) return;
+    const float* p = partials + (size_t)net * G * stride + i;
+    float s = 0.f;
+    for (int g = 0; g < G; ++g) s += p[(size_t)g * stride];
+    const size_t off = ((size_t)(pa.epochs[net] & 1u) * pa.world + pa.rank) * 2u * stride + (size_t)net * stride + i;
+    for (int q = 0; q < pa.world; ++q) reinterpret_cast<float*>(pa.peer_buffers[q])[off] = s;
+}
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 ld_peer4(const float* p) {
+    float4 v;
+    asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint64_t global_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+__host__ __device__ __forceinline__ size_t peer_flag_word(int world, int stride) { return (size_t)4 * world * stride; }
+
+// signal every peer's flag word [slot][my rank] with `e`, then wait until all W words of my own copy show >= e
+__device__ __forceinline__ void peer_handshake(const OrlPeerArgs& pa, int slot, uint32_t e, size_t flag_word) {
+    const int tid = threadIdx.x, W = pa.world;
+    if (tid < W) {
+        __threadfence_system();
+        uint32_t* remote = reinterpret_cast<uint32_t*>(pa.peer_buffers[tid]) + flag_word + slot * ORL_PEER_MAX_WORLD + pa.rank;
+        st_release_sys(remote, e);
+        const uint32_t* mine = reinterpret_cast<const uint32_t*>(pa.peer_buffers[pa.rank]) + flag_word + slot * ORL_PEER_MAX_WORLD + tid;
+        const uint64_t t0 = global_ns();
+        unsigned spins = 0;
+        while ((int32_t)(ld_acquire_sys(mine) - e) < 0) {
+            if ((++spins & 1023u) == 0 && global_ns() - t0 > (uint64_t)pa.timeout_ms * 1000000ull) {
+                atomicExch(pa.error_flag, 1 + tid);   // peer `tid` never arrived: the host raises on the next read-back
+                break;
+            }
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+}
+
+__device__ const float* peer_gather(const OrlPeerArgs& pa, int net, int stride) {
+    const int tid = threadIdx.x, W = pa.world;
+    const uint32_t e = pa.epochs[net] + 1u;
+    peer_handshake(pa, net, e, peer_flag_word(W, stride));
+    // the W slots of this rank's own copy (written by the peers; L1 is bypassed: ld.relaxed.sys)
+    const float* base = pa.local_buffer + (size_t)((e - 1u) & 1u) * W * 2u * stride + (size_t)net * stride;
+    float* out = pa.summed + (size_t)net * stride;
+    for (int i = tid * 4; i < stride; i += blockDim.x * 4) {
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q0 = 0; q0 < W; q0 += 8) {
+            float4 v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if (q0 + q < W) v[q] = ld_peer4(base + (size_t)(q0 + q) * 2u * stride + i);
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if (q0 + q < W) { s.x += v[q].x; s.y += v[q].y; s.z += v[q].z; s.w += v[q].w; }
+        }
+        *reinterpret_cast<float4*>(out + i) = s;
+    }
+    __syncthreads();
+    return out;
+}
+
+// SUM of n <= ORL_PEER_SMALL_MAX doubles over all ranks, in place (the once-per-iteration rollout moments): one CTA
+__global__ void __launch_bounds__(64) peer_sum_f64_kernel(const OrlPeerArgs pa, double* __restrict__ data, int n, int stride) {
+    const int tid = threadIdx.x, W = pa.world;
+    const uint32_t e = pa.epochs[2] + 1u;
+    const size_t flag_word = peer_flag_word(W, stride);
+    const size_t small_byte = flag_word * 4 + (size_t)3 * ORL_PEER_MAX_WORLD * 4 + (size_t)((e - 1u) & 1u) * ORL_PEER_SMALL_MAX * 8;
+    double* mine = reinterpret_cast<double*>(reinterpret_cast<char*>(pa.peer_buffers[pa.rank]) + small_byte);
+    if (tid < n) mine[tid] = data[tid];
+    __syncthreads();
+    peer_handshake(pa, 2, e, flag_word);
+    if (tid < n) {
+        double s = 0.0;
+        for (int q = 0; q < W; ++q) {
+            double v;
+            asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v)
+                         : "l"(reinterpret_cast<const double*>(reinterpret_cast<const char*>(pa.peer_buffers[q]) + small_byte) + tid) : "memory");
+            s += v;
+        }
+        data[tid] = s;
+    }
+    if (tid == 0) pa.epochs[2] = e;
+}
+
+template <bool PEER>
+__global__ void __launch_bounds__(1024) ppo_apply_kernel(const OrlPpoArgs a, const OrlPeerArgs pa) {
     const int net = blockIdx.x;  // 0 policy, 1 critic
     const int d = net == 0 ? a.obs_dim : a.critic_obs_dim;
     const int n = net == 0 ? a.n_actions : 1;
@@ -392,11 +503,11 @@ __global__ void __launch_bounds__(1024) ppo_apply_kernel(const OrlPpoArgs a) {
     float* params = net == 0 ? a.policy_params : a.critic_params;
     float* am = net == 0 ? a.policy_adam_m : a.critic_adam_m;
     float* av = net == 0 ? a.policy_adam_v : a.critic_adam_v;
-    const float* f = a.folded + (size_t)net * stride;
     float* grads = a.grads + (size_t)net * ppo_grads_stride(a.obs_dim, a.critic_obs_dim, a.n_actions);
     __shared__ float red[32];
     __shared__ float s_norm;
     const int tid = threadIdx.x;
+    const float* f = PEER ? peer_gather(pa, net, stride) : a.folded + (size_t)net * stride;
 
     float sq = 0.f;
     for (int i = tid; i < po.total; i += blockDim.x) {
@@ -465,6 +576,11 @@ __global__ void __launch_bounds__(1024) ppo_apply_kernel(const OrlPpoArgs a) {
     }
     if (tid == 0) {
         a.adam_steps[net] = step;
+        if (PEER) {
+            pa.epochs[net] += 1u;
+            // a peer timed out: poison the logged scalars so that the host's one read-back sees it (it then reads error_flag)
+            if (*reinterpret_cast<volatile int32_t*>(pa.error_flag) != 0) a.train_info[net == 0 ? 2 : 0] = __int_as_float(0x7fc00000);
+        }
         const float* ls = f + stride - N_LOSS;
         if (net == 0) {
             a.train_info[2] += ls[0];
@@ -578,6 +694,53 @@ extern "C" int orl_ppo_reduce(const OrlPpoArgs* args, void* stream) {
     return 0;
 }
 
+static int check_peer_args(const OrlPeerArgs& pa) {
+    ORL_CHECK_ARG(pa.world >= 2 && pa.world <= ORL_PEER_MAX_WORLD && pa.rank >= 0 && pa.rank < pa.world, "peer world / rank");
+    ORL_CHECK_ARG(pa.peer_buffers && pa.local_buffer && pa.epochs && pa.error_flag && pa.summed, "null peer buffer");
+    ORL_CHECK_ARG(pa.timeout_ms > 0, "timeout_ms");
+    return 0;
+}
+
+extern "C" long long orl_ppo_peer_bucket_bytes(int obs_dim, int critic_obs_dim, int n_actions, int world) {
+    const int stride = orl_ppo_stride(obs_dim, critic_obs_dim, n_actions);
+    return (long long)peer_flag_word(world, stride) * sizeof(float) + (long long)3 * ORL_PEER_MAX_WORLD * sizeof(uint32_t) +
+           (long long)2 * ORL_PEER_SMALL_MAX * sizeof(double);
+}
+
+extern "C" int orl_peer_sum_f64(const OrlPeerArgs* peer, int stride, double* data, int n, void* stream) {
+    ORL_CHECK_ARG(peer && data && stride > 0 && stride % 4 == 0, "args");
+    if (int e = check_peer_args(*peer)) return e;
+    ORL_CHECK_ARG(n > 0 && n <= ORL_PEER_SMALL_MAX, "n must be in 1..ORL_PEER_SMALL_MAX");
+    peer_sum_f64_kernel<<<1, 64, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*peer, data, n, stride);
+    ORL_LAUNCH_CHECK("peer_sum_f64_kernel");
+    return 0;
+}
+
+extern "C" int orl_ppo_reduce_peer(const OrlPpoArgs* args, const OrlPeerArgs* peer, void* stream) {
+    ORL_CHECK_ARG(args && peer, "args");
+    const OrlPpoArgs& a = *args;
+    if (int e = check_ppo_args(a)) return e;
+    if (int e = check_peer_args(*peer)) return e;
+    const int stride = orl_ppo_stride(a.obs_dim, a.critic_obs_dim, a.n_actions);
+    dim3 grid((stride + 127) / 128, 2);
+    ppo_reduce_peer_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a.partials, *peer, a.grid_per_net, stride);
+    ORL_LAUNCH_CHECK("ppo_reduce_kernel(peer)");
+    return 0;
+}
+
+extern "C" int orl_ppo_apply_peer(const OrlPpoArgs* args, const OrlPeerArgs* peer, void* stream) {
+    ORL_CHECK_ARG(args && peer, "args");
+    const OrlPpoArgs& a = *args;
+    if (int e = check_ppo_args(a)) return e;
+    if (int e = check_peer_args(*peer)) return e;
+    ORL_CHECK_ARG(a.policy_adam_m && a.policy_adam_v && a.critic_adam_m && a.critic_adam_v && a.adam_steps && a.lrs,
+                  "null optimiser state");
+    ORL_CHECK_ARG(a.mb_stats, "mb_stats");
+    ppo_apply_kernel<true><<<2, 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a, *peer);
+    ORL_LAUNCH_CHECK("ppo_apply_kernel(peer)");
+    return 0;
+}
+
 extern "C" int orl_ppo_apply(const OrlPpoArgs* args, void* stream) {
     ORL_CHECK_ARG(args, "args");
     const OrlPpoArgs& a = *args;
@@ -585,7 +748,7 @@ extern "C" int orl_ppo_apply(const OrlPpoArgs* args, void* stream) {
     ORL_CHECK_ARG(a.policy_adam_m && a.policy_adam_v && a.critic_adam_m && a.critic_adam_v && a.adam_steps && a.lrs,
                   "null optimiser state");
     ORL_CHECK_ARG(a.mb_stats, "mb_stats");
-    ppo_apply_kernel<<<2, 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+    ppo_apply_kernel<false><<<2, 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a, OrlPeerArgs{});
     ORL_LAUNCH_CHECK("ppo_apply_kernel");
     return 0;
 }

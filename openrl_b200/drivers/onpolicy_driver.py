@@ -155,6 +155,8 @@ class OnPolicyDriver:
             vals = self._read_graph_stats()        # the only device -> host read of the iteration
             keys = ["value_loss", "critic_grad_norm", "policy_loss", "dist_entropy", "actor_grad_norm", "ratio"]
             train_infos = {k: float(v) for k, v in zip(keys, vals[:6])}
+            if getattr(self.trainer, "peer", None) is not None and not (vals[:6] == vals[:6]).all():
+                self.trainer.peer.check()
             if type(self.trainer).__name__ == "A2CAlgorithm":
                 train_infos.pop("ratio", None)
             rollout_infos = self.envs.statistics_host(vals[6:], T * N) if self.envs.use_monitor else {}

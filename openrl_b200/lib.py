@@ -71,6 +71,7 @@ def load(path=None):
     lib.orl_last_error.argtypes = []
     lib.orl_rnn_workspace_floats.restype = _c.c_int64
     lib.orl_share_workspace_floats.restype = _c.c_int64
+    lib.orl_ppo_peer_bucket_bytes.restype = _c.c_int64
     if lib.orl_abi_version() != 1:
         raise OrlLibraryError("ABI version mismatch")
     if path is None:
@@ -142,6 +143,16 @@ class OrlPpoArgs(ctypes.Structure):
     ]
 
 
+class OrlPeerArgs(ctypes.Structure):
+    """Mirror of OrlPeerArgs (include/openrl_b200.h): the gradient-bucket exchange over NVLink peer memory."""
+    _fields_ = [
+        ("peer_buffers", _P), ("local_buffer", _P), ("epochs", _P), ("error_flag", _P), ("summed", _P),
+        ("world", _c.c_int32), ("rank", _c.c_int32), ("timeout_ms", _c.c_int32), ("reserved", _c.c_int32),
+    ]
+
+
+PEER_MAX_WORLD = 16
+
 _SIGNATURES.update({
     "orl_env_reset": [_I, _I, _I, _P, _P, _P, _P, _I, _c.c_uint64, _P, _P, _P],
     "orl_rollout": [_c.POINTER(OrlRolloutArgs), _P],
@@ -165,6 +176,10 @@ _SIGNATURES.update({
     "orl_ppo_reduce": [_c.POINTER(OrlPpoArgs), _P],
     "orl_ppo_apply": [_c.POINTER(OrlPpoArgs), _P],
     "orl_minibatch_stats": [_P, _c.c_int64, _P, _P, _P, _P],
+    "orl_ppo_peer_bucket_bytes": [_I, _I, _I, _I],
+    "orl_ppo_reduce_peer": [_c.POINTER(OrlPpoArgs), _c.POINTER(OrlPeerArgs), _P],
+    "orl_ppo_apply_peer": [_c.POINTER(OrlPpoArgs), _c.POINTER(OrlPeerArgs), _P],
+    "orl_peer_sum_f64": [_c.POINTER(OrlPeerArgs), _I, _P, _I, _P],
 })
 
 

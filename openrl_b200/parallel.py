@@ -13,6 +13,8 @@ unsharded vec-env would (seed + global_index*10086, sync_venv.py:137); no exchan
 collection or GAE.  The reference has no working distributed path: this is new
 design.  The same functions run on CPU tensors with the gloo backend (tests/test_multiproc_cpu.py).
 """
+import os
+
 import torch.distributed as dist
 
 
@@ -95,6 +97,70 @@ def allreduce_sum_into(t):
         torch.ops.symm_mem.one_shot_all_reduce_out(ent[0], "sum", ent[2], ent[1])
         return ent[1]
     return allreduce_sum_(t)
+
+
+class PeerBucket:
+    """The gradient bucket of the feed-forward update as a symmetric allocation mapped into every peer over NVLink:
+    orl_ppo_reduce_peer pushes this rank's bucket into every rank's copy, orl_ppo_apply_peer signals / waits / sums the slots and applies
+    the optimiser step in the same kernel (include/openrl_b200.h, OrlPeerArgs) — no separate collective per update.
+    `create` returns None (callers then use the all-reduce path) when there is one process, when ORL_PEER_APPLY=0, or
+    when ANY rank fails to set the symmetric mapping up (the ranks agree on that with one MIN all-reduce)."""
+
+    def __init__(self, sym, handle, stride, device):
+        import torch
+
+        from . import lib
+
+        self.sym, self.handle = sym, handle        # keep the allocation and its rendezvous handle alive
+        self.epochs = torch.zeros(4, dtype=torch.int32, device=device)
+        self.error_flag = torch.zeros(1, dtype=torch.int32, device=device)
+        self.summed = torch.zeros(2, stride, dtype=torch.float32, device=device)
+        a = lib.OrlPeerArgs()
+        a.peer_buffers = int(handle.buffer_ptrs_dev)
+        a.local_buffer = sym.data_ptr()
+        a.epochs, a.error_flag, a.summed = lib.ptr(self.epochs), lib.ptr(self.error_flag), lib.ptr(self.summed)
+        a.world, a.rank = int(handle.world_size), int(handle.rank)
+        a.timeout_ms = int(os.environ.get("ORL_PEER_TIMEOUT_MS", "60000"))
+        self.args = a
+
+    def check(self):
+        """Raise if a peer's bucket did not arrive in time (called when the poisoned statistics are read back)."""
+        e = int(self.error_flag.item())
+        if e:
+            raise RuntimeError(f"openrl_b200: rank {e - 1} did not deliver its gradient bucket within "
+                               f"{self.args.timeout_ms} ms (orl_ppo_apply_peer); the ranks are out of step or one has died")
+
+    @staticmethod
+    def create(nbytes, stride, device):
+        import torch
+
+        if not is_distributed() or os.environ.get("ORL_PEER_APPLY", "1") == "0":
+            return None
+        from . import lib
+
+        ok, sym, handle, why = 1, None, None, ""
+        try:
+            if dist.get_world_size() > lib.PEER_MAX_WORLD:
+                raise RuntimeError(f"world size > {lib.PEER_MAX_WORLD}")
+            import torch.distributed._symmetric_memory as symm_mem
+
+            group = dist.group.WORLD
+            sym = symm_mem.empty((nbytes + 3) // 4, dtype=torch.float32, device=device)
+            sym.zero_()
+            handle = symm_mem.rendezvous(sym, group.group_name)
+            int(handle.buffer_ptrs_dev)
+        except Exception as e:  # noqa: BLE001
+            ok, why = 0, f"{type(e).__name__}: {e}"
+        flag = torch.tensor([ok], dtype=torch.int32, device=device)
+        torch.cuda.synchronize(device)            # the zero-fill has landed before any peer may signal into it
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            import warnings
+
+            warnings.warn("openrl_b200: NVLink peer-memory gradient exchange unavailable"
+                          + (f" ({why})" if why else " (on another rank)") + "; using the NCCL all-reduce")
+            return None
+        return PeerBucket(sym, handle, stride, device)
 
 
 def env_shard(global_envs, r=None, w=None):

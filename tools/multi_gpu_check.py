@@ -37,6 +37,8 @@ def run(rank, world, envs, offset_rank, iters, flags):
         b.after_update()
         params = torch.cat([net.module.models[m].flat_params.clone() for m in ("policy", "critic")])
         outs.append((snap, info, params))
+    run.exchange = ("NVLink peer-memory sum inside orl_ppo_apply_peer" if getattr(drv.trainer, "peer", None) is not None
+                    else "all-reduce (NCCL / symmetric-memory one-shot)") if world > 1 else "none"
     return cfg, outs
 
 
@@ -50,6 +52,7 @@ def main():
     flags = ["--seed", "0", "--episode_length", "32", "--ppo_epoch", "4", "--num_mini_batch", "1", "--log_interval", "1000000"]
     iters = 4
     cfg, sharded = run(rank, world, per, rank, iters, flags)
+    exchange = run.exchange
     # (2) lockstep: every rank's parameters equal rank 0's, exactly (same all-reduced bucket, same Adam)
     p_last = sharded[-1][2]
     ref = p_last.clone()
@@ -87,7 +90,7 @@ def main():
         report["later_iterations_params_max_abs_diff"] = [float((sharded[i][2] - single[i][2]).abs().max()) for i in range(1, iters)]
         report["lockstep_max_abs_diff_over_ranks"] = float(lock.item())
         ok &= float(lock.item()) == 0.0
-        report.update(world=world, global_envs=G, T=32, epochs=4, ok=bool(ok))
+        report.update(exchange=exchange, world=world, global_envs=G, T=32, epochs=4, ok=bool(ok))
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         with open(os.path.join(ROOT, "gpurun_out", f"multi_gpu_check_{world}.json"), "w") as f:
             json.dump(report, f, indent=1)
