@@ -5,8 +5,12 @@ exchange steps of the path:
      and counts, `orl_gae` stats) so that advantage normalisation (ppo.py:402-409), masked-mean
      denominators (ppo.py:213-217,315-317) and ValueNorm batch moments (valuenorm.py:64-65) are the
      global-batch values;
-  2. once per update: SUM all-reduce of the folded gradient bucket `folded` (2*stride floats,
-     38 KB for CartPole) between orl_ppo_reduce and orl_ppo_apply.
+  2. once per update: SUM of the folded gradient bucket `folded` (2*stride floats, 37 KB for CartPole) between the
+     reduce and the optimiser step.
+For the feed-forward update both steps run INSIDE our kernels over NVLink peer memory (`PeerBucket` below,
+orl_ppo_reduce_peer / orl_ppo_apply_peer / orl_peer_sum_f64; DESIGN.md §4.5: 1.871 ms vs 1.956 ms per iteration with NCCL
+on 8 B200s); the NCCL all-reduce is the fallback (ORL_PEER_APPLY=0 or no peer mapping) and carries the recurrent and
+shared-network buckets.
 
 Rollouts shard over envs: rank r owns global envs [r*N, (r+1)*N) and seeds them exactly as the
 unsharded vec-env would (seed + global_index*10086, sync_venv.py:137); no exchange during
@@ -47,12 +51,11 @@ def allreduce_sum_(t):
     return t
 
 
-# ---- low-latency all-reduce of the small gradient bucket over NVLink peer memory ---------------------------------
-# The bucket is 37 KB, i.e. latency-bound.  Optional path (ORL_SYMM_ALLREDUCE=1): torch's symmetric-memory one-shot
-# all-reduce (every rank reads all peers' buffers over NVLink / NVSwitch and sums locally, signal-pad barriers,
-# graph-capturable) instead of NCCL.  Measured on 2 x B200 inside the captured iteration graph: 1.862 ms vs 1.866 ms per
-# iteration — no gain once the launches are graph-replayed, so NCCL (the north-star's "single NCCL allreduce on the
-# gradient bucket per update") stays the default.  Any failure to set the symmetric path up falls back to NCCL.
+# ---- alternative for the fallback path: torch's symmetric-memory one-shot all-reduce -----------------------------------
+# ORL_SYMM_ALLREDUCE=1 (with ORL_PEER_APPLY=0): every rank reads all peers' buffers over NVLink and sums locally (signal-pad
+# barriers, graph-capturable) instead of NCCL.  Measured inside the captured iteration graph: 2 x B200 1.862 vs 1.866 ms,
+# 8 x B200 1.907 vs 1.956 ms per iteration; the fused PeerBucket path (1.871 ms) supersedes it.  Any failure to set the
+# symmetric path up falls back to NCCL.
 _SYMM = {}   # data_ptr -> (symmetric input tensor, output tensor, group name)
 
 
