@@ -91,7 +91,8 @@ def main():
     s, d = section("ppo_fwdbwd_tc_kernel — the update (dominant kernel)", os.path.join(G, "r2_tc_update.ncu-rep"),
                    "524 288 rows, whole-buffer minibatch (TMA staging), policy + critic nets, 2 CTAs/SM")
     md.append(s)
-    s, _ = section("rollout_tc_kernel — fused rollout, 128 steps", os.path.join(G, "r2_tc_rollout.ncu-rep"), "32 CTAs x 128 envs; latency-bound by design")
+    s, _ = section("rollout_cartpole_q5_kernel — fused rollout, 128 steps", os.path.join(G, "r2_tc_rollout.ncu-rep"),
+                   "32 CTAs x 128 envs x (4 forward + 2 env) threads; a chain of 128 dependent steps, latency / issue bound by design")
     md.append(s)
     s, _ = section("critic_values_tc_kernel — value pass over (T+1)*B rows", os.path.join(G, "r2_tc_critic.ncu-rep"))
     md.append(s)
