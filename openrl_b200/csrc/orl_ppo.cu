@@ -370,15 +370,37 @@ __global__ void __launch_bounds__(P_NT, 1) ppo_fwdbwd_kernel(const OrlPpoArgs a)
     else ppo_net_pass<false>(a, smem, blockIdx.x - G, G);
 }
 
-// folded[net][i] = sum over the G partial rows of that net, fixed order (deterministic)
-__global__ void ppo_reduce_kernel(const float* __restrict__ partials, float* __restrict__ folded, int G, int stride) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int net = blockIdx.y;
-    if (i >= stride) return;
-    const float* p = partials + (size_t)net * G * stride + i;
-    float s = 0.f;
-    for (int g = 0; g < G; ++g) s += p[(size_t)g * stride];
-    folded[(size_t)net * stride + i] = s;
+// Sum over the G partial rows of one net for 32 consecutive bucket elements per CTA (8 warps): warp w adds rows
+// w, w+8, ... (coalesced 128-byte loads, 8 independent loads in flight per thread), the 8 partial sums are combined in
+// warp order -> a fixed summation order (deterministic), ~2 us instead of ~12 us for the G = 148 sequential loads per thread.
+constexpr int RED_W = 8, RED_NT = 32 * RED_W;
+__device__ __forceinline__ float reduce_partials(const float* __restrict__ partials, int net, int G, int stride, int el,
+                                                 float (*part)[32]) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    float s0 = 0.f, s1 = 0.f;
+    if (el < stride) {
+        const float* p = partials + (size_t)net * G * stride + el;
+        int g = w;
+#pragma unroll 4
+        for (; g + RED_W < G; g += 2 * RED_W) { s0 += p[(size_t)g * stride]; s1 += p[(size_t)(g + RED_W) * stride]; }
+        if (g < G) s0 += p[(size_t)g * stride];
+    }
+    part[w][lane] = s0 + s1;
+    __syncthreads();
+    float t = 0.f;
+    if (w == 0) {
+#pragma unroll
+        for (int k = 0; k < RED_W; ++k) t += part[k][lane];
+    }
+    return t;   // valid in warp 0
+}
+
+// folded[net][i] = sum over the G partial rows of that net
+__global__ void __launch_bounds__(RED_NT) ppo_reduce_kernel(const float* __restrict__ partials, float* __restrict__ folded, int G, int stride) {
+    __shared__ float part[RED_W][32];
+    const int net = blockIdx.y, el = blockIdx.x * 32 + (threadIdx.x & 31);
+    const float s = reduce_partials(partials, net, G, stride, el, part);
+    if (threadIdx.x < 32 && el < stride) folded[(size_t)net * stride + el] = s;
 }
 
 // ---- gradient-bucket exchange over NVLink peer memory, fused into the reduce and optimiser kernels -------------------
@@ -392,15 +414,14 @@ __global__ void ppo_reduce_kernel(const float* __restrict__ partials, float* __r
 // reads, the same order on every rank, so all ranks hold bit-identical sums - and continues as the single-GPU optimiser.
 // Two halves suffice: a rank pushes into half h again in update e+2, after its apply of e+1 saw every peer's flag e+1,
 // and a peer raises flag e+1 only after its apply of e (the last reader of its half h) has retired.
-__global__ void ppo_reduce_peer_kernel(const float* __restrict__ partials, const OrlPeerArgs pa, int G, int stride) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int net = blockIdx.y;
-    if (i >= stride) return;
-    const float* p = partials + (size_t)net * G * stride + i;
-    float s = 0.f;
-    for (int g = 0; g < G; ++g) s += p[(size_t)g * stride];
-    const size_t off = ((size_t)(pa.epochs[net] & 1u) * pa.world + pa.rank) * 2u * stride + (size_t)net * stride + i;
-    for (int q = 0; q < pa.world; ++q) reinterpret_cast<float*>(pa.peer_buffers[q])[off] = s;
+__global__ void __launch_bounds__(RED_NT) ppo_reduce_peer_kernel(const float* __restrict__ partials, const OrlPeerArgs pa, int G, int stride) {
+    __shared__ float part[RED_W][32];
+    const int net = blockIdx.y, el = blockIdx.x * 32 + (threadIdx.x & 31);
+    const float s = reduce_partials(partials, net, G, stride, el, part);
+    if (threadIdx.x < 32 && el < stride) {
+        const size_t off = ((size_t)(pa.epochs[net] & 1u) * pa.world + pa.rank) * 2u * stride + (size_t)net * stride + el;
+        for (int q = 0; q < pa.world; ++q) reinterpret_cast<float*>(pa.peer_buffers[q])[off] = s;
+    }
 }
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
@@ -558,12 +579,15 @@ __global__ void __launch_bounds__(1024) ppo_apply_kernel(const OrlPpoArgs a, con
     if (a.flags & ORL_PPO_MAX_GRAD_NORM) clip = fminf(a.max_grad_norm / (norm + 1e-6f), 1.0f);
 
     const int step = a.adam_steps[net] + 1;
-    const double bc1 = 1.0 - pow((double)a.adam_beta1, (double)step);
-    const double bc2 = 1.0 - pow((double)a.adam_beta2, (double)step);
-    const float lr = a.lrs[net];
-    const float step_size = (float)((double)lr / bc1);
-    const float bc2_sqrt = (float)sqrt(bc2);
-    __syncthreads();  // every thread has read the parameters it needs for unfolding
+    __shared__ float s_adam[2];
+    if (tid == (int)blockDim.x - 1) {   // the two double-precision pow() once per CTA (f64 is slow here), not once per thread
+        const double bc1 = 1.0 - pow((double)a.adam_beta1, (double)step);
+        const double bc2 = 1.0 - pow((double)a.adam_beta2, (double)step);
+        s_adam[0] = (float)((double)a.lrs[net] / bc1);
+        s_adam[1] = (float)sqrt(bc2);
+    }
+    __syncthreads();  // every thread has read the parameters it needs for unfolding; the step constants are in place
+    const float step_size = s_adam[0], bc2_sqrt = s_adam[1];
     for (int i = tid; i < po.total; i += blockDim.x) {
         float g = grads[i] * clip;
         float pv = params[i];
@@ -688,8 +712,8 @@ extern "C" int orl_ppo_reduce(const OrlPpoArgs* args, void* stream) {
     const OrlPpoArgs& a = *args;
     if (int e = check_ppo_args(a)) return e;
     const int stride = orl_ppo_stride(a.obs_dim, a.critic_obs_dim, a.n_actions);
-    dim3 grid((stride + 127) / 128, 2);
-    ppo_reduce_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a.partials, a.folded, a.grid_per_net, stride);
+    dim3 grid((stride + 31) / 32, 2);
+    ppo_reduce_kernel<<<grid, RED_NT, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a.partials, a.folded, a.grid_per_net, stride);
     ORL_LAUNCH_CHECK("ppo_reduce_kernel");
     return 0;
 }
@@ -722,8 +746,8 @@ extern "C" int orl_ppo_reduce_peer(const OrlPpoArgs* args, const OrlPeerArgs* pe
     if (int e = check_ppo_args(a)) return e;
     if (int e = check_peer_args(*peer)) return e;
     const int stride = orl_ppo_stride(a.obs_dim, a.critic_obs_dim, a.n_actions);
-    dim3 grid((stride + 127) / 128, 2);
-    ppo_reduce_peer_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a.partials, *peer, a.grid_per_net, stride);
+    dim3 grid((stride + 31) / 32, 2);
+    ppo_reduce_peer_kernel<<<grid, RED_NT, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a.partials, *peer, a.grid_per_net, stride);
     ORL_LAUNCH_CHECK("ppo_reduce_kernel(peer)");
     return 0;
 }
