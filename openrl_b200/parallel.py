@@ -155,7 +155,8 @@ class PeerBucket:
         except Exception as e:  # noqa: BLE001
             ok, why = 0, f"{type(e).__name__}: {e}"
         flag = torch.tensor([ok], dtype=torch.int32, device=device)
-        torch.cuda.synchronize(device)            # the zero-fill has landed before any peer may signal into it
+        if torch.device(device).type == "cuda":
+            torch.cuda.synchronize(device)        # the zero-fill has landed before any peer may signal into it
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if int(flag.item()) == 0:
             import warnings

@@ -149,3 +149,37 @@ def test_two_rank_recurrent_bucket_equals_global_minibatch(tmp_path):
     for r in res:
         np.testing.assert_allclose(r[2], want, rtol=1e-6, atol=1e-9)
     assert np.abs(want[:gp.size]).max() > 1e-3
+
+
+def _peer_fallback_worker(rank, world, port, q):
+    import warnings
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from openrl_b200 import parallel
+
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        # no NVLink peer mapping on a CPU / gloo group: every rank must come back with None (and say why), none may hang
+        pb = parallel.PeerBucket.create(4096, 64, torch.device("cpu"))
+        msgs = [str(x.message) for x in w]
+    os.environ["ORL_PEER_APPLY"] = "0"
+    off = parallel.PeerBucket.create(4096, 64, torch.device("cpu"))
+    q.put((rank, pb is None, off is None, any("peer-memory gradient exchange unavailable" in m for m in msgs)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_peer_bucket_falls_back_on_every_rank_when_the_mapping_is_unavailable():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_peer_fallback_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(2)], key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(r[1] and r[2] and r[3] for r in res), res
