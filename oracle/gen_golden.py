@@ -261,6 +261,8 @@ def main():
                   2, "identity_continuous")
     if a.only in ("", "flags"):
         gen_flag_variants()
+    if a.only in ("", "oracle_variants"):
+        gen_oracle_variants()
     if a.only in ("", "mpe_mlp"):
         gen_trace("simple_spread", 4,
                   ["--seed", "0", "--episode_length", "25", "--ppo_epoch", "2", "--lr", "7e-4", "--critic_lr", "7e-4",
@@ -284,6 +286,25 @@ FLAG_VARIANTS = {   # name: (canonical flags, the reference parser's spelling, a
     "no_grad_clip_wd": (["--use_max_grad_norm", "false", "--weight_decay", "0.01", "--activation_id", "0"],
                         ["--use_max_grad_norm", "--weight_decay", "0.01", "--activation_id", "0"], "ppo"),
 }
+
+
+# Further option values, pinned for the ORACLE only (tests/test_oracle_loop.py): they are the settings the device-vs-oracle
+# flag matrix (tests/test_ppo_flags_cuda.py) and the lr-schedule test use, so that chain ends at the executed reference too.
+ORACLE_VARIANTS = {
+    "lr_decay": (["--use_linear_lr_decay", "true"], 3),
+    "act_leaky_relu": (["--activation_id", "2"], 2),
+    "act_elu": (["--activation_id", "3"], 2),
+    "coefs": (["--clip_param", "0.05", "--entropy_coef", "0.05", "--value_loss_coef", "1.0", "--huber_delta", "0.5",
+               "--max_grad_norm", "0.5"], 2),
+    "lrs_wd": (["--lr", "1e-3", "--critic_lr", "2e-3", "--weight_decay", "0.01"], 2),
+    "gamma_lambda": (["--gamma", "0.9", "--gae_lambda", "0.8", "--use_adv_normalize", "true"], 2),
+}
+
+
+def gen_oracle_variants():
+    base = ["--seed", "0", "--episode_length", "24", "--ppo_epoch", "2", "--num_mini_batch", "2", "--log_interval", "1000"]
+    for name, (extra, iters) in ORACLE_VARIANTS.items():
+        gen_trace("CartPole-v1", 6, base + extra, iters, f"opt_{name}")
 
 
 def gen_flag_variants():

@@ -30,7 +30,7 @@ DEFAULTS = dict(
     max_grad_norm=10.0, use_gae=True, gamma=0.99, gae_lambda=0.95, use_proper_time_limits=False,
     use_huber_loss=True, huber_delta=10.0, use_value_active_masks=True, use_policy_active_masks=True,
     use_adv_normalize=False, use_valuenorm=True, use_popart=False, dual_clip_ppo=False, dual_clip_coeff=3.0,
-    a2c=False, use_share_model=False, use_naive_recurrent_policy=False,
+    a2c=False, use_share_model=False, use_naive_recurrent_policy=False, use_linear_lr_decay=False,
 )
 
 
@@ -110,6 +110,16 @@ class Trainer:
             b.masks[step + 1] = masks
             b.active_masks[step + 1] = active
 
+    def lr_decay(self, episode, episodes):
+        """RLDriver.learner_update (rl_driver.py:159-161) -> PPOModule.lr_decay (ppo_module.py:91-100) ->
+        update_linear_schedule (modules/utils/util.py:13-17): lr = lr0 - lr0 * episode / episodes, before the returns."""
+        cfg = self.cfg
+        opts = [(self.opt_p, cfg.lr)] if self.opt_c is self.opt_p else [(self.opt_p, cfg.lr), (self.opt_c, cfg.critic_lr)]
+        for opt, lr0 in opts:
+            lr = lr0 - (lr0 * (episode / float(episodes)))
+            for group in opt.param_groups:
+                group["lr"] = lr
+
     def compute_returns(self):
         cfg, b = self.cfg, self.buf
         with torch.no_grad():
@@ -150,8 +160,10 @@ class Trainer:
         for name in ("obs", "masks", "bad_masks", "active_masks", "action_masks"):
             getattr(b, name)[0] = getattr(b, name)[-1].copy()
 
-    def iteration(self):
+    def iteration(self, episode=0, episodes=1):
         self.rollout()
+        if self.cfg.use_linear_lr_decay:
+            self.lr_decay(episode, episodes)
         self.compute_returns()
         out = self.train()
         self.after_update()

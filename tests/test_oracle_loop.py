@@ -119,6 +119,42 @@ def test_oracle_reproduces_reference_flag_variants(tag):
             np.testing.assert_allclose(v, d[f"it{it}/params/{k}"], rtol=1e-4, atol=1e-6, err_msg=k)
 
 
+OPTION_TAGS = ["lr_decay", "act_leaky_relu", "act_elu", "coefs", "lrs_wd", "gamma_lambda"]
+
+
+@pytest.mark.parametrize("tag", OPTION_TAGS)
+def test_oracle_reproduces_reference_option_values(tag):
+    """Option VALUES beyond the branch switches (oracle/gen_golden.py ORACLE_VARIANTS): the linear lr schedule
+    (rl_driver.py:159-161, 3 iterations so the rate changes twice), LeakyReLU / ELU trunks, non-default clip / entropy /
+    value-loss / huber / grad-norm coefficients, separate lrs + weight decay, gamma / lambda with advantage
+    normalisation.  These are the settings of the device-vs-oracle flag matrix (tests/test_ppo_flags_cuda.py) and of the
+    device lr-schedule test: with the oracle pinned here, those chains end at the executed reference."""
+    d = np.load(os.path.join(GOLDEN, f"trace_opt_{tag}.npz"), allow_pickle=True)
+    cfg = loop.cfg_from_flags(str(d["meta/flags"]))
+    iters = int(d["meta/iters"])
+    tr = loop.Trainer(cfg, "CartPole-v1", int(d["meta/env_num"]))
+    for k, v in _params(tr).items():
+        assert np.array_equal(v, d[f"init/{k}"]), k
+    for it in range(iters):
+        tr.rollout()
+        b = tr.buf
+        assert np.array_equal(b.actions, d[f"it{it}/actions"])
+        assert np.array_equal(b.obs, d[f"it{it}/policy_obs"])
+        if cfg.use_linear_lr_decay:
+            tr.lr_decay(it, iters)
+        tr.compute_returns()
+        np.testing.assert_allclose(b.value_preds, d[f"it{it}/value_preds"], rtol=0, atol=1e-5)
+        np.testing.assert_allclose(b.returns[:-1], d[f"it{it}/returns"][:-1], rtol=1e-5, atol=1e-5)
+        updates, perms = tr.train()
+        assert np.array_equal(perms, d[f"it{it}/perms"])
+        np.testing.assert_allclose(updates, d[f"it{it}/updates"], rtol=1e-4, atol=1e-6)
+        tr.after_update()
+        for k, v in _params(tr).items():
+            np.testing.assert_allclose(v, d[f"it{it}/params/{k}"], rtol=1e-4, atol=1e-6, err_msg=k)
+    if tag == "lr_decay":   # the schedule really moved the parameters: the last step is a third of the first
+        assert abs(tr.opt_p.param_groups[0]["lr"] - cfg.lr * (1 - 2 / 3)) < 1e-12
+
+
 def test_oracle_reproduces_reference_share_model_trace():
     """cfg.use_share_model: PolicyValueNetwork (obs_prep -> common -> {act, v_out}, policy_value_network.py:33-174), one
     optimiser, both losses into the same gradients, two clip_grad_norm_ over all parameters (ppo.py:120-141)."""
