@@ -26,7 +26,8 @@ def test_struct_layouts_match_header(tmp_path):
     from openrl_b200 import lib
 
     for name, cls in (("OrlRolloutArgs", lib.OrlRolloutArgs), ("OrlPpoArgs", lib.OrlPpoArgs),
-                      ("OrlRnnArgs", lib.OrlRnnArgs)):
+                      ("OrlRnnArgs", lib.OrlRnnArgs), ("OrlPeerArgs", lib.OrlPeerArgs),
+                      ("OrlSelfPlayArgs", lib.OrlSelfPlayArgs)):
         fields = [f[0] for f in cls._fields_]
         c = _c_layout(name, fields, tmp_path)
         assert c["sizeof"] == ctypes.sizeof(cls), name
@@ -47,6 +48,7 @@ def test_header_flag_values_match_python():
              "ORL_PPO_VALUE_ACTIVE_MASKS": lib.PPO_VALUE_ACTIVE_MASKS, "ORL_PPO_POLICY_ACTIVE_MASKS": lib.PPO_POLICY_ACTIVE_MASKS,
              "ORL_PPO_VALUENORM": lib.PPO_VALUENORM, "ORL_PPO_ADV_NORMALIZE": lib.PPO_ADV_NORMALIZE,
              "ORL_PPO_MAX_GRAD_NORM": lib.PPO_MAX_GRAD_NORM, "ORL_PPO_TENSORCORE": lib.PPO_TENSORCORE, "ORL_PPO_A2C": lib.PPO_A2C,
-             "ORL_PPO_DUAL_CLIP": lib.PPO_DUAL_CLIP}
+             "ORL_PPO_DUAL_CLIP": lib.PPO_DUAL_CLIP, "ORL_PEER_MAX_WORLD": lib.PEER_MAX_WORLD,
+             "ORL_ENV_GRIDWORLD_2P": lib.ENV_GRIDWORLD_2P, "ORL_SP_RANDOM": lib.SP_RANDOM, "ORL_SP_LAST": lib.SP_LAST}
     for k, v in pairs.items():
         assert defs[k] == v, k
